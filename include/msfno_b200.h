@@ -1,0 +1,173 @@
+/* msfno_b200.h -- C ABI of the B200-native MSFNO spectral hot path (libmsfno_b200.so).
+ *
+ * The reference (Slusny/Modulated-Spherical-Fourier-Neural-Operator) has no native code and no
+ * FFI: its hot path is a sequence of PyTorch library calls behind torch.nn.Module classes.
+ * Each entry point below replaces one such sequence; the "replaces" line gives the reference
+ * interface (paths relative to /root/reference).  The Python package
+ * modulated-spherical-fourier-neural-operator_b200/ (import name msfno_b200) mirrors the
+ * reference classes and calls these functions through ctypes with raw device pointers.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers (fp32 unless stated) owned by the caller; the library
+ *    never frees caller memory and allocates only plan-lifetime buffers (tables, twiddles);
+ *  - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it, performs
+ *    no allocation or synchronisation and is CUDA-graph capturable (plan_* calls excepted);
+ *  - return value 0 = MSFNO_OK, otherwise an MSFNO_ERR_* code; msfno_last_error() returns a
+ *    thread-local human-readable message (includes cudaGetErrorString for CUDA errors);
+ *  - complex data are interleaved (re, im) pairs; "channel index" ch = 2*c + ri.
+ *
+ * Internal coefficient layouts (B = batch, C = channels, P = packed triangular positions):
+ *  - STD : [B][C][lmax][mmax][2]      torch complex64 layout of the reference
+ *  - PM  : [B][P][2C]                 position-major (channels contiguous)
+ *  - CM  : [B][2C][P]                 channel-major  (positions contiguous)
+ *  Packed position p = poff[m] + (l - m) for l >= m; each order m owns ceil4(lmax - m) slots
+ *  (pad slots hold zeros).
+ */
+#ifndef MSFNO_B200_H
+#define MSFNO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSFNO_OK 0
+#define MSFNO_ERR_BAD_SHAPE 1   /* shape / argument rejected (mirrors the asserts of torch_harmonics) */
+#define MSFNO_ERR_UNSUPPORTED 2 /* size this build does not support (e.g. nlon with a prime factor > 5) */
+#define MSFNO_ERR_CUDA 3        /* a CUDA runtime call failed; see msfno_last_error() */
+#define MSFNO_ERR_BAD_STATE 4   /* plan used before its table was set */
+
+#define MSFNO_LAYOUT_STD 0
+#define MSFNO_LAYOUT_PM 1
+#define MSFNO_LAYOUT_CM 2
+
+/* msfno_plan_query selectors */
+#define MSFNO_Q_KPAD 0   /* padded latitude pitch of the lat<->m intermediates (multiple of 32) */
+#define MSFNO_Q_MLIM 1   /* number of azimuthal orders carrying data: min(mmax, lmax) */
+#define MSFNO_Q_NPACK 2  /* P: packed positions per (b) plane */
+#define MSFNO_Q_NTRIL 3  /* n: len(torch.tril_indices(lmax, mmax)[0]) of the reference */
+#define MSFNO_Q_LJ 4     /* padded degree extent of the re-laid tables */
+
+/* msfno_gemm precision tiers */
+#define MSFNO_PREC_FP32 0 /* CUDA-core FFMA, fp32 accumulate: the 1e-5 tier */
+#define MSFNO_PREC_TF32 1 /* tcgen05 kind::tf32 tensor-core path: the 2e-3 tier */
+
+typedef struct msfno_plan msfno_plan;
+
+const char* msfno_last_error(void);
+/* compile-time facts: "sm_100a", has_tcgen05 etc. as a static JSON string */
+const char* msfno_build_info(void);
+
+/* ---- plans ------------------------------------------------------------------------------
+ * replaces: torch_harmonics.RealSHT.__init__ / InverseRealSHT.__init__ device-side state
+ *           (call sites MSFNO/Models/sfno/sfnonet.py:537-548); the Legendre tables themselves
+ *           stay caller-owned torch buffers (`weights`, `pct`) so the reference's in-place
+ *           rescale (sfnonet.py:551-555) keeps working: call msfno_plan_set_table again
+ *           whenever the buffer is reassigned or mutated. */
+int msfno_plan_create(msfno_plan** plan, int nlat, int nlon, int lmax, int mmax);
+int msfno_plan_destroy(msfno_plan* plan);
+long msfno_plan_query(const msfno_plan* plan, int what);
+/* table: [mmax][lmax][nlat] fp32 (reference layout).  analysis != 0 -> used by sht_fwd/bwd
+ * (RealSHT.weights); analysis == 0 -> used by isht_fwd/bwd (InverseRealSHT.pct).
+ * Entries with l < m must be zero (they are by construction); otherwise MSFNO_ERR_UNSUPPORTED. */
+int msfno_plan_set_table(msfno_plan* plan, const float* table, int analysis, void* stream);
+/* host copies of the packed-position maps: poff[mmax] and n2p[ntril] (reference tril order) */
+int msfno_plan_get_maps(const msfno_plan* plan, int32_t* poff_host, int32_t* n2p_host);
+
+/* ---- a2 / a14: forward SHT and its adjoint ------------------------------------------------
+ * replaces: torch_harmonics.RealSHT.forward  (2*pi*rfft(norm="forward") + 2 einsum
+ *           '...km,mlk->...lm'), called from MSFNO/Models/sfno/layers.py:405 and :629.
+ * x [B][C][nlat][nlon] -> coef_pm (PM layout).  Optional fused prologue x*in_scale[b*C+c] +
+ * in_shift[b*C+c] (InstanceNorm folded into the transform, sfnonet.py:224/362).
+ * ws: >= msfno_sht_ws_floats() floats of scratch (the lat<->m intermediate). */
+size_t msfno_sht_ws_floats(const msfno_plan* plan, int B, int C);
+int msfno_sht_fwd(msfno_plan* plan, const float* x, const float* in_scale, const float* in_shift,
+                  float* coef_pm, float* ws, int B, int C, void* stream);
+/* adjoint: g_pm (PM) -> gx [B][C][nlat][nlon]; in_scale (optional) multiplies gx per plane. */
+int msfno_sht_bwd(msfno_plan* plan, const float* g_pm, const float* in_scale, float* gx, float* ws,
+                  int B, int C, void* stream);
+
+/* ---- a10 / a14: inverse SHT and its adjoint -----------------------------------------------
+ * replaces: torch_harmonics.InverseRealSHT.forward (2 einsum '...lm,mlk->...km' + stack +
+ *           irfft(n=nlon, norm="forward")), called from layers.py:421 and :638.
+ * coef_cm (CM layout) -> y [B][C][nlat][nlon].  Fused epilogue, all optional:
+ *   y = act( isht(coef) + skip_add ),  act = exact GELU when act_gelu != 0
+ *   stats[b*C+c] += (sum y, sum y^2) in fp64 (feeds InstanceNorm norm1, sfnonet.py:237/376)
+ * replaces additionally: `x + inner_skip(residual)` (sfnonet.py:232/371), act_layer (:235/374)
+ * and the statistics pass of nn.InstanceNorm2d. */
+int msfno_isht_fwd(msfno_plan* plan, const float* coef_cm, float* y, float* ws, int B, int C,
+                   const float* skip_add, int act_gelu, double* stats, void* stream);
+/* adjoint: gy [B][C][nlat][nlon] -> g_cm (CM layout). */
+int msfno_isht_bwd(msfno_plan* plan, const float* gy, float* g_cm, float* ws, int B, int C, void* stream);
+
+/* ---- coefficient layout changes (public boundary of RealSHT / InverseRealSHT) ------------
+ * replaces: the zeros()+slice-assign in RealSHT.forward, view_as_real/complex shuffles and the
+ * tril gather/scatter of SpectralConvS2.forward (layers.py:406-413). */
+int msfno_coef_relayout(const msfno_plan* plan, const float* src, int src_layout, float* dst,
+                        int dst_layout, int B, int C, void* stream);
+
+/* ---- a4 / a5 / a14: SpectralConvS2 per-mode channel contraction ---------------------------
+ * replaces: compl_contract_fwd_c  einsum("bin,kin->bkn") on complex64
+ *           (MSFNO/Models/sfno/contractions.py:37-41 via layers.py:411) and its autograd.
+ * w is the reference parameter layout [Co][Ci][n][2], n in torch.tril_indices order; it is
+ * streamed exactly once per call.  a_pm: PM layout (Ci channels) -> out_cm: CM layout (Co). */
+int msfno_specconv_fwd(const msfno_plan* plan, const float* a_pm, const float* w, float* out_cm,
+                       int B, int Ci, int Co, void* stream);
+/* ga[b,i,n] = sum_k conj(w[k,i,n]) g[b,k,n] :  g_cm (CM, Co) -> ga_pm (PM, Ci) */
+int msfno_specconv_bwd_x(const msfno_plan* plan, const float* g_cm, const float* w, float* ga_pm,
+                         int B, int Ci, int Co, void* stream);
+/* gw[k,i,n] = sum_b conj(a[b,i,n]) g[b,k,n] :  writes gw [Co][Ci][n][2] */
+int msfno_specconv_bwd_w(const msfno_plan* plan, const float* a_pm, const float* g_cm, float* gw,
+                         int B, int Ci, int Co, void* stream);
+
+/* ---- a6 / a7 / a8 / a14: SpectralAttentionS2 mode-shared complex MLP ----------------------
+ * replaces: SpectralAttentionS2.forward_mlp (layers.py:604-620): spectral_layers x
+ *           [compl_mul2d_fwd_c einsum("bixy,io->boxy") (contractions.py:132-137) +
+ *           ComplexReLU mode "real" (activations.py:42-46)] + the `wout` product.
+ * w[l]: [Cin_l][hidden][2] (l = 0: Cin = C, else hidden); wout: [hidden][C][2].
+ * a_pm (PM, C channels) -> out_cm (CM, C channels).
+ * ws: msfno_specattn_ws_floats() floats; after the call it holds the packed real weights and
+ * the post-activation hidden states needed by msfno_specattn_bwd (keep it alive until then). */
+size_t msfno_specattn_ws_floats(const msfno_plan* plan, int B, int C, int hidden, int nlayers);
+int msfno_specattn_fwd(const msfno_plan* plan, const float* a_pm, const float* const* w, int nlayers,
+                       const float* wout, float* out_cm, float* ws, int B, int C, int hidden,
+                       int precision, void* stream);
+/* g_cm (CM) -> ga_pm (PM); gw[l] / gwout receive the weight gradients in the parameter layout.
+ * scratch: msfno_specattn_bwd_scratch_floats() floats. */
+size_t msfno_specattn_bwd_scratch_floats(const msfno_plan* plan, int B, int C, int hidden, int nlayers);
+int msfno_specattn_bwd(const msfno_plan* plan, const float* a_pm, const float* g_cm, const float* ws,
+                       float* ga_pm, float* const* gw, float* gwout, float* scratch, int nlayers,
+                       int B, int C, int hidden, void* stream);
+
+/* ---- a11 / a14: FiLM and the InstanceNorm it follows --------------------------------------
+ * replaces: FiLM.forward (sfnonet.py:689-697): (1 + gamma*scale) * x + beta*scale with
+ *           gamma, beta [B][C] broadcast over HW (einops.repeat materialisation removed). */
+int msfno_film_affine_fwd(const float* x, const float* gamma, const float* beta, float scale, float* y,
+                          int B, int C, long HW, void* stream);
+/* gx = (1+gamma*scale)*gy; ggamma[b,c] = scale*sum(gy*x); gbeta[b,c] = scale*sum(gy). */
+int msfno_film_affine_bwd(const float* gy, const float* x, const float* gamma, float scale, float* gx,
+                          float* ggamma, float* gbeta, int B, int C, long HW, void* stream);
+/* per-plane (sum, sum of squares) in fp64: stats[plane][2] (overwritten).
+ * replaces: the reduction pass of nn.InstanceNorm2d (sfnonet.py:491-499). */
+int msfno_plane_stats(const float* x, double* stats, int planes, long HW, void* stream);
+/* Collapse InstanceNorm(eps, affine nw/nb) followed by optional FiLM(gamma, beta, scale) into one
+ * per-plane affine y = A*x + S.  gamma/beta may be NULL (no FiLM). */
+int msfno_norm_film_coeffs(const double* stats, const float* nw, const float* nb, const float* gamma,
+                           const float* beta, float scale, float eps, float* A, float* S, int B, int C,
+                           long HW, void* stream);
+/* y[plane][:] = A[plane]*x[plane][:] + S[plane] */
+int msfno_plane_affine(const float* x, const float* A, const float* S, float* y, int planes, long HW,
+                       void* stream);
+
+/* ---- generic K-major batched GEMM used by the Legendre and MLP stages ---------------------
+ * D[M][N] = A[M][K] * B[N][K]^T (row-major D, ldd), optional ReLU on even columns.
+ * Exposed for tests and for the 1x1-conv MLPs either side of the path. */
+int msfno_gemm_nt(const float* A, long lda, const float* Bm, long ldb, float* D, long ldd, int M, int N,
+                  int K, int relu_even_cols, int precision, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSFNO_B200_H */

@@ -1,0 +1,102 @@
+"""ctypes binding of libmsfno_b200.so (the C ABI declared in include/msfno_b200.h).
+
+There is NO fallback: if the shared library is missing or a symbol cannot be resolved, importing
+this module raises, and every operator of the package raises on non-CUDA tensors.
+"""
+import ctypes
+import os
+import re
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+LIB_PATH = os.path.join(_HERE, "libmsfno_b200.so")
+HEADER_PATH = os.path.join(_ROOT, "include", "msfno_b200.h")
+
+OK = 0
+LAYOUT_STD, LAYOUT_PM, LAYOUT_CM = 0, 1, 2
+Q_KPAD, Q_MLIM, Q_NPACK, Q_NTRIL, Q_LJ = 0, 1, 2, 3, 4
+PREC_FP32, PREC_TF32 = 0, 1
+
+c_void_p, c_int, c_long, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_size_t
+
+
+def build(verbose=False):
+    """Compile the CUDA sources in csrc/ for sm_100a into libmsfno_b200.so (in-tree)."""
+    script = os.path.join(_HERE, "csrc", "build.sh")
+    res = subprocess.run(["bash", script], capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode != 0:
+        raise RuntimeError("building libmsfno_b200.so failed")
+    return LIB_PATH
+
+
+def declared_symbols():
+    """Every function name declared in include/msfno_b200.h."""
+    with open(HEADER_PATH) as f:
+        src = f.read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(msfno_[a-z0-9_]+)\s*\(", src)))
+
+
+_P = c_void_p  # device / host pointers travel as integers
+_SIGS = {
+    "msfno_last_error": (ctypes.c_char_p, []),
+    "msfno_build_info": (ctypes.c_char_p, []),
+    "msfno_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int]),
+    "msfno_plan_destroy": (c_int, [_P]),
+    "msfno_plan_query": (c_long, [_P, c_int]),
+    "msfno_plan_set_table": (c_int, [_P, _P, c_int, _P]),
+    "msfno_plan_get_maps": (c_int, [_P, _P, _P]),
+    "msfno_sht_ws_floats": (c_size_t, [_P, c_int, c_int]),
+    "msfno_sht_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "msfno_sht_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
+    "msfno_isht_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, _P, _P]),
+    "msfno_isht_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
+    "msfno_coef_relayout": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, _P]),
+    "msfno_specconv_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "msfno_specconv_bwd_x": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "msfno_specconv_bwd_w": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "msfno_specattn_ws_floats": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
+    "msfno_specattn_fwd": (c_int, [_P, _P, ctypes.POINTER(c_void_p), c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "msfno_specattn_bwd_scratch_floats": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
+    "msfno_specattn_bwd": (c_int, [_P, _P, _P, _P, _P, ctypes.POINTER(c_void_p), _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "msfno_film_affine_fwd": (c_int, [_P, _P, _P, c_float, _P, c_int, c_int, c_long, _P]),
+    "msfno_film_affine_bwd": (c_int, [_P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_long, _P]),
+    "msfno_plane_stats": (c_int, [_P, _P, c_int, c_long, _P]),
+    "msfno_norm_film_coeffs": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, _P, _P, c_int, c_int, c_long, _P]),
+    "msfno_plane_affine": (c_int, [_P, _P, _P, _P, c_int, c_long, _P]),
+    "msfno_gemm_nt": (c_int, [_P, c_long, _P, c_long, _P, c_long, c_int, c_int, c_int, c_int, c_int, _P]),
+}
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "libmsfno_b200.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU or PyTorch fallback for the MSFNO hot path)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)  # AttributeError (loud) if the symbol is missing
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error():
+    return lib.msfno_last_error().decode()
+
+
+def check(rc, what=""):
+    if rc != OK:
+        raise RuntimeError("msfno_b200 %s failed (code %d): %s" % (what, rc, last_error()))
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,208 @@
+// FiLM modulation, InstanceNorm statistics and the per-plane affine that the two collapse into.
+//
+// replaces: FiLM.forward (/root/reference MSFNO/Models/sfno/sfnonet.py:689-697; two einops.repeat
+// materialisations + 3 elementwise passes), nn.InstanceNorm2d(eps=1e-6, affine=True) as configured at
+// sfnonet.py:491-499 (3 passes), and their autograd.  InstanceNorm followed by FiLM is one affine per
+// (b, c) plane: y = A*x + S, so the pair costs one read + one write of the tensor.
+#include "common.cuh"
+
+namespace msfno {
+
+__global__ void film_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float scale, float* __restrict__ y, long long HW) {
+  const int plane = blockIdx.y;
+  const float a = 1.0f + gamma[plane] * scale;
+  const float s = beta[plane] * scale;
+  const float* xp = x + (size_t)plane * HW;
+  float* yp = y + (size_t)plane * HW;
+  const bool vec = ((HW & 3) == 0) && (((reinterpret_cast<uintptr_t>(xp) | reinterpret_cast<uintptr_t>(yp)) & 15) == 0);
+  if (vec) {
+    const long long n4 = HW >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(xp) + i);
+      v.x = fmaf(a, v.x, s); v.y = fmaf(a, v.y, s); v.z = fmaf(a, v.z, s); v.w = fmaf(a, v.w, s);
+      __stcs(reinterpret_cast<float4*>(yp) + i, v);
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x)
+      yp[i] = fmaf(a, xp[i], s);
+  }
+}
+
+__global__ void plane_affine_kernel(const float* __restrict__ x, const float* __restrict__ A, const float* __restrict__ S,
+                                    float* __restrict__ y, long long HW) {
+  const int plane = blockIdx.y;
+  const float a = A[plane], s = S[plane];
+  const float* xp = x + (size_t)plane * HW;
+  float* yp = y + (size_t)plane * HW;
+  const bool vec = ((HW & 3) == 0) && (((reinterpret_cast<uintptr_t>(xp) | reinterpret_cast<uintptr_t>(yp)) & 15) == 0);
+  if (vec) {
+    const long long n4 = HW >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      float4 v = __ldcs(reinterpret_cast<const float4*>(xp) + i);
+      v.x = fmaf(a, v.x, s); v.y = fmaf(a, v.y, s); v.z = fmaf(a, v.z, s); v.w = fmaf(a, v.w, s);
+      __stcs(reinterpret_cast<float4*>(yp) + i, v);
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x)
+      yp[i] = fmaf(a, xp[i], s);
+  }
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+  if (lane == 0) sh[warp] = v;
+  __syncthreads();
+  double t = 0.0;
+  if (warp == 0) {
+    t = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;  // valid in thread 0
+}
+
+// grid: (chunks, planes); partial sums accumulated with fp64 atomics into zeroed stats
+__global__ void plane_stats_kernel(const float* __restrict__ x, double* __restrict__ stats, long long HW) {
+  __shared__ double sh[32];
+  const int plane = blockIdx.y;
+  const float* xp = x + (size_t)plane * HW;
+  float s = 0.f, q = 0.f;
+  double ds = 0.0, dq = 0.0;
+  const bool vec = ((HW & 3) == 0) && ((reinterpret_cast<uintptr_t>(xp) & 15) == 0);
+  int cnt = 0;
+  if (vec) {
+    const long long n4 = HW >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(xp) + i);
+      s += (v.x + v.y) + (v.z + v.w);
+      q += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+      if (++cnt == 64) { ds += s; dq += q; s = q = 0.f; cnt = 0; }
+    }
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < HW; i += (long long)gridDim.x * blockDim.x) {
+      const float v = xp[i];
+      s += v; q += v * v;
+      if (++cnt == 256) { ds += s; dq += q; s = q = 0.f; cnt = 0; }
+    }
+  }
+  ds += s; dq += q;
+  const double ts = block_sum(ds, sh);
+  const double tq = block_sum(dq, sh);
+  if (threadIdx.x == 0) {
+    atomicAdd(&stats[2 * plane], ts);
+    atomicAdd(&stats[2 * plane + 1], tq);
+  }
+}
+
+__global__ void norm_film_coeffs_kernel(const double* __restrict__ stats, const float* __restrict__ nw,
+                                        const float* __restrict__ nb, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float scale, float eps, float* __restrict__ A,
+                                        float* __restrict__ S, int B, int C, double inv_hw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int c = i % C;
+  const double mean = stats[2 * i] * inv_hw;
+  double var = stats[2 * i + 1] * inv_hw - mean * mean;  // biased variance, as InstanceNorm uses
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  double a = rstd * (nw ? (double)nw[c] : 1.0);
+  double s = (nb ? (double)nb[c] : 0.0) - mean * a;
+  if (gamma) {
+    const double f = 1.0 + (double)gamma[i] * (double)scale;
+    a *= f;
+    s = s * f + (double)beta[i] * (double)scale;
+  }
+  A[i] = (float)a;
+  S[i] = (float)s;
+}
+
+// one CTA per plane: gx = (1 + gamma*scale) * gy, ggamma = scale * sum(gy*x), gbeta = scale * sum(gy)
+__global__ void film_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                float scale, float* __restrict__ gx, float* __restrict__ ggamma,
+                                float* __restrict__ gbeta, long long HW) {
+  __shared__ double sh[32];
+  const int plane = blockIdx.x;
+  const float a = 1.0f + gamma[plane] * scale;
+  const float* gp = gy + (size_t)plane * HW;
+  const float* xp = x + (size_t)plane * HW;
+  float* op = gx ? gx + (size_t)plane * HW : nullptr;
+  double dg = 0.0, db = 0.0;
+  float sg = 0.f, sb = 0.f;
+  int cnt = 0;
+  for (long long i = threadIdx.x; i < HW; i += blockDim.x) {
+    const float g = gp[i];
+    sg = fmaf(g, xp[i], sg);
+    sb += g;
+    if (op) op[i] = a * g;
+    if (++cnt == 128) { dg += sg; db += sb; sg = sb = 0.f; cnt = 0; }
+  }
+  dg += sg; db += sb;
+  const double tg = block_sum(dg, sh);
+  const double tb = block_sum(db, sh);
+  if (threadIdx.x == 0) {
+    ggamma[plane] = (float)(tg * scale);
+    gbeta[plane] = (float)(tb * scale);
+  }
+}
+
+}  // namespace msfno
+
+using namespace msfno;
+
+static inline int chunks_for(long long HW, int planes) {
+  long long per = (HW / 4 + 255) / 256;               // CTAs to cover a plane once with float4 + 256 threads
+  long long want = (148LL * 8 + planes - 1) / planes;  // fill the machine ~8 CTAs per SM
+  long long c = per < want ? per : want;
+  return (int)(c < 1 ? 1 : c);
+}
+
+extern "C" {
+
+int msfno_film_affine_fwd(const float* x, const float* gamma, const float* beta, float scale, float* y, int B, int C,
+                          long HW, void* stream) {
+  if (!x || !gamma || !beta || !y || B < 1 || C < 1 || HW < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "film_fwd: bad argument");
+  dim3 grid(chunks_for(HW, B * C), B * C);
+  film_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, scale, y, HW);
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+int msfno_film_affine_bwd(const float* gy, const float* x, const float* gamma, float scale, float* gx, float* ggamma,
+                          float* gbeta, int B, int C, long HW, void* stream) {
+  if (!gy || !x || !gamma || !ggamma || !gbeta || B < 1 || C < 1 || HW < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "film_bwd: bad argument");
+  film_bwd_kernel<<<B * C, 1024, 0, (cudaStream_t)stream>>>(gy, x, gamma, scale, gx, ggamma, gbeta, HW);
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+int msfno_plane_stats(const float* x, double* stats, int planes, long HW, void* stream) {
+  if (!x || !stats || planes < 1 || HW < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "plane_stats: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  MSFNO_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)planes, st));
+  dim3 grid(chunks_for(HW, planes), planes);
+  plane_stats_kernel<<<grid, 256, 0, st>>>(x, stats, HW);
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+int msfno_norm_film_coeffs(const double* stats, const float* nw, const float* nb, const float* gamma, const float* beta,
+                           float scale, float eps, float* A, float* S, int B, int C, long HW, void* stream) {
+  if (!stats || !A || !S || B < 1 || C < 1 || HW < 1 || ((gamma == nullptr) != (beta == nullptr)))
+    return record_error(MSFNO_ERR_BAD_SHAPE, "norm_film_coeffs: bad argument");
+  norm_film_coeffs_kernel<<<(B * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, nw, nb, gamma, beta, scale, eps, A, S,
+                                                                                B, C, 1.0 / (double)HW);
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+int msfno_plane_affine(const float* x, const float* A, const float* S, float* y, int planes, long HW, void* stream) {
+  if (!x || !A || !S || !y || planes < 1 || HW < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "plane_affine: bad argument");
+  dim3 grid(chunks_for(HW, planes), planes);
+  plane_affine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, A, S, y, HW);
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+}  // extern "C"

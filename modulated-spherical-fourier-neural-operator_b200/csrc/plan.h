@@ -1,0 +1,85 @@
+// Plan: everything that depends only on the transform geometry (and the caller's Legendre table):
+// twiddles, per-order scale vectors, packed-position maps, re-laid tables, GEMM group lists.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <utility>
+#include <vector>
+
+#include "fft_core.cuh"
+
+namespace msfno {
+
+// One member of a grouped GEMM: offsets (in floats) into the three base pointers + extents.
+struct GemmGroup {
+  long long a_off, b_off, d_off;
+  int M, N, K, pad;
+};
+
+}  // namespace msfno
+
+struct msfno_plan {
+  int nlat, nlon, lmax, mmax;
+  int device;
+  int mlim;   // min(mmax, lmax): orders with at least one degree
+  int kpad;   // nlat rounded up to 32
+  int Lj;     // padded per-order degree extent (ceil4(lmax))
+  int P;      // packed positions
+  int ntril;  // reference tril count
+  msfno::FftSchedule sched;
+  std::vector<int32_t> h_poff, h_plen4, h_n2p;
+  // device buffers
+  float* d_tw = nullptr;    // [H] cf exp(-2 pi i t / H)
+  float* d_tw2 = nullptr;   // [mlim+1] cf exp(-2 pi i m / nlon)
+  float* d_scale_rfft = nullptr;      // forward kernel, RealSHT.forward: 2 pi / nlon
+  float* d_scale_irfft_adj = nullptr; // forward kernel, adjoint of irfft: c_m
+  float* d_scale_irfft = nullptr;     // inverse kernel, irfft(norm="forward"): 1
+  float* d_scale_rfft_adj = nullptr;  // inverse kernel, adjoint of 2 pi rfft(norm="forward")
+  int32_t* d_poff = nullptr;          // [mmax]
+  int32_t* d_n2p = nullptr;           // [ntril]
+  int32_t* d_p2lm = nullptr;          // [P] l * mmax + m, or -1 for pad slots
+  float* d_tab_lk = nullptr;          // analysis table  [mlim][Lj][kpad]   (contract over lat)
+  float* d_tab_kl = nullptr;          // synthesis table [mlim][nlat][Lj]   (contract over degree)
+  int32_t* d_flag = nullptr;          // table validation flag
+  // grouped-GEMM descriptors cached per (kind, B, C)
+  std::mutex mu;
+  std::map<std::pair<int, std::pair<int, int>>, msfno::GemmGroup*> groups;
+};
+
+namespace msfno {
+
+enum GroupKind { GK_ANALYSIS = 0, GK_ANALYSIS_ADJ = 1, GK_SYNTHESIS = 2, GK_SYNTHESIS_ADJ = 3 };
+// returns a device array of B*mlim groups (cached)
+int plan_groups(msfno_plan* p, int kind, int B, int C, const GemmGroup** out, int* ngroups);
+
+int launch_rfft_trunc(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
+                      const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st);
+int launch_irfft_trunc(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
+                       const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st);
+
+// Grouped fp32 GEMM on CUDA cores.  D = opA(A) * opB(B)^T, row-major D.
+//   a_kmajor: A element (m,k) at A[m*lda + k]; otherwise at A[k*lda + m]   (same for B with n)
+struct GemmLaunch {
+  const float* A; const float* B; float* D;
+  long long lda, ldb, ldd;
+  int a_kmajor, b_kmajor;
+  int relu_even;            // ReLU on even output columns (real parts of interleaved complex)
+  const float* mask;        // optional, same layout/offsets as D: zero D[m][n] (even n) where mask[m][n] <= 0 (ReLU backward)
+  long long ldmask;
+  int accumulate;           // D += result
+  const GemmGroup* groups;  // device array
+  int ngroups;
+  int maxM, maxN;           // over groups (grid sizing)
+  int use_single;           // 1: ignore `groups`; group y = `single` shifted by y * (sa, sb, sd) (strided batch)
+  GemmGroup single;
+  long long sa, sb, sd;
+};
+int launch_gemm_ffma(const GemmLaunch& g, cudaStream_t st);
+int launch_gemm_single(const float* A, long long lda, int a_kmajor, const float* B, long long ldb, int b_kmajor,
+                       float* D, long long ldd, int M, int N, int K, int relu_even, const float* mask,
+                       long long ldmask, int accumulate, cudaStream_t st);
+
+}  // namespace msfno

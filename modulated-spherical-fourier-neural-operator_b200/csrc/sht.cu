@@ -1,0 +1,76 @@
+// Forward / inverse spherical harmonic transforms and their adjoints: longitude FFT kernel + per-order
+// Legendre contraction (grouped GEMM over the azimuthal order m).
+//
+// replaces: torch_harmonics.RealSHT.forward / InverseRealSHT.forward, called
+// from /root/reference MSFNO/Models/sfno/layers.py:405,421 (SpectralConvS2) and :629,638
+// (SpectralAttentionS2), and the autograd adjoints of both (Appendix A.4).
+#include "common.cuh"
+#include "plan.h"
+
+using namespace msfno;
+
+static int legendre_gemm(msfno_plan* p, int kind, const float* A, long long lda, int a_k, const float* B, long long ldb,
+                         int b_k, float* D, long long ldd, int maxM, int maxN, int Bsz, int C, cudaStream_t st) {
+  const GemmGroup* groups = nullptr;
+  int ng = 0;
+  int rc = plan_groups(p, kind, Bsz, C, &groups, &ng);
+  if (rc) return rc;
+  GemmLaunch g{};
+  g.A = A; g.B = B; g.D = D;
+  g.lda = lda; g.ldb = ldb; g.ldd = ldd;
+  g.a_kmajor = a_k; g.b_kmajor = b_k;
+  g.groups = groups; g.ngroups = ng; g.maxM = maxM; g.maxN = maxN;
+  return launch_gemm_ffma(g, st);
+}
+
+extern "C" {
+
+size_t msfno_sht_ws_floats(const msfno_plan* p, int B, int C) {
+  if (!p) return 0;
+  return (size_t)B * p->mlim * 2 * C * p->kpad;
+}
+
+int msfno_sht_fwd(msfno_plan* p, const float* x, const float* in_scale, const float* in_shift, float* coef_pm, float* ws,
+                  int B, int C, void* stream) {
+  if (!p || !x || !coef_pm || !ws || B < 1 || C < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "sht_fwd: bad argument");
+  if (!p->d_tab_lk) return record_error(MSFNO_ERR_BAD_STATE, "sht_fwd: analysis table (RealSHT.weights) not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_rfft_trunc(p, x, ws, p->d_scale_rfft, 0, in_scale, in_shift, B, C, st);
+  if (rc) return rc;
+  // coef_pm[b][poff[m]+j][ch] = sum_k tab_lk[m][j][k] * Xt[b][m][ch][k]
+  return legendre_gemm(p, GK_ANALYSIS, p->d_tab_lk, p->kpad, 1, ws, p->kpad, 1, coef_pm, 2 * C, p->h_plen4[0], 2 * C, B, C, st);
+}
+
+int msfno_sht_bwd(msfno_plan* p, const float* g_pm, const float* in_scale, float* gx, float* ws, int B, int C, void* stream) {
+  if (!p || !g_pm || !gx || !ws || B < 1 || C < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "sht_bwd: bad argument");
+  if (!p->d_tab_lk) return record_error(MSFNO_ERR_BAD_STATE, "sht_bwd: analysis table (RealSHT.weights) not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  // gXt[b][m][ch][k] = sum_j g_pm[b][poff[m]+j][ch] * tab_lk[m][j][k]
+  int rc = legendre_gemm(p, GK_ANALYSIS_ADJ, g_pm, 2 * C, 0, p->d_tab_lk, p->kpad, 0, ws, p->kpad, 2 * C, p->nlat, B, C, st);
+  if (rc) return rc;
+  return launch_irfft_trunc(p, ws, gx, p->d_scale_rfft_adj, nullptr, in_scale, 0, nullptr, B, C, st);
+}
+
+int msfno_isht_fwd(msfno_plan* p, const float* coef_cm, float* y, float* ws, int B, int C, const float* skip_add,
+                   int act_gelu, double* stats, void* stream) {
+  if (!p || !coef_cm || !y || !ws || B < 1 || C < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "isht_fwd: bad argument");
+  if (!p->d_tab_kl) return record_error(MSFNO_ERR_BAD_STATE, "isht_fwd: synthesis table (InverseRealSHT.pct) not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  // Yt[b][m][ch][k] = sum_j coef_cm[b][ch][poff[m]+j] * tab_kl[m][k][j]
+  int rc = legendre_gemm(p, GK_SYNTHESIS, coef_cm, p->P, 1, p->d_tab_kl, p->Lj, 1, ws, p->kpad, 2 * C, p->nlat, B, C, st);
+  if (rc) return rc;
+  if (stats) MSFNO_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)B * C, st));
+  return launch_irfft_trunc(p, ws, y, p->d_scale_irfft, skip_add, nullptr, act_gelu, stats, B, C, st);
+}
+
+int msfno_isht_bwd(msfno_plan* p, const float* gy, float* g_cm, float* ws, int B, int C, void* stream) {
+  if (!p || !gy || !g_cm || !ws || B < 1 || C < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "isht_bwd: bad argument");
+  if (!p->d_tab_kl) return record_error(MSFNO_ERR_BAD_STATE, "isht_bwd: synthesis table (InverseRealSHT.pct) not set");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = launch_rfft_trunc(p, gy, ws, p->d_scale_irfft_adj, 1, nullptr, nullptr, B, C, st);
+  if (rc) return rc;
+  // g_cm[b][ch][poff[m]+j] = sum_k gYt[b][m][ch][k] * tab_kl[m][k][j]
+  return legendre_gemm(p, GK_SYNTHESIS_ADJ, ws, p->kpad, 1, p->d_tab_kl, p->Lj, 0, g_cm, p->P, 2 * C, p->h_plen4[0], B, C, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,524 @@
+"""SFNO / MSFNO network surface: drop-in replacements for the classes of
+/root/reference MSFNO/Models/sfno/sfnonet.py -- SpectralFilterLayer (:56-133),
+FourierNeuralOperatorBlock (:136-251), FourierNeuralOperatorBlock_Filmed (:254-393),
+FourierNeuralOperatorNet (:406-686), FiLM (:689-697), FourierNeuralOperatorNet_Filmed (:699-860),
+Film_wrapper (:863-912), FeedForward (:915-928).
+
+Same constructor signatures, forward signatures and state_dict keys (tests/golden/state_dict_keys.json
+is the reference's own key list).  The spectral path (InstanceNorm -> SHT -> spectral op -> ISHT ->
+inner skip -> [GELU] -> InstanceNorm -> FiLM) runs on the sm_100a kernels behind include/msfno_b200.h:
+
+  * inference (no autograd): InstanceNorm norm0 is folded into the SHT prologue, the inner-skip add,
+    GELU and the norm1 statistics into the inverse-SHT epilogue, and norm1-affine o FiLM collapse into
+    one per-(b,c) affine that is folded into the weights of the following 1x1 conv;
+  * training: every op is a torch.autograd.Function over the same kernels (adjoints of SURVEY.md
+    Appendix A.4); normalisation / residual glue stays in PyTorch so autograd can see it.
+
+The 1x1-conv MLPs (encoder, decoder, block MLP, inner skip) are the callers either side of the path
+ and still use the PyTorch library convolution.
+"""
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch.utils.checkpoint import checkpoint
+
+from . import _lib
+from ._lib import check, lib, ptr
+from .layers import MLP, DropPath, SpectralAttentionS2, SpectralConvS2, trunc_normal_
+from .sht import InverseRealSHT, RealSHT, _stream
+
+
+# ------------------------------------------------------------------------------- FiLM / norm helpers
+class _FiLMFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gammas, betas, scale):
+        B, C = x.shape[0], x.shape[1]
+        HW = x[0, 0].numel()
+        y = torch.empty_like(x)
+        check(lib.msfno_film_affine_fwd(ptr(x), ptr(gammas), ptr(betas), float(scale), ptr(y), B, C, HW, _stream()), "film_fwd")
+        ctx.save_for_backward(x, gammas)
+        ctx.scale = float(scale)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gammas = ctx.saved_tensors
+        B, C = x.shape[0], x.shape[1]
+        HW = x[0, 0].numel()
+        gy = gy.contiguous()
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gg = torch.empty_like(gammas)
+        gb = torch.empty_like(gammas)
+        check(lib.msfno_film_affine_bwd(ptr(gy), ptr(x), ptr(gammas), ctx.scale, ptr(gx), ptr(gg), ptr(gb), B, C, HW,
+                                        _stream()), "film_bwd")
+        return gx, gg, gb, None
+
+
+class FiLM(nn.Module):
+    """Feature-wise linear modulation (sfnonet.py:689-697): (1 + gamma*scale) * x + beta*scale."""
+
+    def forward(self, x, gammas, betas, scale=1):
+        if not x.is_cuda:
+            raise RuntimeError("FiLM: msfno_b200 runs on CUDA only (no CPU fallback)")
+        if torch.is_tensor(scale):
+            scale = float(scale)
+        return _FiLMFn.apply(x.contiguous().float(), gammas.contiguous().float(), betas.contiguous().float(), scale).to(x.dtype)
+
+
+def plane_stats(x):
+    """fp64 (sum, sum of squares) per (b, c) plane -> [B*C, 2]."""
+    B, C = x.shape[0], x.shape[1]
+    st = torch.empty((B * C, 2), dtype=torch.float64, device=x.device)
+    check(lib.msfno_plane_stats(ptr(x), ptr(st), B * C, x[0, 0].numel(), _stream()), "plane_stats")
+    return st
+
+
+def norm_film_coeffs(stats, norm, B, C, HW, gamma=None, beta=None, scale=1.0):
+    """Per-plane affine (A, S) equal to FiLM(InstanceNorm(x)) given the plane statistics."""
+    A = torch.empty((B, C), dtype=torch.float32, device=stats.device)
+    S = torch.empty((B, C), dtype=torch.float32, device=stats.device)
+    g = gamma.contiguous().float() if gamma is not None else None
+    b = beta.contiguous().float() if beta is not None else None
+    check(lib.msfno_norm_film_coeffs(ptr(stats), ptr(norm.weight), ptr(norm.bias), ptr(g), ptr(b), float(scale),
+                                     float(norm.eps), ptr(A), ptr(S), B, C, HW, _stream()), "norm_film_coeffs")
+    return A, S
+
+
+def plane_affine(x, A, S):
+    y = torch.empty_like(x)
+    check(lib.msfno_plane_affine(ptr(x), ptr(A), ptr(S), ptr(y), x.shape[0] * x.shape[1], x[0, 0].numel(), _stream()),
+          "plane_affine")
+    return y
+
+
+def _is_plain_instance_norm(m):
+    return isinstance(m, nn.InstanceNorm2d) and m.affine and not m.track_running_stats
+
+
+def _conv1x1_with_input_affine(conv, x, A, S):
+    """conv(A*x + S) for a 1x1 Conv2d with per-(b,c) A, S, computed as one batched matmul with the
+    affine folded into per-sample weights / bias (no extra pass over x)."""
+    B, C, H, W = x.shape
+    Wm = conv.weight.view(conv.out_channels, C)
+    Wb = Wm.unsqueeze(0) * A.unsqueeze(1)                      # [B, O, C]
+    bias = torch.matmul(Wm.unsqueeze(0), S.unsqueeze(2))       # [B, O, 1]
+    if conv.bias is not None:
+        bias = bias + conv.bias.view(1, -1, 1)
+    y = torch.baddbmm(bias, Wb, x.view(B, C, H * W))
+    return y.view(B, conv.out_channels, H, W)
+
+
+# ------------------------------------------------------------------------------- filter layer
+class SpectralFilterLayer(nn.Module):
+    """Dispatch on (filter_type, transform kind) as sfnonet.py:56-133; only the spherical transforms
+    are on the MSFNO hot path (spectral_transform="fft" is unreachable from the reference CLI)."""
+
+    def __init__(self, forward_transform, inverse_transform, embed_dim_sfno, filter_type="linear",
+                 sparsity_threshold=0.0, use_complex_kernels=True, hidden_size_factor=2, compression=None, rank=128,
+                 complex_network=True, complex_activation="real", spectral_layers=1, drop_rate=0.0):
+        super().__init__()
+        if not isinstance(forward_transform, RealSHT):
+            raise NotImplementedError("only RealSHT transforms are supported (spectral_transform='sht')")
+        if filter_type == "non-linear":
+            self.filter = SpectralAttentionS2(
+                forward_transform, inverse_transform, embed_dim_sfno, sparsity_threshold,
+                use_complex_network=complex_network, use_complex_kernels=use_complex_kernels,
+                hidden_size_factor=hidden_size_factor, complex_activation=complex_activation,
+                spectral_layers=spectral_layers, drop_rate=drop_rate, bias=False)
+        elif filter_type == "linear":
+            self.filter = SpectralConvS2(
+                forward_transform, inverse_transform, embed_dim_sfno, sparsity_threshold,
+                use_complex_kernels=use_complex_kernels, compression=compression, rank=rank, bias=False)
+        else:
+            raise NotImplementedError
+
+    def forward(self, x, **fused):
+        return self.filter(x, **fused)
+
+
+# ------------------------------------------------------------------------------- blocks
+class FourierNeuralOperatorBlock(nn.Module):
+    def __init__(self, forward_transform, inverse_transform, embed_dim_sfno, filter_type="linear", mlp_ratio=2.0,
+                 drop_rate=0.0, drop_path=0.0, act_layer=nn.GELU, norm_layer=(nn.LayerNorm, nn.LayerNorm),
+                 sparsity_threshold=0.0, use_complex_kernels=True, compression=None, rank=128, inner_skip="linear",
+                 outer_skip=None, concat_skip=False, mlp_mode="none", complex_network=True, complex_activation="real",
+                 spectral_layers=1, checkpointing_mlp=False):
+        super().__init__()
+        self._build(forward_transform, inverse_transform, embed_dim_sfno, filter_type, mlp_ratio, drop_rate, drop_path,
+                    act_layer, norm_layer, sparsity_threshold, use_complex_kernels, compression, rank, inner_skip,
+                    outer_skip, concat_skip, mlp_mode, complex_network, complex_activation, spectral_layers,
+                    checkpointing_mlp)
+
+    def _build(self, forward_transform, inverse_transform, embed_dim_sfno, filter_type, mlp_ratio, drop_rate, drop_path,
+               act_layer, norm_layer, sparsity_threshold, use_complex_kernels, compression, rank, inner_skip, outer_skip,
+               concat_skip, mlp_mode, complex_network, complex_activation, spectral_layers, checkpointing_mlp):
+        self.norm0 = norm_layer[0]()
+        self.filter_layer = SpectralFilterLayer(
+            forward_transform, inverse_transform, embed_dim_sfno, filter_type, sparsity_threshold,
+            use_complex_kernels=use_complex_kernels, hidden_size_factor=mlp_ratio, compression=compression, rank=rank,
+            complex_network=complex_network, complex_activation=complex_activation, spectral_layers=spectral_layers,
+            drop_rate=drop_rate)
+        if inner_skip == "linear":
+            self.inner_skip = nn.Conv2d(embed_dim_sfno, embed_dim_sfno, 1, 1)
+        elif inner_skip == "identity":
+            self.inner_skip = nn.Identity()
+        self.concat_skip = concat_skip
+        if concat_skip and inner_skip is not None:
+            self.inner_skip_conv = nn.Conv2d(2 * embed_dim_sfno, embed_dim_sfno, 1, bias=False)
+        if filter_type == "linear":
+            self.act_layer = act_layer()
+        self.drop_path = DropPath(drop_path) if drop_path > 0.0 else nn.Identity()
+        self.norm1 = norm_layer[1]()
+        if mlp_mode != "none":
+            self.mlp = MLP(in_features=embed_dim_sfno, hidden_features=int(embed_dim_sfno * mlp_ratio),
+                           act_layer=act_layer, drop_rate=drop_rate, checkpointing_mlp=checkpointing_mlp)
+        if outer_skip == "linear":
+            self.outer_skip = nn.Conv2d(embed_dim_sfno, embed_dim_sfno, 1, 1)
+        elif outer_skip == "identity":
+            self.outer_skip = nn.Identity()
+        if concat_skip and outer_skip is not None:
+            self.outer_skip_conv = nn.Conv2d(2 * embed_dim_sfno, embed_dim_sfno, 1, bias=False)
+
+    # -- helpers ------------------------------------------------------------------------------
+    def _can_fuse(self, x):
+        return (x.is_cuda and not torch.is_grad_enabled() and not self.concat_skip
+                and _is_plain_instance_norm(self.norm0) and _is_plain_instance_norm(self.norm1)
+                and not (hasattr(self, "act_layer") and not isinstance(self.act_layer, nn.GELU))
+                and not (hasattr(self, "act_layer") and getattr(self.act_layer, "approximate", "none") != "none"))
+
+    def _tail(self, x, residual):
+        x = self.drop_path(x)
+        if hasattr(self, "outer_skip"):
+            if self.concat_skip:
+                x = torch.cat((x, self.outer_skip(residual)), dim=1)
+                x = self.outer_skip_conv(x)
+            else:
+                x = x + self.outer_skip(residual)
+        return x
+
+    def _fused(self, x, gamma=None, beta=None, scale=1.0):
+        """Inference path with the normalisations / skip / activation / FiLM folded into the transforms."""
+        residual = x
+        x = x.contiguous().float()
+        B, C = x.shape[0], x.shape[1]
+        A0, S0 = norm_film_coeffs(plane_stats(x), self.norm0, B, C, x[0, 0].numel())
+        skip = self.inner_skip(residual) if hasattr(self, "inner_skip") else None
+        stats1 = torch.empty((B * C, 2), dtype=torch.float64, device=x.device)
+        y = self.filter_layer(x, in_scale=A0, in_shift=S0, skip_add=skip, act_gelu=hasattr(self, "act_layer"),
+                              stats=stats1)
+        A1, S1 = norm_film_coeffs(stats1, self.norm1, B, C, y[0, 0].numel(), gamma, beta, scale)
+        mlp = getattr(self, "mlp", None)
+        if mlp is not None and not mlp.checkpointing_mlp and isinstance(mlp.fwd[0], nn.Conv2d) and len(mlp.fwd) == 3:
+            h = _conv1x1_with_input_affine(mlp.fwd[0], y, A1, S1)
+            y = mlp.fwd[2](mlp.fwd[1](h))
+        else:
+            y = plane_affine(y, A1, S1)
+            if mlp is not None:
+                y = mlp(y)
+        return self._tail(y, residual)
+
+    def _unfused(self, x, gamma=None, beta=None, scale=1.0, film=None):
+        """Op-by-op path (autograd-capable), same order as sfnonet.py:221-251 / :359-393."""
+        residual = x
+        x = self.norm0(x)
+        x = self.filter_layer(x).contiguous()
+        if hasattr(self, "inner_skip"):
+            if self.concat_skip:
+                x = torch.cat((x, self.inner_skip(residual)), dim=1)
+                x = self.inner_skip_conv(x)
+            else:
+                x = x + self.inner_skip(residual)
+        if hasattr(self, "act_layer"):
+            x = self.act_layer(x)
+        x = self.norm1(x)
+        if film is not None:
+            x = film(x, gamma, beta, scale)
+        if hasattr(self, "mlp"):
+            x = self.mlp(x)
+        return self._tail(x, residual)
+
+    def forward(self, x, *overflow):
+        if self._can_fuse(x):
+            return self._fused(x)
+        return self._unfused(x)
+
+
+class FourierNeuralOperatorBlock_Filmed(FourierNeuralOperatorBlock):
+    """Block with FiLM between norm1 and the MLP (sfnonet.py:254-393); same ctor as the plain block."""
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.film = FiLM()
+
+    def global_conv(self, x, residual):
+        x = self.norm0(x)
+        x = self.filter_layer(x).contiguous()
+        if hasattr(self, "inner_skip"):
+            if self.concat_skip:
+                x = torch.cat((x, self.inner_skip(residual)), dim=1)
+                x = self.inner_skip_conv(x)
+            else:
+                x = x + self.inner_skip(residual)
+        if hasattr(self, "act_layer"):
+            x = self.act_layer(x)
+        return self.norm1(x)
+
+    def forward(self, x, gamma, beta, scale=1):
+        if torch.is_tensor(scale):
+            scale = float(scale)
+        if self._can_fuse(x) and not (gamma.requires_grad and torch.is_grad_enabled()):
+            return self._fused(x, gamma, beta, scale)
+        return self._unfused(x, gamma, beta, scale, film=self.film)
+
+
+# ------------------------------------------------------------------------------- networks
+class FourierNeuralOperatorNet(nn.Module):
+    block_cls = FourierNeuralOperatorBlock
+
+    def __init__(self, device, cfg, spectral_transform="sht", filter_type="non-linear", img_size=(721, 1440),
+                 scale_factor=6, in_chans=73, out_chans=73, embed_dim_sfno=256, num_layers=12, mlp_mode="distributed",
+                 mlp_ratio=2.0, drop_rate=0.0, drop_path_rate=0.0, num_blocks=8, sparsity_threshold=0.0,
+                 normalization_layer="instance_norm", hard_thresholding_fraction=1.0, use_complex_kernels=True,
+                 big_skip=True, compression=None, rank=128, complex_network=True, complex_activation="real",
+                 spectral_layers=3, laplace_weighting=False, checkpointing_mlp=False, checkpointing_block=False,
+                 checkpointing_encoder=False, checkpointing_decoder=False, batch_size=1, **overflow):
+        super().__init__()
+        self.cfg = cfg
+        self.device = device
+        self.spectral_transform = spectral_transform
+        self.filter_type = filter_type
+        self.img_size = img_size
+        self.scale_factor = scale_factor
+        self.in_chans = in_chans
+        self.out_chans = out_chans
+        self.embed_dim_sfno = self.num_features = embed_dim_sfno
+        self.num_layers = num_layers
+        self.num_blocks = num_blocks
+        self.hard_thresholding_fraction = hard_thresholding_fraction
+        self.normalization_layer = normalization_layer
+        self.mlp_mode = mlp_mode
+        self.big_skip = big_skip
+        self.compression = compression
+        self.rank = rank
+        self.complex_network = complex_network
+        self.complex_activation = complex_activation
+        self.spectral_layers = spectral_layers
+        self.laplace_weighting = laplace_weighting
+        self.checkpointing_mlp = checkpointing_mlp
+        self.checkpointing_block = checkpointing_block
+        self.checkpointing_encoder = checkpointing_encoder
+        self.checkpointing_decoder = checkpointing_decoder
+        self.batch_size = batch_size
+        self._block_kwargs = dict(mlp_ratio=mlp_ratio, drop_rate=drop_rate, sparsity_threshold=sparsity_threshold,
+                                  use_complex_kernels=use_complex_kernels)
+
+        self.h = self.img_size[0] // self.scale_factor
+        self.w = self.img_size[1] // self.scale_factor
+        self.pos_drop = nn.Dropout(p=drop_rate) if drop_rate > 0.0 else nn.Identity()
+        self.dpr = [x.item() for x in torch.linspace(0, drop_path_rate, self.num_layers)]
+
+        if self.normalization_layer == "layer_norm":
+            self.norm_layer0 = partial(nn.LayerNorm, normalized_shape=(self.img_size[0], self.img_size[1]), eps=1e-6)
+            self.norm_layer1 = partial(nn.LayerNorm, normalized_shape=(self.h, self.w), eps=1e-6)
+        elif self.normalization_layer == "instance_norm":
+            self.norm_layer0 = partial(nn.InstanceNorm2d, num_features=self.embed_dim_sfno, eps=1e-6, affine=True,
+                                       track_running_stats=False)
+            self.norm_layer1 = self.norm_layer0
+        else:
+            raise NotImplementedError(f"Error, normalization {self.normalization_layer} not implemented.")
+
+        self.encoder = MLP(in_features=self.in_chans, hidden_features=self.embed_dim_sfno,
+                           out_features=self.embed_dim_sfno, output_bias=False, act_layer=nn.GELU, drop_rate=0.0,
+                           checkpointing_mlp=checkpointing_mlp)
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.embed_dim_sfno, self.img_size[0], self.img_size[1]))
+
+        modes_lat = int(self.h * self.hard_thresholding_fraction)
+        modes_lon = int((self.w // 2 + 1) * self.hard_thresholding_fraction)
+        if self.spectral_transform != "sht":
+            raise NotImplementedError("only spectral_transform='sht' is on the MSFNO hot path")
+        self.trans_down = RealSHT(*self.img_size, lmax=modes_lat, mmax=modes_lon, grid="equiangular").float()
+        self.itrans_up = InverseRealSHT(*self.img_size, lmax=modes_lat, mmax=modes_lon, grid="equiangular").float()
+        self.trans = RealSHT(self.h, self.w, lmax=modes_lat, mmax=modes_lon, grid="legendre-gauss").float()
+        self.itrans = InverseRealSHT(self.h, self.w, lmax=modes_lat, mmax=modes_lon, grid="legendre-gauss").float()
+        # ad-hoc rescaling of the reference (sfnonet.py:551-555)
+        sht_rescaling_factor = 1e5
+        self.trans_down.weights = self.trans_down.weights * sht_rescaling_factor
+        self.itrans_up.pct = self.itrans_up.pct / sht_rescaling_factor
+        self.trans.weights = self.trans.weights * sht_rescaling_factor
+        self.itrans.pct = self.itrans.pct / sht_rescaling_factor
+
+        self.blocks = self._make_blocks(lambda i: self.block_cls)
+
+        self.decoder = MLP(in_features=self.embed_dim_sfno + self.big_skip * self.in_chans,
+                           hidden_features=self.embed_dim_sfno, out_features=self.out_chans, output_bias=False,
+                           act_layer=nn.GELU, drop_rate=0.0, checkpointing_mlp=checkpointing_mlp)
+        trunc_normal_(self.pos_embed, std=0.02)
+        self.apply(self._init_weights)
+
+    def _make_blocks(self, cls_for, mlp_ratio=None, drop_rate=None, sparsity_threshold=None, use_complex_kernels=None):
+        kw = dict(self._block_kwargs)
+        for k, v in dict(mlp_ratio=mlp_ratio, drop_rate=drop_rate, sparsity_threshold=sparsity_threshold,
+                         use_complex_kernels=use_complex_kernels).items():
+            if v is not None:
+                kw[k] = v
+        blocks = nn.ModuleList([])
+        for i in range(self.num_layers):
+            first_layer = i == 0
+            last_layer = i == self.num_layers - 1
+            forward_transform = self.trans_down if first_layer else self.trans
+            inverse_transform = self.itrans_up if last_layer else self.itrans
+            inner_skip = "linear" if 0 < i < self.num_layers - 1 else None
+            outer_skip = "identity" if 0 < i < self.num_layers - 1 else None
+            mlp_mode = self.mlp_mode if not last_layer else "none"
+            if first_layer:
+                norm_layer = (self.norm_layer0, self.norm_layer1)
+            elif last_layer:
+                norm_layer = (self.norm_layer1, self.norm_layer0)
+            else:
+                norm_layer = (self.norm_layer1, self.norm_layer1)
+            blocks.append(cls_for(i)(
+                forward_transform, inverse_transform, self.embed_dim_sfno, filter_type=self.filter_type,
+                mlp_ratio=kw["mlp_ratio"], drop_rate=kw["drop_rate"], drop_path=self.dpr[i], norm_layer=norm_layer,
+                sparsity_threshold=kw["sparsity_threshold"], use_complex_kernels=kw["use_complex_kernels"],
+                inner_skip=inner_skip, outer_skip=outer_skip, mlp_mode=mlp_mode, compression=self.compression,
+                rank=self.rank, complex_network=self.complex_network, complex_activation=self.complex_activation,
+                spectral_layers=self.spectral_layers, checkpointing_mlp=self.checkpointing_mlp))
+        return blocks
+
+    def _init_weights(self, m):
+        if isinstance(m, (nn.Linear, nn.Conv2d)):
+            trunc_normal_(m.weight, std=0.02)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+        elif isinstance(m, nn.LayerNorm):
+            nn.init.constant_(m.bias, 0)
+            nn.init.constant_(m.weight, 1.0)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {"pos_embed", "cls_token"}
+
+    def forward_features(self, x):
+        x = self.pos_drop(x)
+        if self.checkpointing_block:
+            for blk in self.blocks:
+                x = checkpoint(blk, x, use_reentrant=False)
+        else:
+            for blk in self.blocks:
+                x = blk(x)
+        return x
+
+    def forward(self, x):
+        if self.big_skip:
+            residual = x
+        x = self.encoder(x)
+        x = x + self.pos_embed
+        x = self.forward_features(x)
+        if self.big_skip:
+            x = torch.cat((x, residual), dim=1)
+        return self.decoder(x)
+
+
+class FeedForward(nn.Module):
+    """FiLM head (sfnonet.py:915-928)."""
+
+    def __init__(self, dim, hidden_dim, dropout=0.0, out_dim=256):
+        super().__init__()
+        self.out_features = out_dim
+        self.net = nn.Sequential(nn.LayerNorm(dim), nn.Linear(dim, hidden_dim), nn.GELU(), nn.Dropout(dropout),
+                                 nn.Linear(hidden_dim, out_dim))
+
+    def forward(self, x):
+        return self.net(x)
+
+
+class Film_wrapper(nn.Module):
+    """FiLM generator wrapper (sfnonet.py:863-912).  The generators themselves (GCN / ViT / MAE encoders)
+    are outside the hot path: the pure-PyTorch `mae` + precomputed CLS head is built
+    here; any other generator can be attached as `wrapper.film_gen = <module>`."""
+
+    def __init__(self, device, cfg):
+        super().__init__()
+        self.device = device
+        self.cfg = cfg
+        self.num_film_features = 256
+        if cfg.film_gen_type == "mae":
+            if getattr(cfg, "cls", None) is None:
+                raise NotImplementedError("film_gen_type='mae' without a precomputed CLS needs the reference's "
+                                          "ContextCast encoder; attach it as Film_wrapper.film_gen")
+            self.film_head = FeedForward(dim=cfg.embed_dim, hidden_dim=cfg.mlp_dim, dropout=cfg.dropout,
+                                         out_dim=self.num_film_features * cfg.film_layers * 2)
+            for m in self.film_head.net:
+                if type(m) == nn.Linear:
+                    stdv = 1.0 / math.sqrt(m.weight.size(1)) / cfg.scale_weight
+                    m.weight.data.uniform_(-stdv, stdv)
+                    if m.bias is not None:
+                        m.bias.data.uniform_(-stdv, stdv)
+        else:
+            raise NotImplementedError("film_gen_type=%r: build the reference generator and attach it as "
+                                      "Film_wrapper.film_gen (out of the hot-path scope)" % cfg.film_gen_type)
+
+    def get_parameters(self):
+        if self.cfg.film_gen_type == "mae":
+            return self.film_head.parameters()
+        return self.film_gen.parameters()
+
+    def forward(self, sst):
+        if self.cfg.film_gen_type == "mae":
+            x = self.film_head(sst)
+        else:
+            x = self.film_gen(sst)
+        return x.reshape(sst.shape[0], 2, self.cfg.film_layers, self.num_film_features)
+
+
+class FourierNeuralOperatorNet_Filmed(FourierNeuralOperatorNet):
+    def __init__(self, device, cfg, mlp_ratio=2.0, drop_rate=0.0, sparsity_threshold=0.0, use_complex_kernels=True,
+                 **kwargs):
+        super().__init__(device, cfg, **kwargs)
+        self.advanced_logging = kwargs["advanced_logging"]
+        self.film_layers = kwargs["film_layers"]
+        self.depth = kwargs["model_depth"]
+        # blocks are rebuilt AFTER the base-class init pass, exactly like the reference (sfnonet.py:718-781):
+        # their Conv2d layers therefore keep PyTorch's default init
+        self.blocks = self._make_blocks(
+            lambda i: FourierNeuralOperatorBlock_Filmed
+            if (self.cfg.repeat_film or i >= self.num_layers - self.film_layers) else FourierNeuralOperatorBlock,
+            mlp_ratio=mlp_ratio, drop_rate=drop_rate, sparsity_threshold=sparsity_threshold,
+            use_complex_kernels=use_complex_kernels)
+        self.film_gen = Film_wrapper(device, cfg)
+
+    def forward(self, x, sst, scale=1):
+        film_mod = self.film_gen(sst)
+        gamma, beta = film_mod[:, 0], film_mod[:, 1]
+        if self.advanced_logging:
+            self.gamma = gamma
+            self.beta = beta
+        if self.big_skip:
+            residual = x
+        with torch.no_grad():
+            if self.checkpointing_encoder:
+                x = checkpoint(self.encoder, x, use_reentrant=False)
+            else:
+                x = self.encoder(x)
+            x = x + self.pos_embed
+            x = self.pos_drop(x)
+        for i, blk in enumerate(self.blocks):
+            if self.cfg.repeat_film or i >= self.num_layers - self.film_layers:
+                film_idx = i - (self.num_layers - self.film_layers)
+                if self.checkpointing_block and torch.is_grad_enabled():
+                    x = checkpoint(blk, x, gamma[:, film_idx], beta[:, film_idx], scale, use_reentrant=False)
+                else:
+                    x = blk(x, gamma[:, film_idx], beta[:, film_idx], scale)
+            else:
+                with torch.no_grad():
+                    x = blk(x)
+        if self.big_skip:
+            x = torch.cat((x, residual), dim=1)
+        if self.checkpointing_decoder:
+            x = checkpoint(self.decoder, x, use_reentrant=False)
+        else:
+            x = self.decoder(x)
+        return x

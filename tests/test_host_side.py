@@ -1,0 +1,120 @@
+"""Host-side logic of the product package (no GPU): tables, state_dict surface, C-ABI exports,
+loud failure on CPU tensors, FFT core emulated on the CPU."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLD, ROOT
+from oracle import th_shim
+
+import msfno_b200
+from msfno_b200 import _lib
+
+
+def test_cabi_exports_every_declared_symbol():
+    names = _lib.declared_symbols()
+    assert len(names) >= 25
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
+    assert set(names) <= exported, sorted(set(names) - exported)
+    info = json.loads(_lib.lib.msfno_build_info().decode())
+    assert info["arch"] == "sm_100a"
+
+
+def test_library_is_sm100a_with_bulk_copy():
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+    assert "UBLKCP" in sass  # cp.async.bulk (TMA engine) row loads of the FFT kernel
+
+
+@pytest.mark.parametrize("grid,nlat,nlon,L,M", [("equiangular", 721, 1440, 120, 121), ("legendre-gauss", 120, 240, 120, 121),
+                                                ("equiangular", 24, 48, 12, 13), ("lobatto", 13, 24, 12, 13)])
+def test_tables_match_oracle(grid, nlat, nlon, L, M):
+    a, b = msfno_b200.RealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid), th_shim.RealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid)
+    assert a.weights.shape == b.weights.shape == (M, L, nlat)
+    assert (a.weights - b.weights).abs().max() < 1e-12 * max(1.0, float(b.weights.abs().max()))
+    a, b = msfno_b200.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid), th_shim.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid)
+    assert (a.pct - b.pct).abs().max() < 1e-12 * float(b.pct.abs().max())
+    assert a.lmax == b.lmax and a.mmax == b.mmax and "weights" not in a.state_dict() and "pct" not in a.state_dict()
+
+
+def test_default_lmax_mmax_follow_library():
+    for grid in ("equiangular", "legendre-gauss", "lobatto"):
+        a, b = msfno_b200.RealSHT(16, 32, grid=grid), th_shim.RealSHT(16, 32, grid=grid)
+        assert (a.lmax, a.mmax) == (b.lmax, b.mmax)
+    x, w = msfno_b200.quadrature.legendre_gauss_weights(721, -1, 1)  # losses.py:90 call shape
+    assert abs(w.sum() - 2) < 1e-12
+
+
+def test_state_dict_keys_match_reference():
+    ks = json.load(open(os.path.join(GOLD, "state_dict_keys.json")))
+    for ftype in ("linear", "non-linear"):
+        net = msfno_b200.FourierNeuralOperatorNet("cpu", None, filter_type=ftype, img_size=(24, 48), scale_factor=2,
+                                                  in_chans=5, out_chans=5, embed_dim_sfno=16, num_layers=4)
+        mine = {k: list(v.shape) for k, v in net.state_dict().items()}
+        assert mine == ks["net_" + ftype]
+
+    class Cfg:
+        film_gen_type, cls, embed_dim, mlp_dim, dropout, scale_weight, repeat_film, batch_size = "mae", "x", 512, 1024, 0.0, 1, False, 2
+
+    for fl in (1, 3):
+        cfg = Cfg()
+        cfg.film_layers = fl
+        net = msfno_b200.FourierNeuralOperatorNet_Filmed(
+            "cpu", cfg, mlp_ratio=0.25, advanced_logging=True, film_layers=fl, model_depth=6, filter_type="non-linear",
+            img_size=(12, 24), scale_factor=2, in_chans=4, out_chans=4, embed_dim_sfno=256, num_layers=3, spectral_layers=2)
+        mine = {k: list(v.shape) for k, v in net.state_dict().items()}
+        assert mine == ks["filmed_%d" % fl]
+
+
+def test_no_cpu_fallback():
+    sht = msfno_b200.RealSHT(12, 24, lmax=12, mmax=13, grid="legendre-gauss").float()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        sht(torch.randn(1, 2, 12, 24))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        msfno_b200.FiLM()(torch.randn(1, 2, 4, 4), torch.zeros(1, 2), torch.zeros(1, 2))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "modulated-spherical-fourier-neural-operator_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src and "th_shim" not in src, f
+
+
+def test_fft_core_host_emulation(tmp_path):
+    """csrc/fft_core.cuh (butterflies, Stockham stages, real split/merge) compiled for the host with the 32
+    lanes executed in a loop, against numpy.fft."""
+    core = os.path.join(ROOT, "modulated-spherical-fourier-neural-operator_b200", "csrc", "fft_core.cuh")
+    hdr = tmp_path / "fft_core_host.h"
+    hdr.write_text(open(core).read().replace("#include <cuda_runtime.h>", ""))
+    src = open(os.path.join(ROOT, "tests", "host_emul", "fft_emul.cpp")).read()
+    src = src.replace('#include "../../modulated-spherical-fourier-neural-operator_b200/csrc/fft_core_host.h"',
+                      '#include "%s"' % hdr)
+    cpp = tmp_path / "emul.cpp"
+    cpp.write_text(src)
+    exe = str(tmp_path / "emul")
+    subprocess.run(["g++", "-O1", "-o", exe, str(cpp)], check=True)
+
+    def run(mode, N, M, vals):
+        inp = "%d %d %d\n" % (mode, N, M) + "\n".join("%.9g %.9g" % (a, b) for a, b in vals)
+        out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
+        return np.array(out, dtype=np.float64)
+
+    rng = np.random.default_rng(0)
+    for N, M in ((1440, 120), (240, 120), (48, 12), (24, 13), (72, 9), (2880, 240)):
+        x = rng.standard_normal(N).astype(np.float32)
+        got = run(0, N, M, x.reshape(-1, 2)).reshape(-1, 2)
+        ref = np.fft.rfft(x.astype(np.float64))[:M]
+        assert np.linalg.norm(got[:, 0] + 1j * got[:, 1] - ref) / np.linalg.norm(ref) < 1e-6
+        X = (rng.standard_normal(M) + 1j * rng.standard_normal(M)).astype(np.complex64)
+        goti = run(1, N, M, np.stack([X.real, X.imag], 1))
+        refi = np.fft.irfft(X.astype(np.complex128), n=N, norm="forward")
+        assert np.linalg.norm(goti - refi) / np.linalg.norm(refi) < 1e-6
