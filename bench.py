@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- SFNO 6 h forecast steps/s at 721x1440x73 (BASELINE.json metric), one JSON line on stdout.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload sfno12_nonlinear|sfno12_linear|filter_linear] [--precision fp32|tf32]
+
+A "step" is one pass of the hot path over one batch of synthetic input: one full 12-block SFNO forward
+(FourierNeuralOperatorNet defaults: 73 variables, embed 256, scale_factor 6 -> lmax 120 / mmax 121), batch 1
+per GPU, random-init weights.  `value` times it with the input resident in HBM; `e2e` times the same call
+through the public nn.Module API with HOST (pinned) input and output buffers, copies inside the timed
+region.  N > 1: one process per GPU (torchrun), each rank forecasts its own member -- the path shards over
+independent members with no data-path collective ("scaling": "weak").
+
+`--impl reference` times the reference's CPU implementation of the same path (the oracle port of the
+reference modules + restated torch_harmonics; the reference itself is Python that cannot travel to the GPU
+box) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sfno_6h_forecast_steps_per_sec_721x1440x73"
+UNIT = "steps/s"
+IMG, NVAR, EMBED, NLAYERS, LMAX, MMAX = (721, 1440), 73, 256, 12, 120, 121
+NPOS = 7260  # |{(l, m): l >= m}| = modes carrying data
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """SM clock and throttle reasons sampled through NVML DURING the timed region (20 ms period)."""
+
+    def __init__(self, index):
+        self.index, self.rows, self.stop_flag, self.th = index, [], False, None
+
+    def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+        except Exception as e:
+            self.err = repr(e)
+            self.th = None
+
+    def _loop(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.rows.append((nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM), get_reasons(self.h)))
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def stop(self):
+        if self.th is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable: %s" % getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.th.join(timeout=1)
+        bits = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+                0x80: "hw_power_brake_slowdown"}
+        reasons = set()
+        for _, r in self.rows:
+            for b, n in bits.items():
+                if r & b:
+                    reasons.add(n)
+        sm = [c for c, _ in self.rows]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step_factory(workload):
+    """Builds the oracle (CPU restatement of the reference path) for the workload; returns (step_fn, info)."""
+    import torch
+    from oracle import sfno_oracle
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    if workload == "filter_linear":
+        raise SystemExit("--impl reference supports the sfno12_* workloads")
+    ftype = "linear" if workload == "sfno12_linear" else "non-linear"
+    tr = sfno_oracle.Transforms(IMG, 6)
+    sd = sfno_oracle.make_state_dict(filter_type=ftype, img_size=IMG, in_chans=NVAR, out_chans=NVAR, embed=EMBED,
+                                     num_layers=NLAYERS, seed=0)
+    x = torch.randn(1, NVAR, *IMG, generator=g)
+
+    def full():
+        with torch.no_grad():
+            return sfno_oracle.sfno_forward(x, sd, tr, ftype, NLAYERS)
+
+    def partial(nblocks):
+        """encoder + first nblocks blocks (bounded sample); timing is extrapolated by the caller."""
+        import torch.nn.functional as F
+        with torch.no_grad():
+            h = sfno_oracle.mlp_1x1(x, sd, "encoder.") + sd["pos_embed"]
+            for i in range(nblocks):
+                h = sfno_oracle.block_forward(h, sd, i, NLAYERS, ftype, tr)
+            return h
+
+    return full, partial, dict(cores=torch.get_num_threads(), ftype=ftype)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    full, partial, info = cpu_reference_step_factory(args.workload)
+    t0 = time.perf_counter()
+    full()
+    t_full = time.perf_counter() - t0  # always one complete forward first (also the warm-up)
+    budget = 200.0
+    total = args.steps + max(args.warmup - 1, 0)
+    if t_full * total <= budget:
+        sample, scale, fn = "1 full 12-block forward per step", 1.0, full
+    else:
+        # bounded sample: encoder + the first nb blocks; scaled to a full step by the measured ratio
+        nb = 2
+        t0 = time.perf_counter()
+        partial(nb)
+        t_part = time.perf_counter() - t0
+        scale = t_full / t_part
+        sample = "encoder + first %d of 12 blocks per step, scaled x%.2f to a full forward (ratio measured on one full forward)" % (nb, scale)
+        fn = lambda: partial(nb)
+    for _ in range(max(args.warmup - 1, 0)):
+        fn()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fn()
+    dt = (time.perf_counter() - t0) * scale
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, "cpu"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, precision):
+    names = {"sfno12_nonlinear": "configs[1]: full SFNO 12-block forward, 73 vars, embed 256, 721x1440, batch 1/GPU, "
+                                 "filter_type=non-linear (SpectralAttentionS2, the reference default main.py runs)",
+             "sfno12_linear": "configs[1] variant: full SFNO 12-block forward with filter_type=linear (SpectralConvS2, 11.7 G params)",
+             "filter_linear": "configs[0]: single spectral filter RealSHT->SpectralConvS2->InverseRealSHT on 721x1440, 256 ch, batch 1"}
+    return {"workload": names[args.workload], "precision_tier": precision, "batch_per_gpu": 1, "lmax": LMAX, "mmax": MMAX,
+            "l2_policy": "inputs larger than L2 (x 303 MB, activations 1.06 GB per pass vs 126 MB L2)",
+            "parallelism": "independent members, one per GPU, no data-path collective"}
+
+
+# ----------------------------------------------------------------------------------------- our arm
+def build_ours(args, dev):
+    import torch
+    import msfno_b200
+    msfno_b200.set_precision(args.precision)
+    torch.manual_seed(0)
+    if args.workload == "filter_linear":
+        sht = msfno_b200.RealSHT(*IMG, lmax=LMAX, mmax=MMAX, grid="equiangular").float()
+        isht = msfno_b200.InverseRealSHT(*IMG, lmax=LMAX, mmax=MMAX, grid="equiangular").float()
+        sht.weights = sht.weights * 1e5
+        isht.pct = isht.pct / 1e5
+        mod = msfno_b200.SpectralConvS2(sht, isht, EMBED, use_complex_kernels=True)
+        mod.forward_transform, mod.inverse_transform = sht, isht
+        return mod.to(dev).eval(), (1, EMBED, *IMG)
+    ftype = "linear" if args.workload == "sfno12_linear" else "non-linear"
+    if ftype == "linear":
+        # build directly on the device: 11.7 G parameters (46.8 GB) never touch host memory
+        with torch.device(dev):
+            net = msfno_b200.FourierNeuralOperatorNet(dev, None, filter_type=ftype)
+    else:
+        net = msfno_b200.FourierNeuralOperatorNet(dev, None, filter_type=ftype)
+    return net.to(dev).eval(), (1, NVAR, *IMG)
+
+
+def dominant_kernel_roofline(args, net, dev, pk):
+    """Roofline of the kernel with the largest share of the step, timed live with CUDA events on the launching
+    stream, L2 flushed between launches.  Share evidence: profiles/*launches*.csv."""
+    import torch
+    from msfno_b200 import _lib
+    from msfno_b200._lib import lib, ptr, check
+    st = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(192 * 1024 * 1024 // 4, device=dev)
+
+    def timed(fn, iters=8):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return sum(ts) / len(ts)
+
+    if args.workload == "sfno12_nonlinear":
+        # spectral complex-MLP hidden layer: real GEMM [P x 1024] x [1024 x 1024] (2 of the 4 MLP launches per block)
+        Pp = 7440
+        A = torch.randn(Pp, 1024, device=dev)
+        W = torch.randn(1024, 1024, device=dev)
+        D = torch.empty(Pp, 1024, device=dev)
+        prec = _lib.PREC_TF32 if args.precision == "tf32" else _lib.PREC_FP32
+        ms = timed(lambda: check(lib.msfno_gemm_nt(ptr(A), 1024, ptr(W), 1024, ptr(D), 1024, Pp, 1024, 1024, 1, prec, st)))
+        flops = 2.0 * NPOS * 1024 * 1024  # algorithmic: only the 7260 modes with l >= m
+        ach = flops / (ms * 1e-3) / 1e12
+        peak = pk["bf16_sustained"] / 2.0
+        return {"kernel": "gemm (spectral complex-MLP hidden layer, M=7260 modes, N=K=1024 real)", "bound": "tensor",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "peak_source": "%s bf16_tflops_sustained / 2 (TF32 = half of BF16, BASELINE.md section 2)" % pk["src"],
+                "ms_per_launch": ms}
+    # linear workloads: the SpectralConvS2 weight stream
+    import msfno_b200
+    filt = net if args.workload == "filter_linear" else net.blocks[1].filter_layer.filter
+    sht = filt.forward_transform
+    plan = sht._get_plan(dev)
+    a_pm = torch.randn(1, plan.P, 2 * EMBED, device=dev)
+    out = torch.empty(1, 2 * EMBED, plan.P, device=dev)
+    w = filt.w.detach()
+    ms = timed(lambda: check(lib.msfno_specconv_fwd(plan.h, ptr(a_pm), ptr(w), ptr(out), 1, EMBED, EMBED, st)))
+    by = 8.0 * EMBED * EMBED * NPOS + 16.0 * EMBED * NPOS
+    ach = by / (ms * 1e-3) / 1e9
+    return {"kernel": "specconv_fwd_kernel (per-mode complex channel contraction, 3.8 GB weight stream)", "bound": "hbm",
+            "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
+            "peak_source": "%s hbm_gbs" % pk["src"], "ms_per_launch": ms}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: the MSFNO hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from msfno_b200 import _lib
+    pk = peaks()
+    net, xshape = build_ours(args, dev)
+    g = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(*xshape, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        y = net(x_dev)
+        y_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+        for _ in range(max(args.warmup - 1, 0)):
+            net(x_dev)
+        # ---- device-resident leg ---------------------------------------------------------------
+        sampler = ClockSampler(local)
+        sync_all()
+        if rank == 0:
+            sampler.start()
+        l0 = _lib.lib.msfno_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            y = net(x_dev)
+        e1.record()
+        sync_all()
+        launches = _lib.lib.msfno_launch_count() - l0
+        ms_dev = max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if rank == 0 else None
+        # ---- end-to-end leg: host buffers in, host buffers out -----------------------------------
+        for _ in range(2):
+            x_dev.copy_(x_host, non_blocking=True)
+            y_host.copy_(net(x_dev), non_blocking=True)
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            x_dev.copy_(x_host, non_blocking=True)
+            y_host.copy_(net(x_dev), non_blocking=True)
+        e1.record()
+        sync_all()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+
+        roof = dominant_kernel_roofline(args, net, dev, pk) if rank == 0 else None
+
+    bad = not torch.isfinite(y_host).all()
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline and args.workload != "filter_linear":
+        try:
+            full, partial, info = cpu_reference_step_factory(args.workload)
+            full()  # warm-up (thread pools, page faults)
+            t0 = time.perf_counter()
+            full()
+            dt = time.perf_counter() - t0
+            cpu_baseline = {"value": 1.0 / dt, "unit": UNIT, "cores": info["cores"], "kind": "port",
+                            "sample": "1 full 12-block forward (after 1 warm-up) of the oracle port of the reference path, fp32"}
+        except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU measurement
+            cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
+
+    value = world * args.steps / (ms_dev * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
+        "config": workload_config(args, args.precision),
+        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roof,
+        "cpu_baseline": cpu_baseline,
+        "output_finite": not bad,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sfno12_nonlinear", choices=["sfno12_nonlinear", "sfno12_linear", "filter_linear"])
+    ap.add_argument("--precision", default=os.environ.get("MSFNO_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

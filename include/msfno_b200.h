@@ -59,6 +59,8 @@ typedef struct msfno_plan msfno_plan;
 const char* msfno_last_error(void);
 /* compile-time facts: "sm_100a", has_tcgen05 etc. as a static JSON string */
 const char* msfno_build_info(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+unsigned long long msfno_launch_count(void);
 
 /* ---- plans ------------------------------------------------------------------------------
  * replaces: torch_harmonics.RealSHT.__init__ / InverseRealSHT.__init__ device-side state

@@ -11,6 +11,7 @@ There is no CPU fallback: importing requires libmsfno_b200.so (see __graft_entry
 """
 from . import _lib  # noqa: F401  (loads the shared library; raises loudly when it is missing)
 from . import legendre, quadrature
+from .precision import get_precision, set_precision
 from .sht import InverseRealSHT, RealSHT
 from .layers import MLP, ComplexReLU, DropPath, SpectralAttentionS2, SpectralConvS2, trunc_normal_
 from .sfnonet import (FeedForward, FiLM, Film_wrapper, FourierNeuralOperatorBlock, FourierNeuralOperatorBlock_Filmed,
@@ -18,7 +19,7 @@ from .sfnonet import (FeedForward, FiLM, Film_wrapper, FourierNeuralOperatorBloc
 from . import harmonics
 
 __all__ = [
-    "RealSHT", "InverseRealSHT", "quadrature", "legendre", "harmonics",
+    "RealSHT", "InverseRealSHT", "quadrature", "legendre", "harmonics", "set_precision", "get_precision",
     "SpectralConvS2", "SpectralAttentionS2", "ComplexReLU", "MLP", "DropPath", "trunc_normal_",
     "SpectralFilterLayer", "FiLM", "FourierNeuralOperatorBlock", "FourierNeuralOperatorBlock_Filmed",
     "FourierNeuralOperatorNet", "FourierNeuralOperatorNet_Filmed", "Film_wrapper", "FeedForward",

@@ -45,6 +45,7 @@ _P = c_void_p  # device / host pointers travel as integers
 _SIGS = {
     "msfno_last_error": (ctypes.c_char_p, []),
     "msfno_build_info": (ctypes.c_char_p, []),
+    "msfno_launch_count": (ctypes.c_ulonglong, []),
     "msfno_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int]),
     "msfno_plan_destroy": (c_int, [_P]),
     "msfno_plan_query": (c_long, [_P, c_int]),

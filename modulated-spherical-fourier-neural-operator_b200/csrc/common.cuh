@@ -15,6 +15,7 @@ namespace msfno {
 
 int record_cuda_error(cudaError_t e, const char* file, int line);
 int record_error(int code, const char* msg);
+void count_launch(int n = 1);  // kernels of this library launched so far (msfno_launch_count)
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -165,6 +165,7 @@ int msfno_film_affine_fwd(const float* x, const float* gamma, const float* beta,
   if (!x || !gamma || !beta || !y || B < 1 || C < 1 || HW < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "film_fwd: bad argument");
   dim3 grid(chunks_for(HW, B * C), B * C);
   film_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, scale, y, HW);
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }
@@ -173,6 +174,7 @@ int msfno_film_affine_bwd(const float* gy, const float* x, const float* gamma, f
                           float* gbeta, int B, int C, long HW, void* stream) {
   if (!gy || !x || !gamma || !ggamma || !gbeta || B < 1 || C < 1 || HW < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "film_bwd: bad argument");
   film_bwd_kernel<<<B * C, 1024, 0, (cudaStream_t)stream>>>(gy, x, gamma, scale, gx, ggamma, gbeta, HW);
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }
@@ -183,6 +185,7 @@ int msfno_plane_stats(const float* x, double* stats, int planes, long HW, void* 
   MSFNO_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)planes, st));
   dim3 grid(chunks_for(HW, planes), planes);
   plane_stats_kernel<<<grid, 256, 0, st>>>(x, stats, HW);
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }
@@ -193,6 +196,7 @@ int msfno_norm_film_coeffs(const double* stats, const float* nw, const float* nb
     return record_error(MSFNO_ERR_BAD_SHAPE, "norm_film_coeffs: bad argument");
   norm_film_coeffs_kernel<<<(B * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, nw, nb, gamma, beta, scale, eps, A, S,
                                                                                 B, C, 1.0 / (double)HW);
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }
@@ -201,6 +205,7 @@ int msfno_plane_affine(const float* x, const float* A, const float* S, float* y,
   if (!x || !A || !S || !y || planes < 1 || HW < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "plane_affine: bad argument");
   dim3 grid(chunks_for(HW, planes), planes);
   plane_affine_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, A, S, y, HW);
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }

@@ -250,6 +250,7 @@ int launch_rfft_trunc(const msfno_plan* p, const float* x, float* Xt, const floa
   rfft_trunc_kernel<<<grid, nw * 32, smem, st>>>(x, Xt, reinterpret_cast<const cf*>(p->d_tw),
                                                  reinterpret_cast<const cf*>(p->d_tw2), mscale, in_scale, in_shift,
                                                  p->sched, p->nlat, p->nlon, p->mlim, p->kpad, C, zero_imag, use_bulk);
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }
@@ -268,6 +269,7 @@ int launch_irfft_trunc(const msfno_plan* p, const float* Yt, float* y, const flo
   irfft_trunc_kernel<<<grid, nw * 32, smem, st>>>(Yt, y, reinterpret_cast<const cf*>(p->d_tw),
                                                   reinterpret_cast<const cf*>(p->d_tw2), mscale, skip, out_scale, stats,
                                                   p->sched, p->nlat, p->nlon, p->mlim, p->kpad, C, act_gelu, vec_ok);
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }

@@ -190,6 +190,7 @@ int launch_gemm_ffma(const GemmLaunch& g, cudaStream_t st) {
   else if (g.a_kmajor && !g.b_kmajor) gemm_ffma_kernel<true, false><<<grid, 256, 0, st>>>(g, tilesN);
   else if (!g.a_kmajor && g.b_kmajor) gemm_ffma_kernel<false, true><<<grid, 256, 0, st>>>(g, tilesN);
   else gemm_ffma_kernel<false, false><<<grid, 256, 0, st>>>(g, tilesN);
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }

@@ -7,6 +7,7 @@
 #include <math.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
 
 #include "common.cuh"
@@ -15,6 +16,8 @@
 namespace msfno {
 
 static thread_local std::string g_last_error;
+static std::atomic<unsigned long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int record_error(int code, const char* msg) {
   g_last_error = msg;
@@ -152,6 +155,8 @@ extern "C" {
 
 const char* msfno_last_error(void) { return g_last_error.c_str(); }
 
+unsigned long long msfno_launch_count(void) { return g_launches.load(); }
+
 const char* msfno_build_info(void) {
   return "{\"arch\": \"sm_100a\", \"abi\": 1, \"tiers\": [\"fp32\", \"tf32\"], \"fft\": \"stockham-smem-bulkcopy\"}";
 }
@@ -264,6 +269,7 @@ int msfno_plan_set_table(msfno_plan* p, const float* table, int analysis, void* 
     if (!p->d_tab_kl) MSFNO_CUDA_OK(cudaMalloc(&p->d_tab_kl, sizeof(float) * (size_t)p->mlim * p->nlat * p->Lj));
     relayout_kl_kernel<<<592, 256, 0, st>>>(table, p->d_tab_kl, p->lmax, p->nlat, p->mlim, p->Lj);
   }
+  count_launch(2);
   MSFNO_CUDA_OK(cudaGetLastError());
   int32_t flag = 0;
   MSFNO_CUDA_OK(cudaMemcpyAsync(&flag, p->d_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
@@ -277,6 +283,7 @@ int msfno_coef_relayout(const msfno_plan* p, const float* src, int sl, float* ds
   if (sl == dl || sl < 0 || sl > 2 || dl < 0 || dl > 2) return record_error(MSFNO_ERR_BAD_SHAPE, "coef_relayout: bad layouts");
   coef_relayout_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(src, sl, dst, dl, p->d_poff, p->d_p2lm, B, C, p->lmax,
                                                                  p->mmax, p->mlim, p->P);
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }

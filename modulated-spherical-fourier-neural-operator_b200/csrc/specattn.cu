@@ -94,6 +94,7 @@ int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* cons
   int cin = C;
   for (int l = 0; l < nl; ++l) {
     pack_cweight_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(w[l], ws + L.wbig[l], cin, hid);
+    count_launch();
     int rc = launch_gemm_single(in, 2 * cin, 1, ws + L.wbig[l], 2 * cin, 1, ws + L.h[l], 2 * hid, rows, 2 * hid, 2 * cin,
                                 /*relu_even=*/1, nullptr, 0, 0, st);
     if (rc) return rc;
@@ -101,6 +102,7 @@ int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* cons
     cin = hid;
   }
   pack_cweight_kernel<<<(hid * C + 255) / 256, 256, 0, st>>>(wout, ws + L.wbig_out, hid, C);
+  count_launch();
   // out_cm[b][ch][p] = sum_k wbig_out[ch][k] * h[b*P + p][k]   (strided batch over b)
   GemmLaunch g{};
   g.A = ws + L.wbig_out; g.B = in; g.D = out_cm;
@@ -136,6 +138,7 @@ int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm
     if (rc) return rc;
   }
   unpack_cweight_grad_kernel<<<(hid * C + 255) / 256, 256, 0, st>>>(gwbig, gwout, hid, C);
+  count_launch();
   // gz_last[b*P+p][k] = relu'(h) * sum_ch g_cm[b][ch][p] * Wout_big[ch][k]
   {
     GemmLaunch g{};
@@ -159,6 +162,7 @@ int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm
                                 0, st);
     if (rc) return rc;
     unpack_cweight_grad_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(gwbig, gw[l], cin, hid);
+    count_launch();
     // g_in[row][cincol] = sum_hidcol gz[row][hidcol] * Wbig_l[hidcol][cincol]  (masked by ReLU of the layer below)
     float* dst = (l == 0) ? ga_pm : gz[cur ^ 1];
     rc = launch_gemm_single(gz[cur], 2 * hid, 1, ws + L.wbig[l], 2 * cin, 0, dst, 2 * cin, rows, 2 * cin, 2 * hid, 0,

@@ -276,6 +276,7 @@ int msfno_specconv_fwd(const msfno_plan* p, const float* a_pm, const float* w, f
   else if (B <= 4) LAUNCH_FWD(4, 1)
   else LAUNCH_FWD(8, 1)
 #undef LAUNCH_FWD
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }
@@ -297,6 +298,7 @@ int msfno_specconv_bwd_x(const msfno_plan* p, const float* g_cm, const float* w,
   else if (B <= 4) LAUNCH_BX(4, 1)
   else LAUNCH_BX(8, 1)
 #undef LAUNCH_BX
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }
@@ -314,6 +316,7 @@ int msfno_specconv_bwd_w(const msfno_plan* p, const float* a_pm, const float* g_
     dim3 grid((p->ntril + SC_THREADS - 1) / SC_THREADS, (Co + KT - 1) / KT, (Ci + IT - 1) / IT);
     specconv_bwdw_kernel<1, KT, IT><<<grid, SC_THREADS, 0, st>>>(a_pm, g_cm, gw, p->d_n2p, B, Ci, Co, p->ntril, p->P);
   }
+  count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }

@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
+from . import precision as _precision
 from ._lib import check, lib, ptr
 from .sht import RealSHT, InverseRealSHT, _stream, _require_cuda, relayout
 
@@ -200,7 +201,7 @@ class SpectralAttentionS2(nn.Module):
 
     def __init__(self, forward_transform, inverse_transform, embed_dim, sparsity_threshold=0.0, hidden_size_factor=2,
                  use_complex_network=True, use_complex_kernels=False, complex_activation="real", bias=False,
-                 spectral_layers=1, drop_rate=0.0, precision="fp32"):
+                 spectral_layers=1, drop_rate=0.0, precision=None):
         super().__init__()
         if bias:
             raise NotImplementedError("SpectralAttentionS2 bias is never enabled by the reference nets (sfnonet.py:89)")
@@ -233,7 +234,8 @@ class SpectralAttentionS2(nn.Module):
         self.precision = precision
 
     def spectral(self, a_pm):
-        prec = _lib.PREC_TF32 if self.precision == "tf32" else _lib.PREC_FP32
+        tier = self.precision if self.precision is not None else _precision.get_precision()
+        prec = _lib.PREC_TF32 if tier == "tf32" else _lib.PREC_FP32
         ws = [w.float().contiguous() for w in self.w]
         return _SpecAttn.apply(a_pm, self._sht, prec, self.wout.float().contiguous(), *ws)
 

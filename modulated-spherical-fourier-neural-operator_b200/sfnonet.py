@@ -26,6 +26,7 @@ import torch.nn.functional as F
 from torch.utils.checkpoint import checkpoint
 
 from . import _lib
+from . import precision as _precision
 from ._lib import check, lib, ptr
 from .layers import MLP, DropPath, SpectralAttentionS2, SpectralConvS2, trunc_normal_
 from .sht import InverseRealSHT, RealSHT, _stream
@@ -412,14 +413,15 @@ class FourierNeuralOperatorNet(nn.Module):
         return x
 
     def forward(self, x):
-        if self.big_skip:
-            residual = x
-        x = self.encoder(x)
-        x = x + self.pos_embed
-        x = self.forward_features(x)
-        if self.big_skip:
-            x = torch.cat((x, residual), dim=1)
-        return self.decoder(x)
+        with _precision.library_scope():
+            if self.big_skip:
+                residual = x
+            x = self.encoder(x)
+            x = x + self.pos_embed
+            x = self.forward_features(x)
+            if self.big_skip:
+                x = torch.cat((x, residual), dim=1)
+            return self.decoder(x)
 
 
 class FeedForward(nn.Module):
@@ -491,6 +493,10 @@ class FourierNeuralOperatorNet_Filmed(FourierNeuralOperatorNet):
         self.film_gen = Film_wrapper(device, cfg)
 
     def forward(self, x, sst, scale=1):
+        with _precision.library_scope():
+            return self._forward(x, sst, scale)
+
+    def _forward(self, x, sst, scale=1):
         film_mod = self.film_gen(sst)
         gamma, beta = film_mod[:, 0], film_mod[:, 1]
         if self.advanced_logging:

@@ -1,0 +1,90 @@
+"""GPU parity: whole SFNO / MSFNO nets (fused inference path and autograd path) against the golden outputs of
+the unmodified reference, plus training-step gradients against the oracle's autograd."""
+import os
+
+import pytest
+import torch
+
+from conftest import GOLD, TOL_FP32, rel_l2
+from oracle import sfno_oracle
+
+pytestmark = pytest.mark.gpu
+
+import msfno_b200
+
+
+def _load(net, sd):
+    full = dict(net.state_dict())
+    for k, v in sd.items():
+        assert k in full and full[k].shape == v.shape, k
+        full[k] = v
+    net.load_state_dict(full, strict=True)
+    return net
+
+
+def _oracle_sd(cfg, ftype, seed, film_layers=0):
+    return sfno_oracle.make_state_dict(filter_type=ftype, img_size=cfg["img_size"], scale_factor=cfg["scale_factor"],
+                                       in_chans=cfg["in_chans"], out_chans=cfg["out_chans"], embed=cfg["embed_dim_sfno"],
+                                       num_layers=cfg["num_layers"], mlp_ratio=cfg["mlp_ratio"],
+                                       spectral_layers=cfg["spectral_layers"], seed=seed, film_layers=film_layers)
+
+
+@pytest.mark.parametrize("name,ftype", [("net_linear_small.pt", "linear"), ("net_nonlinear_small.pt", "non-linear")])
+def test_small_net_matches_reference(name, ftype):
+    d = torch.load(os.path.join(GOLD, name))
+    cfg = d["cfg"]
+    net = _load(msfno_b200.FourierNeuralOperatorNet("cuda", None, **cfg), _oracle_sd(cfg, ftype, d["seed"])).cuda().eval()
+    x = d["x"].cuda()
+    with torch.no_grad():
+        y_fused = net(x)
+    assert rel_l2(y_fused, d["y"]) < TOL_FP32
+    y_auto = net(x.clone().requires_grad_(True))   # autograd (unfused) path
+    assert rel_l2(y_auto, d["y"]) < TOL_FP32
+
+
+class _Cfg:
+    film_gen_type, cls, embed_dim, mlp_dim, dropout, scale_weight, repeat_film = "mae", "x", 512, 1024, 0.0, 1, False
+
+
+@pytest.mark.parametrize("fl", [1, 3])
+def test_filmed_net_matches_reference(fl):
+    d = torch.load(os.path.join(GOLD, "filmed_fl%d_small.pt" % fl))
+    cfg = dict(d["cfg"])
+    c = _Cfg()
+    c.film_layers, c.batch_size = fl, d["x"].shape[0]
+    mlp_ratio = cfg.pop("mlp_ratio")
+    net = msfno_b200.FourierNeuralOperatorNet_Filmed("cuda", c, mlp_ratio=mlp_ratio, advanced_logging=True,
+                                                     film_layers=fl, model_depth=6, **cfg)
+    cfg["mlp_ratio"] = mlp_ratio
+    sd = _oracle_sd(cfg, "non-linear", d["seed"], film_layers=fl)
+    net = _load(net, sd).cuda().eval()
+    x, cond = d["x"].cuda(), d["cond"].cuda()
+    with torch.no_grad():
+        y = net(x, cond, d["scale"])
+    assert rel_l2(net.gamma, d["gamma"]) < 1e-5
+    assert rel_l2(y, d["y"]) < TOL_FP32
+
+    # training step: gradients w.r.t. the FiLM head and (fl=3) through SHT / spectral MLP / ISHT
+    y2 = net(x, cond, d["scale"])
+    assert rel_l2(y2, d["y"]) < TOL_FP32
+    gy = torch.randn(d["y"].shape, generator=torch.Generator().manual_seed(1))
+    with msfno_b200.precision.library_scope():
+        y2.backward(gy.cuda())
+
+    sdo = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    tr = sfno_oracle.Transforms(cfg["img_size"], cfg["scale_factor"])
+    B = x.shape[0]
+    fm = sfno_oracle.film_head(d["cond"], sdo).reshape(B, 2, fl, 256)
+    # reference semantics: encoder and un-FiLMed blocks run under no_grad (sfnonet.py:817-827,843-844); compare
+    # only parameters that receive gradient in both: the film head and the FiLMed blocks' spectral weights
+    yo = sfno_oracle.sfno_forward(d["x"], sdo, tr, "non-linear", cfg["num_layers"], film_mod=fm, film_layers=fl,
+                                  scale=d["scale"])
+    yo.backward(gy)
+    got = dict(net.named_parameters())
+    for k in ("film_gen.film_head.net.4.weight", "film_gen.film_head.net.1.weight", "decoder.fwd.0.weight"):
+        assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
+    last = cfg["num_layers"] - 1
+    k = "blocks.%d.filter_layer.filter.wout" % last
+    assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
+    k = "blocks.%d.filter_layer.filter.w.0" % last
+    assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
