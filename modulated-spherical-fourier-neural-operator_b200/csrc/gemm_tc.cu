@@ -1,0 +1,308 @@
+// Grouped TF32 GEMM on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) issued by one thread,
+// operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), fp32 accumulators in
+// TMEM, read back with tcgen05.ld for the epilogue.  This is the "tensor-core tier" (<= 2e-3 rel-L2) engine of
+// the spectral complex MLP and of the Legendre contractions.
+//
+// replaces: the cuBLAS GEMMs torch.einsum dispatches to in /root/reference
+//   MSFNO/Models/sfno/contractions.py:132-137 ("bixy,io->boxy") and in torch_harmonics' Legendre einsums.
+//
+// D[M][N] = A[M][K] * B[N][K]^T, both operands K-major fp32 in global memory, described to TMA as plain 2-D
+// tensors [rows][ld]; a group selects its sub-problem by (row, column) coordinates, so one tensor map per
+// operand serves all groups of a launch.  Out-of-range rows/columns are zero-filled by TMA.
+//
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
+// warps 4-7 = epilogue (TMEM lane quarter q = warp % 4).  BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32 fp32
+// (= one 128-byte swizzle span = 4 UMMA K-steps of 8).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "plan.h"
+
+namespace msfno {
+
+static constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 6;
+static constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
+static constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;  // 16 KB
+static constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+static constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+
+struct TcParams {
+  float* D;
+  long long lda, ldb, ldd;
+  const GemmGroup* groups;
+  GemmGroup single;
+  long long sa, sb, sd;
+  int use_single;
+  int relu_even;
+  int round_tf32;
+  int tilesN;
+};
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+// try_wait in a bounded loop: a faulty descriptor traps (error surfaced to the host) instead of hanging the SM
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.b32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (=1), descriptor version 1
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ float round_to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  GemmGroup grp;
+  if (p.use_single) {
+    grp = p.single;
+    grp.a_off += blockIdx.y * p.sa;
+    grp.b_off += blockIdx.y * p.sb;
+    grp.d_off += blockIdx.y * p.sd;
+  } else {
+    grp = p.groups[blockIdx.y];
+  }
+  const int tm = blockIdx.x / p.tilesN, tn = blockIdx.x - tm * p.tilesN;
+  const int m0 = tm * TC_BM, n0 = tn * TC_BN;
+  if (m0 >= grp.M || n0 >= grp.N) return;  // uniform for the CTA, before any barrier / allocation
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TC_STAGES;
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (grp.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(TC_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0 && lane == 0) {
+      // ---------------- TMA producer ----------------
+      const int a_row = (int)(grp.a_off / p.lda) + m0, a_col = (int)(grp.a_off % p.lda);
+      const int b_row = (int)(grp.b_off / p.ldb) + n0, b_col = (int)(grp.b_off % p.ldb);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
+        mbar_wait_bounded(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
+        uint8_t* sa = tiles + s * TC_STAGE_BYTES;
+        tma_load_2d(sa, &tmA, &full[s], a_col + kb * TC_BK, a_row);
+        tma_load_2d(sa + TC_A_BYTES, &tmB, &full[s], b_col + kb * TC_BK, b_row);
+      }
+    } else if (warp == 1 && lane == 0) {
+      // ---------------- MMA issuer ----------------
+      // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
+        mbar_wait_bounded(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * TC_STAGE_BYTES;
+        const uint64_t adesc = make_smem_desc_sw128(sa);
+        const uint64_t bdesc = make_smem_desc_sw128(sa + TC_A_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          // advance 8 tf32 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
+          tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+        }
+        tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+      }
+      tc_commit(tmem_full);    // accumulator complete
+    }
+  }
+
+  if (warp >= 4) {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    const int q = warp & 3;
+    const int row = m0 + q * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait_bounded(tmem_full, 0);
+      tc_fence_after();
+    }
+    float* drow = p.D + grp.d_off + (long long)row * p.ldd;
+    const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+      uint32_t r[32];
+      if (nkb > 0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      const int gn = n0 + c0;
+      if (row < grp.M && gn < grp.N) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = __uint_as_float(r[j]);
+          if (p.relu_even && !(j & 1)) t = fmaxf(t, 0.f);
+          if (p.round_tf32) t = round_to_tf32(t);
+          v[j] = t;
+        }
+        if (vec && gn + 31 < grp.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(drow + gn + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gn + j < grp.N) drow[gn + j] = v[j];
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TC_BN));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D fp32 tensor [rows][ld] (cols valid), box = 32 columns x box_rows rows, 128-byte swizzle
+static int make_map(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
+  return MSFNO_OK;
+}
+
+bool gemm_tc_supported(const GemmLaunch& g) {
+  if (!g.a_kmajor || !g.b_kmajor || g.mask || g.accumulate) return false;
+  if ((g.lda & 3) || (g.ldb & 3)) return false;
+  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
+  return get_encode() != nullptr;
+}
+
+// a_rows / b_rows: number of rows of the underlying 2-D buffers (TMA zero-fills beyond them);
+// a_cols / b_cols: valid columns (<= ld)
+int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
+                   int round_tf32, cudaStream_t st) {
+  if (g.ngroups <= 0 || g.maxM <= 0 || g.maxN <= 0) return MSFNO_OK;
+  CUtensorMap tmA, tmB;
+  int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, TC_BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, TC_BN);
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+  });
+  MSFNO_CUDA_OK(attr_err);
+  TcParams p{};
+  p.D = g.D; p.lda = g.lda; p.ldb = g.ldb; p.ldd = g.ldd;
+  p.groups = g.groups; p.single = g.single; p.sa = g.sa; p.sb = g.sb; p.sd = g.sd; p.use_single = g.use_single;
+  p.relu_even = g.relu_even; p.round_tf32 = round_tf32;
+  const int tilesM = (g.maxM + TC_BM - 1) / TC_BM;
+  p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;
+  dim3 grid(tilesM * p.tilesN, g.ngroups);
+  gemm_tc_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(tmA, tmB, p);
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+}  // namespace msfno

@@ -82,4 +82,10 @@ int launch_gemm_single(const float* A, long long lda, int a_kmajor, const float*
                        float* D, long long ldd, int M, int N, int K, int relu_even, const float* mask,
                        long long ldmask, int accumulate, cudaStream_t st);
 
+// tcgen05 / TMEM / TMA TF32 path (gemm_tc.cu).  Supported when both operands are K-major, 16-byte aligned,
+// no ReLU-mask / accumulate epilogue.  a_rows/a_cols (b_rows/b_cols) describe the whole 2-D buffer behind A (B).
+bool gemm_tc_supported(const GemmLaunch& g);
+int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
+                   int round_tf32, cudaStream_t st);
+
 }  // namespace msfno

@@ -16,11 +16,18 @@
 namespace msfno {
 
 // w [Ci][Co][2] -> wbig [2Co][2Ci]
-__global__ void pack_cweight_kernel(const float* __restrict__ w, float* __restrict__ wbig, int Ci, int Co) {
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void pack_cweight_kernel(const float* __restrict__ w, float* __restrict__ wbig, int Ci, int Co, int round_tf32) {
   const int total = Ci * Co;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
     const int i = idx % Ci, o = idx / Ci;  // consecutive threads -> consecutive i (coalesced writes)
-    const float2 v = *reinterpret_cast<const float2*>(w + ((size_t)i * Co + o) * 2);
+    float2 v = *reinterpret_cast<const float2*>(w + ((size_t)i * Co + o) * 2);
+    if (round_tf32) { v.x = rna_tf32(v.x); v.y = rna_tf32(v.y); }
     float* r0 = wbig + (size_t)(2 * o) * (2 * Ci) + 2 * i;
     float* r1 = r0 + 2 * Ci;
     r0[0] = v.x; r0[1] = -v.y;
@@ -39,6 +46,23 @@ __global__ void unpack_cweight_grad_kernel(const float* __restrict__ g, float* _
     v.y = r1[0] - r0[1];
     *reinterpret_cast<float2*>(gw + ((size_t)i * Co + o) * 2) = v;
   }
+}
+
+// D[M][N] = A[M][K] * B[N][K]^T on the selected engine (tensor cores when the tier and the operands allow it)
+static int gemm_nt_any(int tc, const float* A, long long lda, const float* Bm, long long ldb, float* D, long long ldd, int M,
+                       int N, int K, int relu_even, int round_tf32, cudaStream_t st) {
+  if (tc) {
+    GemmLaunch g{};
+    g.A = A; g.B = Bm; g.D = D;
+    g.lda = lda; g.ldb = ldb; g.ldd = ldd;
+    g.a_kmajor = 1; g.b_kmajor = 1;
+    g.relu_even = relu_even;
+    g.ngroups = 1; g.maxM = M; g.maxN = N;
+    g.use_single = 1;
+    g.single = GemmGroup{0, 0, 0, M, N, K, 0};
+    if (gemm_tc_supported(g)) return launch_gemm_tc(g, M, K, N, K, round_tf32, st);
+  }
+  return launch_gemm_single(A, lda, 1, Bm, ldb, 1, D, ldd, M, N, K, relu_even, nullptr, 0, 0, st);
 }
 
 struct AttnWs {
@@ -86,22 +110,22 @@ size_t msfno_specattn_bwd_scratch_floats(const msfno_plan* p, int B, int C, int 
 int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* const* w, int nl, const float* wout,
                        float* out_cm, float* ws, int B, int C, int hid, int precision, void* stream) {
   if (!p || !a_pm || !w || !wout || !out_cm || !ws || nl < 1 || nl > 16) return record_error(MSFNO_ERR_BAD_SHAPE, "specattn_fwd: bad argument");
-  (void)precision;
   cudaStream_t st = (cudaStream_t)stream;
   const AttnWs L = attn_layout(p->P, B, C, hid, nl);
   const int rows = B * p->P;
+  const int tc = (precision == MSFNO_PREC_TF32);
   const float* in = a_pm;
   int cin = C;
   for (int l = 0; l < nl; ++l) {
-    pack_cweight_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(w[l], ws + L.wbig[l], cin, hid);
+    pack_cweight_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(w[l], ws + L.wbig[l], cin, hid, tc);
     count_launch();
-    int rc = launch_gemm_single(in, 2 * cin, 1, ws + L.wbig[l], 2 * cin, 1, ws + L.h[l], 2 * hid, rows, 2 * hid, 2 * cin,
-                                /*relu_even=*/1, nullptr, 0, 0, st);
+    int rc = gemm_nt_any(tc, in, 2 * cin, ws + L.wbig[l], 2 * cin, ws + L.h[l], 2 * hid, rows, 2 * hid, 2 * cin,
+                         /*relu_even=*/1, /*round_tf32=*/tc, st);
     if (rc) return rc;
     in = ws + L.h[l];
     cin = hid;
   }
-  pack_cweight_kernel<<<(hid * C + 255) / 256, 256, 0, st>>>(wout, ws + L.wbig_out, hid, C);
+  pack_cweight_kernel<<<(hid * C + 255) / 256, 256, 0, st>>>(wout, ws + L.wbig_out, hid, C, tc);
   count_launch();
   // out_cm[b][ch][p] = sum_k wbig_out[ch][k] * h[b*P + p][k]   (strided batch over b)
   GemmLaunch g{};
@@ -112,7 +136,9 @@ int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* cons
   g.use_single = 1;
   g.single = GemmGroup{0, 0, 0, 2 * C, p->P, 2 * hid, 0};
   g.sa = 0; g.sb = (long long)p->P * 2 * hid; g.sd = (long long)2 * C * p->P;
-  int rc = launch_gemm_ffma(g, st);
+  int rc;
+  if (tc && gemm_tc_supported(g)) rc = launch_gemm_tc(g, 2 * C, 2 * hid, (long long)B * p->P, 2 * hid, 0, st);
+  else rc = launch_gemm_ffma(g, st);
   if (rc) return rc;
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
@@ -177,8 +203,7 @@ int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm
 int msfno_gemm_nt(const float* A, long lda, const float* Bm, long ldb, float* D, long ldd, int M, int N, int K,
                   int relu_even_cols, int precision, void* stream) {
   if (!A || !Bm || !D || M < 0 || N < 0 || K < 0) return record_error(MSFNO_ERR_BAD_SHAPE, "gemm_nt: bad argument");
-  (void)precision;
-  return launch_gemm_single(A, lda, 1, Bm, ldb, 1, D, ldd, M, N, K, relu_even_cols, nullptr, 0, 0, (cudaStream_t)stream);
+  return gemm_nt_any(precision == MSFNO_PREC_TF32, A, lda, Bm, ldb, D, ldd, M, N, K, relu_even_cols, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

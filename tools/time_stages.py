@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--C", type=int, default=256)
     ap.add_argument("--B", type=int, default=1)
     ap.add_argument("--linear", action="store_true")
+    ap.add_argument("--precision", default="fp32")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     B, C = a.B, a.C
@@ -63,7 +64,7 @@ def main():
         s, i = tr["inner"]
         x = torch.randn(B, C, 120, 240, device=dev)
         pm = s.forward_packed(x)
-        att = msfno_b200.SpectralAttentionS2(s, i, C, hidden_size_factor=2, spectral_layers=3).to(dev)
+        att = msfno_b200.SpectralAttentionS2(s, i, C, hidden_size_factor=2, spectral_layers=3, precision=a.precision).to(dev)
         out["specattn_mlp"] = timeit(lambda: att.spectral(pm), flush=flush)
         out["specattn_mlp_TFLOPs_dense_equiv"] = 8 * 786432 * (C / 256) ** 2 * B * 7260 / out["specattn_mlp"] / 1e9
         out["specattn_filter_inner"] = timeit(lambda: att(x), flush=flush)
