@@ -8,6 +8,8 @@
 //           /root/reference MSFNO/Models/sfno/layers.py:405,421,629,638).
 // Unlike cuFFT it only ever writes / reads the mlim = min(mmax, lmax) orders the Legendre stage
 // uses, directly in the [b][m][2c+ri][lat] layout that stage contracts over (lat contiguous).
+#include <stdlib.h>
+
 #include "fft_core.cuh"
 #include "common.cuh"
 #include "plan.h"
@@ -229,6 +231,12 @@ irfft_trunc_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf
 }
 
 // ---------------------------------------------------------------------------------------------
+// MSFNO_FFT_GENERIC=1 forces the radix-stage kernels (A/B comparison and debugging)
+static bool force_generic_fft() {
+  static const bool v = [] { const char* e = getenv("MSFNO_FFT_GENERIC"); return e && e[0] == '1'; }();
+  return v;
+}
+
 static int pick_warps(size_t fixed_bytes, size_t per_warp_bytes, int* nwarps, size_t* total) {
   for (int nw = 8; nw >= 1; nw >>= 1) {
     size_t t = fixed_bytes + 256 + nw * (per_warp_bytes + 16 * 2);
@@ -246,6 +254,8 @@ int launch_rfft_trunc(const msfno_plan* p, const float* x, float* Xt, const floa
   if (rc) return rc;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(rfft_trunc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int use_bulk = (p->nlon % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  if (use_bulk && fft2d_supported(p->nlon) && !force_generic_fft())
+    return launch_rfft2d(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
   dim3 grid((p->nlat + ROWS_PER_TILE - 1) / ROWS_PER_TILE, B * C);
   rfft_trunc_kernel<<<grid, nw * 32, smem, st>>>(x, Xt, reinterpret_cast<const cf*>(p->d_tw),
                                                  reinterpret_cast<const cf*>(p->d_tw2), mscale, in_scale, in_shift,
@@ -265,6 +275,8 @@ int launch_irfft_trunc(const msfno_plan* p, const float* Yt, float* y, const flo
   MSFNO_CUDA_OK(cudaFuncSetAttribute(irfft_trunc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int vec_ok = (p->nlon % 4 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
                      (!skip || (reinterpret_cast<uintptr_t>(skip) & 15) == 0);
+  if (vec_ok && fft2d_supported(p->nlon) && !force_generic_fft())
+    return launch_irfft2d(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
   dim3 grid((p->nlat + ROWS_PER_TILE - 1) / ROWS_PER_TILE, B * C);
   irfft_trunc_kernel<<<grid, nw * 32, smem, st>>>(Yt, y, reinterpret_cast<const cf*>(p->d_tw),
                                                   reinterpret_cast<const cf*>(p->d_tw2), mscale, skip, out_scale, stats,

@@ -1,0 +1,335 @@
+// Four-step longitude FFT kernels (forward truncated r2c, inverse zero-padded c2r) for the production sizes:
+//   nlon = 1440 (H = 720 = 24 x 30), nlon = 240 (H = 120 = 15 x 8, 4 rows per warp), nlon = 2880 (H = 1440 = 36 x 40).
+// Same interface, data layout and fused prologue/epilogue as the generic Stockham kernels in fft.cu (which remain
+// the fallback for every other size); the difference is the arithmetic core: two rounds of fully unrolled
+// in-register DFTs (fft_reg.cuh) with compile-time twiddles, one shared-memory exchange in between, no integer
+// division, bank-conflict-free pitches.  ~4x fewer issued instructions per row than the radix-stage kernel.
+//
+// replaces: torch.fft.rfft(norm="forward") * 2 pi and torch.fft.irfft(n=nlon, norm="forward") inside
+// torch_harmonics RealSHT / InverseRealSHT (/root/reference MSFNO/Models/sfno/layers.py:405,421,629,638).
+#include "common.cuh"
+#include "fft2d_core.cuh"
+#include "plan.h"
+
+namespace msfno {
+
+static constexpr int ROWS_PER_TILE2 = 32;
+static constexpr int OST2 = 33;
+
+template <int P1, int P2, int RW>
+__global__ void __launch_bounds__(256, 1)
+rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __restrict__ g_tw,
+              const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ in_scale,
+              const float* __restrict__ in_shift, int nlat, int mlim, int kpad, int C, int zero_imag) {
+  constexpr int H = P1 * P2, NLON = 2 * H, WP = WorkPitch<P2>::value;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nw = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bc = blockIdx.y;
+  const int b = bc / C, c = bc - b * C;
+  const int k0 = blockIdx.x * ROWS_PER_TILE2;
+  const int XS = xs_size(H, mlim);
+
+  cf* tw = reinterpret_cast<cf*>(smem_raw);
+  cf* tw2 = tw + H;
+  float* ostage = reinterpret_cast<float*>(tw2 + (mlim + 1));
+  size_t off = (size_t)(reinterpret_cast<unsigned char*>(ostage + 2 * mlim * OST2) - smem_raw);
+  off = (off + 15) & ~(size_t)15;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + off);
+  off += sizeof(uint64_t) * 2 * nw;
+  off = (off + 127) & ~(size_t)127;
+  const size_t per_warp = sizeof(cf) * ((size_t)2 * RW * H + (size_t)RW * P1 * WP + (size_t)RW * XS);
+  unsigned char* wbase = smem_raw + off + (size_t)warp * ((per_warp + 127) & ~(size_t)127);
+  cf* raw[2] = {reinterpret_cast<cf*>(wbase), reinterpret_cast<cf*>(wbase) + RW * H};
+  cf* work = raw[1] + RW * H;
+  cf* xs = work + RW * P1 * WP;
+
+  for (int i = threadIdx.x; i < H; i += blockDim.x) tw[i] = g_tw[i];
+  for (int i = threadIdx.x; i <= mlim; i += blockDim.x) tw2[i] = g_tw2[i];
+  if (lane == 0) {
+    mbar_init(&bars[2 * warp + 0], 1);
+    mbar_init(&bars[2 * warp + 1], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+
+  const float sc_in = in_scale ? in_scale[bc] : 1.0f;
+  const float sh_in = in_shift ? in_shift[bc] : 0.0f;
+  const float* xbase = x + ((size_t)bc * nlat) * NLON;
+  constexpr int NGROUPS = ROWS_PER_TILE2 / RW;
+  const int iters = (NGROUPS + nw - 1) / nw;
+
+  auto rows_valid = [&](int it) -> int {  // valid rows of the row group this warp handles in iteration `it`
+    const int g = warp + it * nw;
+    if (g >= NGROUPS) return 0;
+    const int r0 = k0 + g * RW;
+    const int nv = nlat - r0;
+    return nv < 0 ? 0 : (nv > RW ? RW : nv);
+  };
+  auto issue_load = [&](int it, int nv) {
+    if (lane == 0) {
+      const int g = warp + it * nw;
+      const uint32_t bytes = (uint32_t)nv * NLON * 4u;
+      mbar_arrive_expect_tx(&bars[2 * warp + (it & 1)], bytes);
+      bulk_g2s(raw[it & 1], xbase + (size_t)(k0 + g * RW) * NLON, bytes, &bars[2 * warp + (it & 1)]);
+    }
+  };
+
+  int nv = rows_valid(0);
+  if (nv > 0) issue_load(0, nv);
+  for (int it = 0; it < iters; ++it) {
+    if (nv <= 0) break;  // warp-uniform; groups are ascending so later ones are invalid too
+    const int nv_next = (it + 1 < iters) ? rows_valid(it + 1) : 0;
+    if (nv_next > 0) issue_load(it + 1, nv_next);
+    mbar_wait(&bars[2 * warp + (it & 1)], (uint32_t)((it >> 1) & 1));
+    const cf* in = raw[it & 1];
+    const int g = warp + it * nw;
+
+    // step 1: RW*P2 column transforms of length P1
+    for (int t = lane; t < RW * P2; t += 32) {
+      const int r = t / P2, n2 = t - r * P2;
+      if (r < nv) fft2d_step1<P1, P2, -1>(in + r * H, P2, work + r * P1 * WP, tw, n2);
+    }
+    __syncwarp();
+    // step 2: RW*P1 row transforms of length P2; keep only the bins the real split needs
+    for (int t = lane; t < RW * P1; t += 32) {
+      const int r = t / P1, k1 = t - r * P1;
+      if (r < nv) {
+        cf v[P2];
+        fft2d_step2<P1, P2, -1>(work + r * P1 * WP, k1, v);
+        cf* xr = xs + r * XS;
+        static_for<0, P2>([&](auto cc) {
+          constexpr int k2 = decltype(cc)::value;
+          const int xi = xs_index(k1 + P1 * k2, H, mlim);
+          if (xi >= 0) xr[xi] = v[k2];
+        });
+      }
+    }
+    __syncwarp();
+    // real split -> staging tile
+    for (int r = 0; r < nv; ++r) {
+      const int rr = g * RW + r;  // row inside the 32-row tile
+      for (int m = lane; m < mlim; m += 32) {
+        cf X = r2c_split_xs(xs + r * XS, tw2, H, mlim, m);
+        const float ms = mscale[m];
+        X.x *= ms * sc_in;
+        X.y *= ms * sc_in;
+        if (m == 0) X.x += ms * sh_in * (float)NLON;
+        if (zero_imag && (m == 0 || m == H)) X.y = 0.0f;
+        ostage[(2 * m) * OST2 + rr] = X.x;
+        ostage[(2 * m + 1) * OST2 + rr] = X.y;
+      }
+    }
+    fence_proxy_async();
+    __syncwarp();
+    nv = nv_next;
+  }
+  __syncthreads();
+
+  const int nvalid = min(ROWS_PER_TILE2, nlat - k0);
+  for (int seg = warp; seg < 2 * mlim; seg += nw) {
+    const int m = seg >> 1, ri = seg & 1;
+    const float v = (lane < nvalid) ? ostage[seg * OST2 + lane] : 0.0f;
+    Xt[(((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane] = v;
+  }
+}
+
+template <int P1, int P2, int RW>
+__global__ void __launch_bounds__(256, 1)
+irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __restrict__ g_tw,
+               const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ skip,
+               const float* __restrict__ out_scale, double* __restrict__ stats, int nlat, int mlim, int kpad, int C,
+               int act_gelu) {
+  constexpr int H = P1 * P2, NLON = 2 * H, WP = WorkPitch<P2>::value;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int nw = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bc = blockIdx.y;
+  const int b = bc / C, c = bc - b * C;
+  const int k0 = blockIdx.x * ROWS_PER_TILE2;
+
+  cf* tw = reinterpret_cast<cf*>(smem_raw);
+  cf* tw2 = tw + H;
+  float* istage = reinterpret_cast<float*>(tw2 + (mlim + 1));
+  size_t off = (size_t)(reinterpret_cast<unsigned char*>(istage + 2 * mlim * OST2) - smem_raw);
+  off = (off + 15) & ~(size_t)15;
+  double* red = reinterpret_cast<double*>(smem_raw + off);
+  off += sizeof(double) * 2 * nw;
+  off = (off + 127) & ~(size_t)127;
+  const size_t per_warp = sizeof(cf) * ((size_t)RW * P1 * WP + (size_t)RW * H);
+  unsigned char* wbase = smem_raw + off + (size_t)warp * ((per_warp + 127) & ~(size_t)127);
+  cf* work = reinterpret_cast<cf*>(wbase);
+  cf* outb = work + RW * P1 * WP;
+
+  for (int i = threadIdx.x; i < H; i += blockDim.x) tw[i] = g_tw[i];
+  for (int i = threadIdx.x; i <= mlim; i += blockDim.x) tw2[i] = g_tw2[i];
+  const int nvalid = min(ROWS_PER_TILE2, nlat - k0);
+  for (int seg = warp; seg < 2 * mlim; seg += nw) {
+    const int m = seg >> 1, ri = seg & 1;
+    float v = 0.0f;
+    if (lane < nvalid) v = Yt[(((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane] * mscale[m];
+    istage[seg * OST2 + lane] = v;
+  }
+  __syncthreads();
+
+  const float osc = out_scale ? out_scale[bc] : 1.0f;
+  float lsum = 0.0f, lsq = 0.0f;
+  constexpr int NGROUPS = ROWS_PER_TILE2 / RW;
+  const int iters = (NGROUPS + nw - 1) / nw;
+  for (int it = 0; it < iters; ++it) {
+    const int g = warp + it * nw;
+    if (g >= NGROUPS) break;
+    int nv = nlat - (k0 + g * RW);
+    if (nv <= 0) break;
+    if (nv > RW) nv = RW;
+
+    // Hermitian merge into the [n1][n2] work matrix (zero beyond mlim; Im dropped at bins 0 and H)
+    for (int r = 0; r < nv; ++r) {
+      const int rr = g * RW + r;
+      auto Xh = [&](int q) -> cf {
+        if (q >= mlim) return cf{0.0f, 0.0f};
+        cf v{istage[(2 * q) * OST2 + rr], istage[(2 * q + 1) * OST2 + rr]};
+        if (q == 0 || q == H) v.y = 0.0f;
+        return v;
+      };
+      cf* wr = work + r * P1 * WP;
+      for (int k = lane; k < H; k += 32) {
+        const int kk = H - k;
+        cf o{0.0f, 0.0f};
+        if (k < mlim || kk < mlim) {
+          cf w;
+          if (k <= mlim) w = tw2[k];
+          else { w = tw2[kk]; w.x = -w.x; }
+          o = c2r_merge(Xh(k), Xh(kk), w);
+        }
+        const int n1 = k / P2;
+        wr[n1 * WP + (k - n1 * P2)] = o;
+      }
+    }
+    __syncwarp();
+    for (int t = lane; t < RW * P2; t += 32) {
+      const int r = t / P2, n2 = t - r * P2;
+      if (r < nv) fft2d_step1<P1, P2, +1>(work + r * P1 * WP, WP, work + r * P1 * WP, tw, n2);
+    }
+    __syncwarp();
+    for (int t = lane; t < RW * P1; t += 32) {
+      const int r = t / P1, k1 = t - r * P1;
+      if (r < nv) {
+        cf v[P2];
+        fft2d_step2<P1, P2, +1>(work + r * P1 * WP, k1, v);
+        cf* orow = outb + r * H;
+        static_for<0, P2>([&](auto cc) {
+          constexpr int k2 = decltype(cc)::value;
+          orow[k1 + P1 * k2] = v[k2];
+        });
+      }
+    }
+    __syncwarp();
+    // epilogue: the row buffer is the output row in natural float order
+    for (int r = 0; r < nv; ++r) {
+      const size_t goff = ((size_t)bc * nlat + (k0 + g * RW + r)) * NLON;
+      const float4* row4 = reinterpret_cast<const float4*>(outb + r * H);
+      const float4* skip4 = skip ? reinterpret_cast<const float4*>(skip + goff) : nullptr;
+      float4* y4 = reinterpret_cast<float4*>(y + goff);
+      for (int i = lane; i < (NLON >> 2); i += 32) {
+        float4 v = row4[i];
+        v.x *= osc; v.y *= osc; v.z *= osc; v.w *= osc;
+        if (skip4) { const float4 s = skip4[i]; v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w; }
+        if (act_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+        lsum += (v.x + v.y) + (v.z + v.w);
+        lsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+        y4[i] = v;
+      }
+    }
+    __syncwarp();
+  }
+
+  if (stats) {
+    double ds = (double)lsum, dq = (double)lsq;
+    for (int o = 16; o > 0; o >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    if (lane == 0) { red[2 * warp] = ds; red[2 * warp + 1] = dq; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0.0, q = 0.0;
+      for (int w = 0; w < nw; ++w) { s += red[2 * w]; q += red[2 * w + 1]; }
+      atomicAdd(&stats[2 * bc], s);
+      atomicAdd(&stats[2 * bc + 1], q);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+static bool pick_warps2(size_t fixed, size_t per_warp, int max_groups, int* nwarps, size_t* total) {
+  for (int nw = 8; nw >= 1; nw >>= 1) {
+    if (nw > max_groups && nw > 1) continue;
+    const size_t t = fixed + 512 + (size_t)nw * (((per_warp + 127) & ~(size_t)127) + 32);
+    if (t <= 227 * 1024) { *nwarps = nw; *total = t; return true; }
+  }
+  return false;
+}
+
+template <int P1, int P2, int RW>
+static int launch_fwd(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
+                      const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st) {
+  constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
+  const int XS = xs_size(H, p->mlim);
+  const size_t fixed = sizeof(cf) * (H + p->mlim + 1) + sizeof(float) * 2 * p->mlim * OST2;
+  const size_t per_warp = sizeof(cf) * ((size_t)2 * RW * H + (size_t)RW * P1 * WP + (size_t)RW * XS);
+  int nw; size_t smem;
+  if (!pick_warps2(fixed, per_warp, ROWS_PER_TILE2 / RW, &nw, &smem))
+    return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT does not fit in shared memory");
+  auto kern = rfft2d_kernel<P1, P2, RW>;
+  MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((p->nlat + ROWS_PER_TILE2 - 1) / ROWS_PER_TILE2, B * C);
+  kern<<<grid, nw * 32, smem, st>>>(x, Xt, reinterpret_cast<const cf*>(p->d_tw), reinterpret_cast<const cf*>(p->d_tw2),
+                                    mscale, in_scale, in_shift, p->nlat, p->mlim, p->kpad, C, zero_imag);
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+template <int P1, int P2, int RW>
+static int launch_inv(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
+                      const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st) {
+  constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
+  const size_t fixed = sizeof(cf) * (H + p->mlim + 1) + sizeof(float) * 2 * p->mlim * OST2 + 16 * 8;
+  const size_t per_warp = sizeof(cf) * ((size_t)RW * P1 * WP + (size_t)RW * H);
+  int nw; size_t smem;
+  if (!pick_warps2(fixed, per_warp, ROWS_PER_TILE2 / RW, &nw, &smem))
+    return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT does not fit in shared memory");
+  auto kern = irfft2d_kernel<P1, P2, RW>;
+  MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((p->nlat + ROWS_PER_TILE2 - 1) / ROWS_PER_TILE2, B * C);
+  kern<<<grid, nw * 32, smem, st>>>(Yt, y, reinterpret_cast<const cf*>(p->d_tw), reinterpret_cast<const cf*>(p->d_tw2),
+                                    mscale, skip, out_scale, stats, p->nlat, p->mlim, p->kpad, C, act_gelu);
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+bool fft2d_supported(int nlon) { return nlon == 1440 || nlon == 240 || nlon == 2880; }
+
+int launch_rfft2d(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
+                  const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st) {
+  switch (p->nlon) {
+    case 1440: return launch_fwd<24, 30, 1>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
+    case 240: return launch_fwd<15, 8, 4>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
+    case 2880: return launch_fwd<36, 40, 1>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
+    default: return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT: unsupported nlon");
+  }
+}
+
+int launch_irfft2d(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
+                   const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st) {
+  switch (p->nlon) {
+    case 1440: return launch_inv<24, 30, 1>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
+    case 240: return launch_inv<15, 8, 4>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
+    case 2880: return launch_inv<36, 40, 1>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
+    default: return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT: unsupported nlon");
+  }
+}
+
+}  // namespace msfno

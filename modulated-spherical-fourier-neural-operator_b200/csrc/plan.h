@@ -88,4 +88,11 @@ bool gemm_tc_supported(const GemmLaunch& g);
 int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
                    int round_tf32, cudaStream_t st);
 
+// four-step in-register FFT kernels (fft2d.cu) for nlon in {240, 1440, 2880}
+bool fft2d_supported(int nlon);
+int launch_rfft2d(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
+                  const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st);
+int launch_irfft2d(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
+                   const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st);
+
 }  // namespace msfno
