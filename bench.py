@@ -301,16 +301,16 @@ def run_ours(args):
         launches = _lib.lib.msfno_launch_count() - l0
         ms_dev = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop() if rank == 0 else None
-        # ---- end-to-end leg: host buffers in, host buffers out -----------------------------------
-        for _ in range(2):
-            x_dev.copy_(x_host, non_blocking=True)
-            y_host.copy_(net(x_dev), non_blocking=True)
+        # ---- end-to-end leg: host buffers in, host buffers out, through the public HostPipeline API ----------
+        import msfno_b200
+        pipe = msfno_b200.HostPipeline(net, dev)
+        xs = [x_host, x_host.clone().pin_memory()]
+        ys = [y_host, torch.empty_like(y_host).pin_memory()]
+        pipe.run([xs[i % 2] for i in range(3)], [ys[i % 2] for i in range(3)])
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            x_dev.copy_(x_host, non_blocking=True)
-            y_host.copy_(net(x_dev), non_blocking=True)
+        pipe.run([xs[i % 2] for i in range(args.steps)], [ys[i % 2] for i in range(args.steps)])
         e1.record()
         sync_all()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))

@@ -104,6 +104,21 @@ int msfno_isht_fwd(msfno_plan* plan, const float* coef_cm, float* y, float* ws, 
 /* adjoint: gy [B][C][nlat][nlon] -> g_cm (CM layout). */
 int msfno_isht_bwd(msfno_plan* plan, const float* gy, float* g_cm, float* ws, int B, int C, void* stream);
 
+/* ---- stage-level entry points for the spatially sharded SHT (BASELINE config 5) ----------
+ * The reference has no distributed transform (DDP only, main.py:39-49); these expose the two halves of
+ * msfno_sht_* / msfno_isht_* separately so a lat<->m all-to-all can sit between them.
+ * msfno_fft_stage: longitude transform only, on a plan whose nlat is the LOCAL latitude count.
+ *   inverse = 0: x [B][C][nlat][nlon] -> Xt [B][mlim][2C][kpad]   (adjoint != 0: adjoint of irfft instead)
+ *   inverse = 1: Yt -> y                                           (adjoint != 0: adjoint of rfft instead)
+ * msfno_legendre_stage: Legendre contraction for the azimuthal orders [m_lo, m_hi) only; the lat<->m buffer
+ *   holds just those orders ([B][m_hi-m_lo][2C][kpad]) and the PM / CM coefficient buffers just their packed
+ *   positions [poff[m_lo], poff[m_hi]).  kind: 0 analysis (Xt -> PM), 1 its adjoint (PM -> Xt),
+ *   2 synthesis (CM -> Yt), 3 its adjoint (Yt -> CM). */
+int msfno_fft_stage(msfno_plan* plan, int inverse, int adjoint, const float* src, float* dst, int B, int C,
+                    void* stream);
+int msfno_legendre_stage(msfno_plan* plan, int kind, const float* src, float* dst, int m_lo, int m_hi, int B,
+                         int C, void* stream);
+
 /* ---- coefficient layout changes (public boundary of RealSHT / InverseRealSHT) ------------
  * replaces: the zeros()+slice-assign in RealSHT.forward, view_as_real/complex shuffles and the
  * tril gather/scatter of SpectralConvS2.forward (layers.py:406-413). */

@@ -17,10 +17,11 @@ from .layers import MLP, ComplexReLU, DropPath, SpectralAttentionS2, SpectralCon
 from .sfnonet import (FeedForward, FiLM, Film_wrapper, FourierNeuralOperatorBlock, FourierNeuralOperatorBlock_Filmed,
                       FourierNeuralOperatorNet, FourierNeuralOperatorNet_Filmed, SpectralFilterLayer)
 from . import harmonics
+from .pipeline import HostPipeline
 
 __all__ = [
     "RealSHT", "InverseRealSHT", "quadrature", "legendre", "harmonics", "set_precision", "get_precision",
     "SpectralConvS2", "SpectralAttentionS2", "ComplexReLU", "MLP", "DropPath", "trunc_normal_",
     "SpectralFilterLayer", "FiLM", "FourierNeuralOperatorBlock", "FourierNeuralOperatorBlock_Filmed",
-    "FourierNeuralOperatorNet", "FourierNeuralOperatorNet_Filmed", "Film_wrapper", "FeedForward",
+    "FourierNeuralOperatorNet", "FourierNeuralOperatorNet_Filmed", "Film_wrapper", "FeedForward", "HostPipeline",
 ]

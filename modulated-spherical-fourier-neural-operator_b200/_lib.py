@@ -56,6 +56,8 @@ _SIGS = {
     "msfno_sht_bwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P]),
     "msfno_isht_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P, c_int, _P, _P]),
     "msfno_isht_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
+    "msfno_fft_stage": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P]),
+    "msfno_legendre_stage": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "msfno_coef_relayout": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     "msfno_specconv_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "msfno_specconv_bwd_x": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),

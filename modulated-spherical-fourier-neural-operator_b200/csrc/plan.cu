@@ -115,19 +115,27 @@ static int upload(T** dptr, const std::vector<T>& h) {
   return MSFNO_OK;
 }
 
-int plan_groups(msfno_plan* p, int kind, int B, int C, const GemmGroup** out, int* ngroups) {
+int plan_groups(msfno_plan* p, int kind, int B, int C, const GemmGroup** out, int* ngroups, int m_lo, int m_hi) {
+  // orders [m_lo, m_hi) only (spatially sharded SHT: a rank owns a contiguous range of azimuthal orders); the
+  // lat<->m intermediate and the coefficient buffers are then indexed relative to m_lo / poff[m_lo].
+  if (m_hi < 0 || m_hi > p->mlim) m_hi = p->mlim;
+  if (m_lo < 0) m_lo = 0;
+  const int mloc = m_hi - m_lo;
   std::lock_guard<std::mutex> lk(p->mu);
-  auto key = std::make_pair(kind, std::make_pair(B, C));
+  std::vector<int> key = {kind, B, C, m_lo, m_hi};
   auto it = p->groups.find(key);
   if (it == p->groups.end()) {
-    const long long C2 = 2 * C, kpad = p->kpad, P = p->P, Lj = p->Lj, nlat = p->nlat;
-    std::vector<GemmGroup> h((size_t)B * p->mlim);
+    const long long C2 = 2 * C, kpad = p->kpad, Lj = p->Lj, nlat = p->nlat;
+    const long long p0 = (m_lo < p->mlim) ? p->h_poff[m_lo] : p->P;
+    const long long p1 = (m_hi < p->mlim) ? p->h_poff[m_hi] : p->P;
+    const long long Ploc = p1 - p0;
+    std::vector<GemmGroup> h((size_t)B * (mloc > 0 ? mloc : 0));
     for (int b = 0; b < B; ++b)
-      for (int m = 0; m < p->mlim; ++m) {
+      for (int m = m_lo; m < m_hi; ++m) {
         GemmGroup g{};
-        const long long xt = ((long long)b * p->mlim + m) * C2 * kpad;   // lat<->m intermediate
-        const long long pm = ((long long)b * P + p->h_poff[m]) * C2;     // PM coefficient rows of order m
-        const long long cm = (long long)b * C2 * P + p->h_poff[m];       // CM coefficient columns of order m
+        const long long xt = ((long long)b * mloc + (m - m_lo)) * C2 * kpad;       // lat<->m intermediate
+        const long long pm = ((long long)b * Ploc + p->h_poff[m] - p0) * C2;       // PM coefficient rows of order m
+        const long long cm = (long long)b * C2 * Ploc + p->h_poff[m] - p0;         // CM coefficient columns of order m
         const int len = p->h_plen4[m];
         switch (kind) {
           case GK_ANALYSIS:      g = GemmGroup{(long long)m * Lj * kpad, xt, pm, len, (int)C2, (int)nlat, 0}; break;
@@ -135,7 +143,7 @@ int plan_groups(msfno_plan* p, int kind, int B, int C, const GemmGroup** out, in
           case GK_SYNTHESIS:     g = GemmGroup{cm, (long long)m * nlat * Lj, xt, (int)C2, (int)nlat, len, 0}; break;
           default:               g = GemmGroup{xt, (long long)m * nlat * Lj, cm, (int)C2, len, (int)nlat, 0}; break;
         }
-        h[(size_t)b * p->mlim + m] = g;
+        h[(size_t)b * mloc + (m - m_lo)] = g;
       }
     GemmGroup* d = nullptr;
     int rc = upload(&d, h);
@@ -143,7 +151,7 @@ int plan_groups(msfno_plan* p, int kind, int B, int C, const GemmGroup** out, in
     it = p->groups.emplace(key, d).first;
   }
   *out = it->second;
-  *ngroups = B * p->mlim;
+  *ngroups = B * (mloc > 0 ? mloc : 0);
   return MSFNO_OK;
 }
 

@@ -46,14 +46,14 @@ struct msfno_plan {
   int32_t* d_flag = nullptr;          // table validation flag
   // grouped-GEMM descriptors cached per (kind, B, C)
   std::mutex mu;
-  std::map<std::pair<int, std::pair<int, int>>, msfno::GemmGroup*> groups;
+  std::map<std::vector<int>, msfno::GemmGroup*> groups;  // key: kind, B, C, m_lo, m_hi
 };
 
 namespace msfno {
 
 enum GroupKind { GK_ANALYSIS = 0, GK_ANALYSIS_ADJ = 1, GK_SYNTHESIS = 2, GK_SYNTHESIS_ADJ = 3 };
 // returns a device array of B*mlim groups (cached)
-int plan_groups(msfno_plan* p, int kind, int B, int C, const GemmGroup** out, int* ngroups);
+int plan_groups(msfno_plan* p, int kind, int B, int C, const GemmGroup** out, int* ngroups, int m_lo = 0, int m_hi = -1);
 
 int launch_rfft_trunc(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
                       const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st);

@@ -10,10 +10,11 @@
 using namespace msfno;
 
 static int legendre_gemm(msfno_plan* p, int kind, const float* A, long long lda, int a_k, const float* B, long long ldb,
-                         int b_k, float* D, long long ldd, int maxM, int maxN, int Bsz, int C, cudaStream_t st) {
+                         int b_k, float* D, long long ldd, int maxM, int maxN, int Bsz, int C, cudaStream_t st,
+                         int m_lo = 0, int m_hi = -1) {
   const GemmGroup* groups = nullptr;
   int ng = 0;
-  int rc = plan_groups(p, kind, Bsz, C, &groups, &ng);
+  int rc = plan_groups(p, kind, Bsz, C, &groups, &ng, m_lo, m_hi);
   if (rc) return rc;
   GemmLaunch g{};
   g.A = A; g.B = B; g.D = D;
@@ -71,6 +72,44 @@ int msfno_isht_bwd(msfno_plan* p, const float* gy, float* g_cm, float* ws, int B
   if (rc) return rc;
   // g_cm[b][ch][poff[m]+j] = sum_k gYt[b][m][ch][k] * tab_kl[m][k][j]
   return legendre_gemm(p, GK_SYNTHESIS_ADJ, ws, p->kpad, 1, p->d_tab_kl, p->Lj, 0, g_cm, p->P, 2 * C, p->h_plen4[0], B, C, st);
+}
+
+// ---- stage-level entry points (spatially sharded SHT) -------------------------------------
+int msfno_fft_stage(msfno_plan* p, int inverse, int adjoint, const float* src, float* dst, int B, int C, void* stream) {
+  if (!p || !src || !dst || B < 1 || C < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "fft_stage: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!inverse)  // x -> Xt : RealSHT longitude stage, or (adjoint) the adjoint of irfft
+    return launch_rfft_trunc(p, src, dst, adjoint ? p->d_scale_irfft_adj : p->d_scale_rfft, adjoint ? 1 : 0, nullptr, nullptr,
+                             B, C, st);
+  return launch_irfft_trunc(p, src, dst, adjoint ? p->d_scale_rfft_adj : p->d_scale_irfft, nullptr, nullptr, 0, nullptr, B,
+                            C, st);
+}
+
+int msfno_legendre_stage(msfno_plan* p, int kind, const float* src, float* dst, int m_lo, int m_hi, int B, int C,
+                         void* stream) {
+  if (!p || !src || !dst || B < 1 || C < 1 || m_lo < 0 || m_hi > p->mlim || m_lo >= m_hi)
+    return record_error(MSFNO_ERR_BAD_SHAPE, "legendre_stage: bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long p0 = p->h_poff[m_lo];
+  const long long p1 = (m_hi < p->mlim) ? p->h_poff[m_hi] : p->P;
+  const long long Ploc = p1 - p0;
+  const int maxlen = p->h_plen4[m_lo];
+  switch (kind) {
+    case GK_ANALYSIS:
+      if (!p->d_tab_lk) return record_error(MSFNO_ERR_BAD_STATE, "legendre_stage: analysis table not set");
+      return legendre_gemm(p, kind, p->d_tab_lk, p->kpad, 1, src, p->kpad, 1, dst, 2 * C, maxlen, 2 * C, B, C, st, m_lo, m_hi);
+    case GK_ANALYSIS_ADJ:
+      if (!p->d_tab_lk) return record_error(MSFNO_ERR_BAD_STATE, "legendre_stage: analysis table not set");
+      return legendre_gemm(p, kind, src, 2 * C, 0, p->d_tab_lk, p->kpad, 0, dst, p->kpad, 2 * C, p->nlat, B, C, st, m_lo, m_hi);
+    case GK_SYNTHESIS:
+      if (!p->d_tab_kl) return record_error(MSFNO_ERR_BAD_STATE, "legendre_stage: synthesis table not set");
+      return legendre_gemm(p, kind, src, Ploc, 1, p->d_tab_kl, p->Lj, 1, dst, p->kpad, 2 * C, p->nlat, B, C, st, m_lo, m_hi);
+    case GK_SYNTHESIS_ADJ:
+      if (!p->d_tab_kl) return record_error(MSFNO_ERR_BAD_STATE, "legendre_stage: synthesis table not set");
+      return legendre_gemm(p, kind, src, p->kpad, 1, p->d_tab_kl, p->Lj, 0, dst, Ploc, 2 * C, maxlen, B, C, st, m_lo, m_hi);
+    default:
+      return record_error(MSFNO_ERR_BAD_SHAPE, "legendre_stage: bad kind");
+  }
 }
 
 }  // extern "C"
