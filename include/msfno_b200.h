@@ -75,6 +75,9 @@ long msfno_plan_query(const msfno_plan* plan, int what);
  * (RealSHT.weights); analysis == 0 -> used by isht_fwd/bwd (InverseRealSHT.pct).
  * Entries with l < m must be zero (they are by construction); otherwise MSFNO_ERR_UNSUPPORTED. */
 int msfno_plan_set_table(msfno_plan* plan, const float* table, int analysis, void* stream);
+/* precision tier of the Legendre contractions of the FORWARD transforms (adjoints always run fp32):
+ * MSFNO_PREC_FP32 (default) or MSFNO_PREC_TF32 (tcgen05 tensor-core GEMM). */
+int msfno_plan_set_precision(msfno_plan* plan, int precision);
 /* host copies of the packed-position maps: poff[mmax] and n2p[ntril] (reference tril order) */
 int msfno_plan_get_maps(const msfno_plan* plan, int32_t* poff_host, int32_t* n2p_host);
 
@@ -177,6 +180,19 @@ int msfno_norm_film_coeffs(const double* stats, const float* nw, const float* nb
 /* y[plane][:] = A[plane]*x[plane][:] + S[plane] */
 int msfno_plane_affine(const float* x, const float* A, const float* S, float* y, int planes, long HW,
                        void* stream);
+
+/* ---- 8(f) N2: 1x1 convolution (NCHW) with fused epilogue ------------------------------------------------
+ * replaces: nn.Conv2d(cin, cout, 1) + bias + nn.GELU + residual/pos_embed add + torch.cat of the big skip
+ *           (MSFNO/Models/sfno/layers.py:161-168; sfnonet.py:184-185,232,249,671,682-684).
+ *   y[b][o][p] = act( sum_c w[o][c] x[b][c][p] + sum_c w2[o][c] x2[b][c][p] + bias[o] ) + add[b][o][p]
+ * x: [B][Cin][HW] with batch stride x_bstride (floats); w: [Cout][ldw] row-major, ldw >= Cin, ldw % 4 == 0, columns
+ * >= Cin zero; w_bstride != 0 selects per-sample weights (InstanceNorm/FiLM affine folded into the conv).
+ * x2 / w2 (optional): second input accumulated into the same output (the decoder's concat of x and the big skip).
+ * bias (optional, [Cout], bias_bstride 0 or Cout), add (optional, [Cout][HW], add_bstride 0 or Cout*HW). */
+int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const float* w, long ldw, long w_bstride,
+                      const float* x2, long x2_bstride, int Cin2, const float* w2, long ldw2, const float* bias,
+                      long bias_bstride, const float* add, long add_bstride, float* y, int B, int Cout, long HW,
+                      int act_gelu, int precision, void* stream);
 
 /* ---- generic K-major batched GEMM used by the Legendre and MLP stages ---------------------
  * D[M][N] = A[M][K] * B[N][K]^T (row-major D, ldd), optional ReLU on even columns.

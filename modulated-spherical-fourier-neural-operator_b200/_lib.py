@@ -50,6 +50,7 @@ _SIGS = {
     "msfno_plan_destroy": (c_int, [_P]),
     "msfno_plan_query": (c_long, [_P, c_int]),
     "msfno_plan_set_table": (c_int, [_P, _P, c_int, _P]),
+    "msfno_plan_set_precision": (c_int, [_P, c_int]),
     "msfno_plan_get_maps": (c_int, [_P, _P, _P]),
     "msfno_sht_ws_floats": (c_size_t, [_P, c_int, c_int]),
     "msfno_sht_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, _P]),
@@ -71,6 +72,8 @@ _SIGS = {
     "msfno_plane_stats": (c_int, [_P, _P, c_int, c_long, _P]),
     "msfno_norm_film_coeffs": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, _P, _P, c_int, c_int, c_long, _P]),
     "msfno_plane_affine": (c_int, [_P, _P, _P, _P, c_int, c_long, _P]),
+    "msfno_conv1x1_fwd": (c_int, [_P, c_long, c_int, _P, c_long, c_long, _P, c_long, c_int, _P, c_long, _P, c_long, _P, c_long, _P,
+                          c_int, c_int, c_long, c_int, c_int, _P]),
     "msfno_gemm_nt": (c_int, [_P, c_long, _P, c_long, _P, c_long, c_int, c_int, c_int, c_int, c_int, _P]),
 }
 

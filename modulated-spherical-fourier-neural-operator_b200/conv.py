@@ -1,0 +1,51 @@
+"""1x1-convolution front end of msfno_conv1x1_fwd (inference path of the channel MLPs).
+
+Mirrors what the reference does with nn.Conv2d(.., 1) + bias + nn.GELU + residual adds + torch.cat
+(/root/reference MSFNO/Models/sfno/layers.py:161-168, sfnonet.py:232,249,671,682-684) in ONE kernel launch."""
+import torch
+
+from . import _lib
+from . import precision as _precision
+from ._lib import check, lib, ptr
+
+_pad_cache = {}
+
+
+def padded_weight(weight):
+    """[Cout, Cin, 1, 1] (or [Cout, Cin]) -> contiguous [Cout, ceil4(Cin)] with zero padding, cached per version."""
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device))
+    hit = _pad_cache.get(key)
+    if hit is not None:
+        return hit
+    w2 = weight.detach().reshape(weight.shape[0], -1).float()
+    cin = w2.shape[1]
+    ld = (cin + 3) // 4 * 4
+    if ld != cin:
+        w2 = torch.nn.functional.pad(w2, (0, ld - cin))
+    w2 = w2.contiguous()
+    if len(_pad_cache) > 256:
+        _pad_cache.clear()
+    _pad_cache[key] = w2
+    return w2
+
+
+def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, cin2=0, per_sample_w=False,
+            per_sample_bias=False):
+    """y = act(conv1x1(x, w) [+ conv1x1(x2, w2)] + bias) + add   for contiguous NCHW fp32 CUDA tensors.
+    w: [Cout, ld] (or [B, Cout, ld] with per_sample_w) zero-padded rows; bias [Cout] (or [B, Cout]);
+    add: [B or 1, Cout, H, W]."""
+    B, _, H, W = x.shape
+    HW = H * W
+    cout = w.shape[-2]
+    y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
+    prec = _lib.PREC_TF32 if _precision.get_precision() == "tf32" else _lib.PREC_FP32
+    add_bs = 0
+    if add is not None:
+        add = add.contiguous()
+        add_bs = cout * HW if add.shape[0] == B and B > 1 else (0 if add.shape[0] == 1 else cout * HW)
+    check(lib.msfno_conv1x1_fwd(ptr(x), x.shape[1] * HW, cin, ptr(w), w.shape[-1], (cout * w.shape[-1]) if per_sample_w else 0,
+                                ptr(x2), (x2.shape[1] * HW) if x2 is not None else 0, cin2, ptr(w2),
+                                w2.shape[-1] if w2 is not None else 0, ptr(bias), cout if per_sample_bias else 0, ptr(add),
+                                add_bs, ptr(y), B, cout, HW, 1 if act_gelu else 0, prec,
+                                torch.cuda.current_stream().cuda_stream), "conv1x1_fwd")
+    return y

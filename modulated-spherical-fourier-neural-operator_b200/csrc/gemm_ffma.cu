@@ -111,10 +111,25 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(GemmLaunch g, int til
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
   TileRegs ra, rb;
-  const int nk = (K + BKT - 1) / BKT;
+  // k-tiles of the first operand pair followed by those of the optional second pair (same majorness)
+  const int nk1 = (K + BKT - 1) / BKT;
+  const int K2 = g.A2 ? g.K2 : 0;
+  const int nk = nk1 + (K2 + BKT - 1) / BKT;
+  const float* __restrict__ A2 = g.A2 ? g.A2 + blockIdx.y * g.sa2 : nullptr;
+  const float* __restrict__ B2 = g.B2 ? g.B2 + blockIdx.y * g.sb2 : nullptr;
+  const bool vecA2 = A2 && (((g.sa2 | g.lda2) & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.A2) & 15) == 0);
+  const bool vecB2 = B2 && (((g.sb2 | g.ldb2) & 3) == 0) && ((reinterpret_cast<uintptr_t>(g.B2) & 15) == 0);
+  auto load_pair = [&](int kt) {
+    if (kt < nk1) {
+      load_tile<A_KMAJOR>(ra, A, g.lda, m0, kt * BKT, M, K, vecA, tid);
+      load_tile<B_KMAJOR>(rb, B, g.ldb, n0, kt * BKT, N, K, vecB, tid);
+    } else {
+      load_tile<A_KMAJOR>(ra, A2, g.lda2, m0, (kt - nk1) * BKT, M, K2, vecA2, tid);
+      load_tile<B_KMAJOR>(rb, B2, g.ldb2, n0, (kt - nk1) * BKT, N, K2, vecB2, tid);
+    }
+  };
   if (nk > 0) {
-    load_tile<A_KMAJOR>(ra, A, g.lda, m0, 0, M, K, vecA, tid);
-    load_tile<B_KMAJOR>(rb, B, g.ldb, n0, 0, N, K, vecB, tid);
+    load_pair(0);
     store_tile<A_KMAJOR>(ra, As[0], tid);
     store_tile<B_KMAJOR>(rb, Bs[0], tid);
   }
@@ -122,10 +137,7 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(GemmLaunch g, int til
 
   for (int kt = 0; kt < nk; ++kt) {
     const int cur = kt & 1;
-    if (kt + 1 < nk) {
-      load_tile<A_KMAJOR>(ra, A, g.lda, m0, (kt + 1) * BKT, M, K, vecA, tid);
-      load_tile<B_KMAJOR>(rb, B, g.ldb, n0, (kt + 1) * BKT, N, K, vecB, tid);
-    }
+    if (kt + 1 < nk) load_pair(kt + 1);
 #pragma unroll
     for (int k = 0; k < BKT; ++k) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[cur][k][ty * 4]);
@@ -156,6 +168,17 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(GemmLaunch g, int til
       const int gn = n0 + hh * 64 + tx * 4;
       if (gn >= N) continue;
       float v[4] = {acc[i][hh * 4 + 0], acc[i][hh * 4 + 1], acc[i][hh * 4 + 2], acc[i][hh * 4 + 3]};
+      if (g.bias) {
+        const float bv = g.bias[blockIdx.y * g.sbias + gm];
+        v[0] += bv; v[1] += bv; v[2] += bv; v[3] += bv;
+      }
+      if (g.act_gelu) { v[0] = gelu_erf(v[0]); v[1] = gelu_erf(v[1]); v[2] = gelu_erf(v[2]); v[3] = gelu_erf(v[3]); }
+      if (g.add) {
+        const float* ap = g.add + blockIdx.y * g.sadd + (long long)gm * g.ldadd + gn;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (gn + j < N) v[j] += ap[j];
+      }
       if (g.relu_even) {
         v[0] = fmaxf(v[0], 0.f);
         v[2] = fmaxf(v[2], 0.f);

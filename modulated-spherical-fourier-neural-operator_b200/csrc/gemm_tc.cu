@@ -1,17 +1,20 @@
 // Grouped TF32 GEMM on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) issued by one thread,
 // operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), fp32 accumulators in
 // TMEM, read back with tcgen05.ld for the epilogue.  This is the "tensor-core tier" (<= 2e-3 rel-L2) engine of
-// the spectral complex MLP and of the Legendre contractions.
+// the spectral complex MLP, of the Legendre contractions and of the 1x1-conv MLPs either side of the path.
 //
-// replaces: the cuBLAS GEMMs torch.einsum dispatches to in /root/reference
-//   MSFNO/Models/sfno/contractions.py:132-137 ("bixy,io->boxy") and in torch_harmonics' Legendre einsums.
+// replaces: the cuBLAS / cuDNN GEMMs behind torch.einsum and nn.Conv2d(1x1) in /root/reference
+//   MSFNO/Models/sfno/contractions.py:132-137 ("bixy,io->boxy"), torch_harmonics' Legendre einsums and
+//   MSFNO/Models/sfno/layers.py:161-168 (MLP.fwd).
 //
-// D[M][N] = A[M][K] * B[N][K]^T, both operands K-major fp32 in global memory, described to TMA as plain 2-D
-// tensors [rows][ld]; a group selects its sub-problem by (row, column) coordinates, so one tensor map per
-// operand serves all groups of a launch.  Out-of-range rows/columns are zero-filled by TMA.
+// D[M][N] = A[M][K] * op(B) (+ A2 * op(B2)),  D = act(D + bias[row]) + add
+//   A  : K-major  [M][lda]                      (weights / tables)
+//   B  : K-major  [N][ldb]   (B_MN = false)     or   MN-major [K][ldb], N contiguous (B_MN = true: NCHW activations)
+// Operands are described to TMA as plain 2-D tensors; a group selects its sub-problem by (row, column)
+// coordinates, so one tensor map per operand serves all groups of a launch.  Out-of-range boxes are zero-filled.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator,
-// warps 4-7 = epilogue (TMEM lane quarter q = warp % 4).  BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32 fp32
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator; afterwards all
+// 8 warps drain the accumulator (TMEM lane quarter q = warp % 4, column half = warp / 4).  BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32 fp32
 // (= one 128-byte swizzle span = 4 UMMA K-steps of 8).
 #include <cuda.h>
 
@@ -22,7 +25,7 @@
 
 namespace msfno {
 
-static constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 6;
+static constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;  // 3 x 32 KB stages -> two CTAs per SM (one's epilogue overlaps the other's main loop)
 static constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 static constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;  // 16 KB
 static constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -37,7 +40,12 @@ struct TcParams {
   int use_single;
   int relu_even;
   int round_tf32;
-  int tilesN;
+  int tilesN, tilesM;
+  const float* bias; long long sbias;
+  const float* add; long long ldadd, sadd;
+  int act_gelu;
+  long long lda2, ldb2, sa2, sb2;
+  int K2;
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
@@ -81,14 +89,20 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// K-major, 128-byte swizzle: rows of 128 B, 8-row atoms of 1024 B (SBO), LBO unused (=1), descriptor version 1
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
+// Shared-memory matrix descriptor, 128-byte swizzle, descriptor version 1.
+//   K-major : rows of 128 B (32 tf32 along K), 8-row atoms of 1024 B -> SBO = 1024, LBO unused (= 1)
+//   MN-major: k-rows of 128 B (32 tf32 along N), 8-k-row atoms of 1024 B -> SBO = 1024 (next 8 k),
+//             LBO = byte distance between consecutive 32-element N blocks
+//   layout_type: 2 = SWIZZLE_128B (16-byte swizzle atomicity), 1 = SWIZZLE_128B_BASE32B (32-byte atomicity: the only
+//   layout the tensor core accepts for MN-major 32-bit operands; its atoms are 4 k-rows of 128 B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 __device__ __forceinline__ float round_to_tf32(float x) {
@@ -97,8 +111,10 @@ __device__ __forceinline__ float round_to_tf32(float x) {
   return __uint_as_float(r);
 }
 
-__global__ void __launch_bounds__(256, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+template <bool B_MN>
+__global__ void __launch_bounds__(256, 2)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   GemmGroup grp;
   if (p.use_single) {
@@ -109,7 +125,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     grp = p.groups[blockIdx.y];
   }
-  const int tm = blockIdx.x / p.tilesN, tn = blockIdx.x - tm * p.tilesN;
+  // M-tiles of one N-tile are adjacent in launch order, so the (large) B operand of that N-tile is re-read from L2
+  const int tn = blockIdx.x / p.tilesM, tm = blockIdx.x - tn * p.tilesM;
   const int m0 = tm * TC_BM, n0 = tn * TC_BN;
   if (m0 >= grp.M || n0 >= grp.N) return;  // uniform for the CTA, before any barrier / allocation
 
@@ -122,7 +139,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = (grp.K + TC_BK - 1) / TC_BK;
+  const int nkb1 = (grp.K + TC_BK - 1) / TC_BK;
+  const int nkb = nkb1 + (p.K2 + TC_BK - 1) / TC_BK;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < TC_STAGES; ++s) {
@@ -144,33 +162,50 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (nkb > 0) {
     if (warp == 0 && lane == 0) {
       // ---------------- TMA producer ----------------
-      const int a_row = (int)(grp.a_off / p.lda) + m0, a_col = (int)(grp.a_off % p.lda);
-      const int b_row = (int)(grp.b_off / p.ldb) + n0, b_col = (int)(grp.b_off % p.ldb);
+      // first pair: offsets come from the group; second pair: plain strided batch (blockIdx.y * s?2)
+      const long long a_off2 = blockIdx.y * p.sa2, b_off2 = blockIdx.y * p.sb2;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
+        const bool second = kb >= nkb1;
+        const int kk = (second ? kb - nkb1 : kb) * TC_BK;
+        const long long aoff = second ? a_off2 : grp.a_off, boff = second ? b_off2 : grp.b_off;
+        const long long lda = second ? p.lda2 : p.lda, ldb = second ? p.ldb2 : p.ldb;
+        const CUtensorMap* ma = second ? &tmA2 : &tmA;
+        const CUtensorMap* mb = second ? &tmB2 : &tmB;
         mbar_wait_bounded(&empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
         uint8_t* sa = tiles + s * TC_STAGE_BYTES;
-        tma_load_2d(sa, &tmA, &full[s], a_col + kb * TC_BK, a_row);
-        tma_load_2d(sa + TC_A_BYTES, &tmB, &full[s], b_col + kb * TC_BK, b_row);
+        tma_load_2d(sa, ma, &full[s], (int)(aoff % lda) + kk, (int)(aoff / lda) + m0);
+        if (!B_MN) {
+          tma_load_2d(sa + TC_A_BYTES, mb, &full[s], (int)(boff % ldb) + kk, (int)(boff / ldb) + n0);
+        } else {
+          // [K][N] operand: four boxes of 32 (n) x 32 (k); box j holds n in [n0 + 32 j, +32)
+          const int ncol = (int)(boff % ldb) + n0, krow = (int)(boff / ldb) + kk;
+#pragma unroll
+          for (int j = 0; j < TC_BN / 32; ++j)
+            tma_load_2d(sa + TC_A_BYTES + j * (TC_BK * 128), mb, &full[s], ncol + 32 * j, krow);
+        }
       }
     } else if (warp == 1 && lane == 0) {
       // ---------------- MMA issuer ----------------
-      // instruction descriptor: D=f32, A=B=tf32, both K-major, N>>3 at bit 17, M>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // instruction descriptor: D=f32 (bit 4), A=B=tf32 (bits 7,10), B major (bit 16), N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
         mbar_wait_bounded(&full[s], ph);
         tc_fence_after();
         const uint32_t sa = base + s * TC_STAGE_BYTES;
-        const uint64_t adesc = make_smem_desc_sw128(sa);
-        const uint64_t bdesc = make_smem_desc_sw128(sa + TC_A_BYTES);
+        const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          // advance 8 tf32 = 32 bytes along K inside the swizzle span: +2 in the (addr >> 4) field
-          tc_mma_tf32(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+          // A (K-major): advance 8 tf32 = 32 bytes inside the swizzle span
+          const uint64_t adesc = make_smem_desc(sa + 32 * k, 16, 1024);
+          // B K-major: same; B MN-major (SW128_BASE32B): 8 k-rows = two 512-byte atoms (SBO), N blocks 4096 bytes apart (LBO)
+          const uint64_t bdesc = B_MN ? make_smem_desc(sb + 1024 * k, TC_BK * 128, 512, 1) : make_smem_desc(sb + 32 * k, 16, 1024);
+          tc_mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
         }
         tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
       }
@@ -178,9 +213,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
-  if (warp >= 4) {
+  __syncwarp();  // producer / MMA lanes rejoin their warps: every warp takes part in the epilogue
+  {
     // ---------------- epilogue: TMEM -> registers -> global ----------------
+    // warp w drains TMEM lane quarter q = w % 4 (hardware restriction) and column half w / 4
     const int q = warp & 3;
+    const int chalf = warp >> 2;
     const int row = m0 + q * 32 + lane;
     if (nkb > 0) {
       mbar_wait_bounded(tmem_full, 0);
@@ -188,8 +226,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     float* drow = p.D + grp.d_off + (long long)row * p.ldd;
     const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    const float bv = (p.bias && row < grp.M) ? p.bias[blockIdx.y * p.sbias + row] : 0.0f;
+    const float* arow = p.add ? p.add + blockIdx.y * p.sadd + (long long)row * p.ldadd : nullptr;
 #pragma unroll 1
-    for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+    for (int c0 = chalf * (TC_BN / 2); c0 < (chalf + 1) * (TC_BN / 2); c0 += 32) {
       uint32_t r[32];
       if (nkb > 0) {
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
@@ -209,15 +249,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const int gn = n0 + c0;
       if (row < grp.M && gn < grp.N) {
+        const bool full_vec = vec && gn + 31 < grp.N;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(r[j]);
-          if (p.relu_even && !(j & 1)) t = fmaxf(t, 0.f);
-          if (p.round_tf32) t = round_to_tf32(t);
+          float t = __uint_as_float(r[j]) + bv;
+          if (p.act_gelu) t = gelu_erf(t);
           v[j] = t;
         }
-        if (vec && gn + 31 < grp.N) {
+        if (arow) {
+          if (full_vec && ((p.ldadd | p.sadd) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.add) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a4 = *reinterpret_cast<const float4*>(arow + gn + j);
+              v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (gn + j < grp.N) v[j] += arow[gn + j];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (p.relu_even && !(j & 1)) v[j] = fmaxf(v[j], 0.f);
+          if (p.round_tf32) v[j] = round_to_tf32(v[j]);
+        }
+        if (full_vec) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(drow + gn + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
         } else {
@@ -255,7 +313,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // 2-D fp32 tensor [rows][ld] (cols valid), box = 32 columns x box_rows rows, 128-byte swizzle
-static int make_map(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+static int make_map(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows,
+                    bool atom32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -263,43 +322,63 @@ static int make_map(CUtensorMap* tm, const float* base, long long rows, long lon
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
   return MSFNO_OK;
 }
 
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 bool gemm_tc_supported(const GemmLaunch& g) {
-  if (!g.a_kmajor || !g.b_kmajor || g.mask || g.accumulate) return false;
-  if ((g.lda & 3) || (g.ldb & 3)) return false;
-  if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.B) & 15)) return false;
+  if (!g.a_kmajor || g.mask || g.accumulate) return false;
+  if ((g.lda & 3) || (g.ldb & 3) || !aligned16(g.A) || !aligned16(g.B)) return false;
+  if (g.A2 && ((g.lda2 & 3) || (g.ldb2 & 3) || !aligned16(g.A2) || !aligned16(g.B2))) return false;
   return get_encode() != nullptr;
 }
 
-// a_rows / b_rows: number of rows of the underlying 2-D buffers (TMA zero-fills beyond them);
-// a_cols / b_cols: valid columns (<= ld)
+// a_rows / b_rows: rows of the underlying 2-D buffers (TMA zero-fills beyond them); a_cols / b_cols: valid columns.
+// For an MN-major B (g.b_kmajor == 0) the buffer is [K rows][N cols].
 int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
-                   int round_tf32, cudaStream_t st) {
+                   int round_tf32, cudaStream_t st, long long a2_rows, long long a2_cols, long long b2_rows,
+                   long long b2_cols) {
   if (g.ngroups <= 0 || g.maxM <= 0 || g.maxN <= 0) return MSFNO_OK;
-  CUtensorMap tmA, tmB;
+  const bool bmn = !g.b_kmajor;
+  CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, TC_BM);
   if (rc) return rc;
-  rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, TC_BN);
+  rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, bmn ? TC_BK : TC_BN, bmn);
   if (rc) return rc;
+  if (g.A2) {
+    rc = make_map(&tmA2, g.A2, a2_rows, a2_cols, g.lda2, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&tmB2, g.B2, b2_rows, b2_cols, g.ldb2, bmn ? TC_BK : TC_BN, bmn);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA;
+    tmB2 = tmB;
+  }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
   });
   MSFNO_CUDA_OK(attr_err);
   TcParams p{};
   p.D = g.D; p.lda = g.lda; p.ldb = g.ldb; p.ldd = g.ldd;
   p.groups = g.groups; p.single = g.single; p.sa = g.sa; p.sb = g.sb; p.sd = g.sd; p.use_single = g.use_single;
   p.relu_even = g.relu_even; p.round_tf32 = round_tf32;
+  p.bias = g.bias; p.sbias = g.sbias; p.add = g.add; p.ldadd = g.ldadd; p.sadd = g.sadd; p.act_gelu = g.act_gelu;
+  p.lda2 = g.A2 ? g.lda2 : 4; p.ldb2 = g.A2 ? g.ldb2 : 4; p.sa2 = g.sa2; p.sb2 = g.sb2; p.K2 = g.A2 ? g.K2 : 0;
   const int tilesM = (g.maxM + TC_BM - 1) / TC_BM;
   p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;
+  p.tilesM = tilesM;
   dim3 grid(tilesM * p.tilesN, g.ngroups);
-  gemm_tc_kernel<<<grid, 256, TC_SMEM_BYTES, st>>>(tmA, tmB, p);
+  if (bmn) gemm_tc_kernel<true><<<grid, 256, TC_SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, p);
+  else gemm_tc_kernel<false><<<grid, 256, TC_SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, p);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

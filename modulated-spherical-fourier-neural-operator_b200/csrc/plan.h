@@ -24,6 +24,7 @@ struct GemmGroup {
 struct msfno_plan {
   int nlat, nlon, lmax, mmax;
   int device;
+  int precision = 0;  // MSFNO_PREC_*: tier of the Legendre contractions (forward transforms only)
   int mlim;   // min(mmax, lmax): orders with at least one degree
   int kpad;   // nlat rounded up to 32
   int Lj;     // padded per-order degree extent (ceil4(lmax))
@@ -70,6 +71,16 @@ struct GemmLaunch {
   const float* mask;        // optional, same layout/offsets as D: zero D[m][n] (even n) where mask[m][n] <= 0 (ReLU backward)
   long long ldmask;
   int accumulate;           // D += result
+  // fused epilogue of the 1x1-conv form: D = act(acc + bias[row]) + add[row][col]
+  const float* bias;        // per output row (+ group_index * sbias)
+  long long sbias;
+  const float* add;         // same row/col indexing as D with leading dimension ldadd (+ group_index * sadd)
+  long long ldadd, sadd;
+  int act_gelu;
+  // optional second operand pair accumulated into the same D (K-concatenation without a concat copy)
+  const float* A2; const float* B2;
+  long long lda2, ldb2, sa2, sb2;
+  int K2;
   const GemmGroup* groups;  // device array
   int ngroups;
   int maxM, maxN;           // over groups (grid sizing)
@@ -86,7 +97,8 @@ int launch_gemm_single(const float* A, long long lda, int a_kmajor, const float*
 // no ReLU-mask / accumulate epilogue.  a_rows/a_cols (b_rows/b_cols) describe the whole 2-D buffer behind A (B).
 bool gemm_tc_supported(const GemmLaunch& g);
 int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
-                   int round_tf32, cudaStream_t st);
+                   int round_tf32, cudaStream_t st, long long a2_rows = 0, long long a2_cols = 0, long long b2_rows = 0,
+                   long long b2_cols = 0);
 
 // four-step in-register FFT kernels (fft2d.cu) for nlon in {240, 1440, 2880}
 bool fft2d_supported(int nlon);

@@ -21,6 +21,13 @@ static int legendre_gemm(msfno_plan* p, int kind, const float* A, long long lda,
   g.lda = lda; g.ldb = ldb; g.ldd = ldd;
   g.a_kmajor = a_k; g.b_kmajor = b_k;
   g.groups = groups; g.ngroups = ng; g.maxM = maxM; g.maxN = maxN;
+  if (p->precision == MSFNO_PREC_TF32 && (kind == GK_ANALYSIS || kind == GK_SYNTHESIS) && gemm_tc_supported(g)) {
+    // tensor-core tier: the 2-D buffers behind A and B as TMA sees them (zero-fill outside)
+    const int mloc = (m_hi < 0 ? p->mlim : m_hi) - m_lo;
+    if (kind == GK_ANALYSIS)
+      return launch_gemm_tc(g, (long long)p->mlim * p->Lj, p->kpad, (long long)Bsz * mloc * 2 * C, p->kpad, 0, st);
+    return launch_gemm_tc(g, (long long)Bsz * 2 * C, lda, (long long)p->mlim * p->nlat, p->Lj, 0, st);
+  }
   return launch_gemm_ffma(g, st);
 }
 
@@ -72,6 +79,12 @@ int msfno_isht_bwd(msfno_plan* p, const float* gy, float* g_cm, float* ws, int B
   if (rc) return rc;
   // g_cm[b][ch][poff[m]+j] = sum_k gYt[b][m][ch][k] * tab_kl[m][k][j]
   return legendre_gemm(p, GK_SYNTHESIS_ADJ, ws, p->kpad, 1, p->d_tab_kl, p->Lj, 0, g_cm, p->P, 2 * C, p->h_plen4[0], B, C, st);
+}
+
+int msfno_plan_set_precision(msfno_plan* p, int precision) {
+  if (!p || (precision != MSFNO_PREC_FP32 && precision != MSFNO_PREC_TF32)) return record_error(MSFNO_ERR_BAD_SHAPE, "plan_set_precision: bad argument");
+  p->precision = precision;
+  return MSFNO_OK;
 }
 
 // ---- stage-level entry points (spatially sharded SHT) -------------------------------------

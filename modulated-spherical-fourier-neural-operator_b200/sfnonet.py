@@ -28,6 +28,7 @@ from torch.utils.checkpoint import checkpoint
 from . import _lib
 from . import precision as _precision
 from ._lib import check, lib, ptr
+from .conv import conv1x1, padded_weight
 from .layers import MLP, DropPath, SpectralAttentionS2, SpectralConvS2, trunc_normal_
 from .sht import InverseRealSHT, RealSHT, _stream
 
@@ -200,25 +201,45 @@ class FourierNeuralOperatorBlock(nn.Module):
                 x = x + self.outer_skip(residual)
         return x
 
-    def _fused(self, x, gamma=None, beta=None, scale=1.0):
-        """Inference path with the normalisations / skip / activation / FiLM folded into the transforms."""
+    def _fused(self, x, gamma=None, beta=None, scale=1.0, defer_affine=False):
+        """Inference path with the normalisations / skip / activation / FiLM folded into the transforms and the
+        channel MLP run as two fused 1x1-conv GEMMs (msfno_conv1x1_fwd).  With defer_affine=True (a block without
+        MLP, i.e. the last one) the un-normalised output and the pending per-plane affine (A, S) are returned so the
+        caller can fold them into the next 1x1 conv instead of spending a full-tensor pass."""
         residual = x
         x = x.contiguous().float()
         B, C = x.shape[0], x.shape[1]
         A0, S0 = norm_film_coeffs(plane_stats(x), self.norm0, B, C, x[0, 0].numel())
-        skip = self.inner_skip(residual) if hasattr(self, "inner_skip") else None
+        skip = None
+        if hasattr(self, "inner_skip"):
+            if isinstance(self.inner_skip, nn.Conv2d):
+                skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
+            else:
+                skip = self.inner_skip(residual)
         stats1 = torch.empty((B * C, 2), dtype=torch.float64, device=x.device)
         y = self.filter_layer(x, in_scale=A0, in_shift=S0, skip_add=skip, act_gelu=hasattr(self, "act_layer"),
                               stats=stats1)
         A1, S1 = norm_film_coeffs(stats1, self.norm1, B, C, y[0, 0].numel(), gamma, beta, scale)
         mlp = getattr(self, "mlp", None)
-        if mlp is not None and not mlp.checkpointing_mlp and isinstance(mlp.fwd[0], nn.Conv2d) and len(mlp.fwd) == 3:
-            h = _conv1x1_with_input_affine(mlp.fwd[0], y, A1, S1)
-            y = mlp.fwd[2](mlp.fwd[1](h))
-        else:
-            y = plane_affine(y, A1, S1)
-            if mlp is not None:
-                y = mlp(y)
+        no_drop = isinstance(self.drop_path, nn.Identity) or not self.training
+        if mlp is None and defer_affine and not hasattr(self, "outer_skip"):
+            return y, A1, S1
+        if (mlp is not None and len(mlp.fwd) == 3 and isinstance(mlp.fwd[0], nn.Conv2d) and isinstance(mlp.fwd[1], nn.GELU)
+                and getattr(mlp.fwd[1], "approximate", "none") == "none" and isinstance(mlp.fwd[2], nn.Conv2d)):
+            fc1, fc2 = mlp.fwd[0], mlp.fwd[2]
+            W1 = padded_weight(fc1.weight)                                  # [hid, C]
+            Wb = (W1.unsqueeze(0) * A1.unsqueeze(1)).contiguous()           # norm1 o FiLM folded into fc1
+            bias_b = torch.matmul(S1, W1[:, :C].t())
+            if fc1.bias is not None:
+                bias_b = bias_b + fc1.bias
+            h = conv1x1(y, Wb, C, bias=bias_b.contiguous(), act_gelu=True, per_sample_w=True, per_sample_bias=True)
+            fuse_res = no_drop and not self.concat_skip and isinstance(getattr(self, "outer_skip", None), nn.Identity)
+            out = conv1x1(h, padded_weight(fc2.weight), fc2.in_channels, bias=fc2.bias,
+                          add=residual.contiguous().float() if fuse_res else None)
+            return out if fuse_res else self._tail(out, residual)
+        y = plane_affine(y, A1, S1)
+        if mlp is not None:
+            y = mlp(y)
         return self._tail(y, residual)
 
     def _unfused(self, x, gamma=None, beta=None, scale=1.0, film=None):
@@ -412,8 +433,56 @@ class FourierNeuralOperatorNet(nn.Module):
                 x = blk(x)
         return x
 
+    # -- fused inference path (no autograd): encoder / decoder as fused 1x1-conv GEMMs ---------------------
+    def _can_fuse_net(self, x):
+        enc, dec = self.encoder.fwd, self.decoder.fwd
+        ok_mlp = all(len(m) == 3 and isinstance(m[0], nn.Conv2d) and isinstance(m[1], nn.GELU)
+                     and getattr(m[1], "approximate", "none") == "none" and isinstance(m[2], nn.Conv2d) for m in (enc, dec))
+        return (x.is_cuda and not torch.is_grad_enabled() and ok_mlp and isinstance(self.pos_drop, nn.Identity)
+                and self.big_skip and not self.checkpointing_block and all(b._can_fuse(x) for b in self.blocks)
+                and not hasattr(self.blocks[-1], "mlp") and not hasattr(self.blocks[-1], "outer_skip"))
+
+    def _encode_fused(self, x):
+        enc = self.encoder.fwd
+        x = x.contiguous().float()
+        h = conv1x1(x, padded_weight(enc[0].weight), self.in_chans, bias=enc[0].bias, act_gelu=True)
+        return conv1x1(h, padded_weight(enc[2].weight), enc[2].in_channels, bias=enc[2].bias, add=self.pos_embed)
+
+    def _decode_fused(self, y, A, S, residual):
+        """decoder(cat(A*y + S, residual)): the pending affine of the last block is folded into the first conv's
+        weights, the concat is replaced by a second operand pair accumulating into the same tile."""
+        dec = self.decoder.fwd
+        E = self.embed_dim_sfno
+        Wd = dec[0].weight.view(dec[0].out_channels, -1)
+        W1, W2 = padded_weight(Wd[:, :E]), padded_weight(Wd[:, E:])
+        Wb = (W1.unsqueeze(0) * torch.nn.functional.pad(A, (0, W1.shape[1] - E)).unsqueeze(1)).contiguous()
+        bias_b = torch.matmul(S, W1[:, :E].t())
+        if dec[0].bias is not None:
+            bias_b = bias_b + dec[0].bias
+        h = conv1x1(y, Wb, E, bias=bias_b.contiguous(), act_gelu=True, x2=residual.contiguous().float(), w2=W2,
+                    cin2=self.in_chans, per_sample_w=True, per_sample_bias=True)
+        return conv1x1(h, padded_weight(dec[2].weight), dec[2].in_channels, bias=dec[2].bias)
+
+    def _forward_fused(self, x, film=None):
+        """film: None or (gamma [B, film_layers, C], beta, scale, first_filmed_block_index)."""
+        residual = x
+        x = self._encode_fused(x)
+        last = len(self.blocks) - 1
+        for i, blk in enumerate(self.blocks):
+            g = b = None
+            sc = 1.0
+            if film is not None and i >= film[3]:
+                g, b, sc = film[0][:, i - film[3]], film[1][:, i - film[3]], film[2]
+            if i == last:
+                y, A, S = blk._fused(x, g, b, sc, defer_affine=True)
+            else:
+                x = blk._fused(x, g, b, sc)
+        return self._decode_fused(y, A, S, residual)
+
     def forward(self, x):
         with _precision.library_scope():
+            if self._can_fuse_net(x):
+                return self._forward_fused(x)
             if self.big_skip:
                 residual = x
             x = self.encoder(x)
@@ -502,6 +571,10 @@ class FourierNeuralOperatorNet_Filmed(FourierNeuralOperatorNet):
         if self.advanced_logging:
             self.gamma = gamma
             self.beta = beta
+        if self._can_fuse_net(x) and not self.cfg.repeat_film:
+            if torch.is_tensor(scale):
+                scale = float(scale)
+            return self._forward_fused(x, film=(gamma, beta, scale, self.num_layers - self.film_layers))
         if self.big_skip:
             residual = x
         with torch.no_grad():

@@ -20,6 +20,7 @@ import torch.nn as nn
 
 from . import _lib
 from . import legendre as _legendre
+from . import precision as _precision
 from . import quadrature as _quadrature
 from ._lib import check, lib, ptr
 
@@ -48,6 +49,7 @@ class _Plan:
         self.P = lib.msfno_plan_query(self.h, _lib.Q_NPACK)
         self.ntril = lib.msfno_plan_query(self.h, _lib.Q_NTRIL)
         self.table_key = None
+        self.precision = _lib.PREC_FP32
 
     def set_table(self, table, analysis):
         key = (table.data_ptr(), table._version, tuple(table.shape))
@@ -179,6 +181,10 @@ class _SHTBase(nn.Module):
             raise RuntimeError("%s.%s lives on %s but the input is on %s" % (type(self).__name__, self._table_name,
                                                                              table.device, device))
         plan.set_table(table, self._analysis)
+        tier = _lib.PREC_TF32 if _precision.get_precision() == "tf32" else _lib.PREC_FP32
+        if tier != plan.precision:
+            check(lib.msfno_plan_set_precision(plan.h, tier), "plan_set_precision")
+            plan.precision = tier
         return plan
 
     def __deepcopy__(self, memo):

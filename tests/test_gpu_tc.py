@@ -63,3 +63,89 @@ def test_spectral_attention_tf32_tier(B, C):
         got = mod(x.cuda())
     err = rel_l2(got, want)
     assert err < TOL_TF32, err
+
+
+@pytest.fixture
+def tf32_tier():
+    msfno_b200.set_precision("tf32")
+    yield
+    msfno_b200.set_precision("fp32")
+
+
+@pytest.mark.parametrize("grid,nlat,nlon,L,M,B,C", [("equiangular", 721, 1440, 120, 121, 1, 4),
+                                                    ("legendre-gauss", 120, 240, 120, 121, 2, 8),
+                                                    ("equiangular", 91, 180, 30, 31, 1, 3)])
+def test_sht_tf32_tier(tf32_tier, grid, nlat, nlon, L, M, B, C):
+    o_s = th_shim.RealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid).float()
+    o_i = th_shim.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid).float()
+    sht = msfno_b200.RealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid).float().cuda()
+    isht = msfno_b200.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid).float().cuda()
+    for t in (o_s, sht):
+        t.weights = t.weights * 1e5
+    for t in (o_i, isht):
+        t.pct = t.pct / 1e5
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, C, nlat, nlon, generator=g)
+    with torch.no_grad():
+        got = sht(x.cuda())
+    assert rel_l2(torch.view_as_real(got), torch.view_as_real(o_s(x))) < TOL_TF32
+    cin = torch.view_as_complex(torch.randn(B, C, L, M, 2, generator=g)) * 1e3
+    with torch.no_grad():
+        got_y = isht(cin.cuda())
+    assert rel_l2(got_y, o_i(cin)) < TOL_TF32
+
+
+@pytest.mark.parametrize("name,ftype", [("net_linear_small.pt", "linear"), ("net_nonlinear_small.pt", "non-linear")])
+def test_small_net_tf32_tier(tf32_tier, name, ftype):
+    import os
+    from conftest import GOLD
+    d = torch.load(os.path.join(GOLD, name))
+    cfg = d["cfg"]
+    sd = sfno_oracle.make_state_dict(filter_type=ftype, img_size=cfg["img_size"], scale_factor=cfg["scale_factor"],
+                                     in_chans=cfg["in_chans"], out_chans=cfg["out_chans"], embed=cfg["embed_dim_sfno"],
+                                     num_layers=cfg["num_layers"], mlp_ratio=cfg["mlp_ratio"],
+                                     spectral_layers=cfg["spectral_layers"], seed=d["seed"])
+    net = msfno_b200.FourierNeuralOperatorNet("cuda", None, **cfg)
+    full = dict(net.state_dict())
+    full.update(sd)
+    net.load_state_dict(full, strict=True)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        y = net(d["x"].cuda())
+    assert rel_l2(y, d["y"]) < TOL_TF32
+
+
+@pytest.mark.parametrize("tier,tol", [("fp32", 1e-5), ("tf32", TOL_TF32)])
+@pytest.mark.parametrize("B,Cin,Cout,H,W,Cin2", [(1, 73, 256, 37, 72, 0), (2, 256, 512, 12, 24, 0), (1, 256, 73, 31, 52, 0),
+                                                   (2, 64, 96, 16, 40, 73), (1, 8, 8, 4, 4, 0), (1, 256, 256, 120, 240, 73)])
+def test_conv1x1_fused(tier, tol, B, Cin, Cout, H, W, Cin2):
+    """y = gelu(conv(x, w) [+ conv(x2, w2)] + bias) + add against torch fp64 (msfno_conv1x1_fwd, both engines)."""
+    from msfno_b200.conv import conv1x1, padded_weight
+    msfno_b200.set_precision(tier)
+    try:
+        g = torch.Generator().manual_seed(B * 1000 + Cin + Cout)
+        x = torch.randn(B, Cin, H, W, generator=g).cuda()
+        w = (torch.randn(Cout, Cin, 1, 1, generator=g) / Cin ** 0.5).cuda()
+        bias = torch.randn(Cout, generator=g).cuda()
+        add = torch.randn(B, Cout, H, W, generator=g).cuda()
+        x2 = w2 = None
+        ref = torch.nn.functional.conv2d(x.double(), w.double())
+        if Cin2:
+            x2 = torch.randn(B, Cin2, H, W, generator=g).cuda()
+            w2 = (torch.randn(Cout, Cin2, 1, 1, generator=g) / Cin2 ** 0.5).cuda()
+            ref = ref + torch.nn.functional.conv2d(x2.double(), w2.double())
+        ref = torch.nn.functional.gelu(ref + bias.double()[None, :, None, None]) + add.double()
+        got = conv1x1(x, padded_weight(w), Cin, bias=bias, act_gelu=True, add=add, x2=x2,
+                      w2=padded_weight(w2) if w2 is not None else None, cin2=Cin2)
+        assert rel_l2(got, ref) < tol
+        # per-sample weights and bias (InstanceNorm/FiLM affine folded into the conv), no activation, broadcast add
+        A = (torch.rand(B, Cin, generator=g) + 0.5).cuda()
+        wp = padded_weight(w)
+        Wb = (wp.unsqueeze(0) * torch.nn.functional.pad(A, (0, wp.shape[1] - Cin)).unsqueeze(1)).contiguous()
+        bb = torch.randn(B, Cout, generator=g).cuda()
+        add1 = torch.randn(1, Cout, H, W, generator=g).cuda()
+        got = conv1x1(x, Wb, Cin, bias=bb, add=add1, per_sample_w=True, per_sample_bias=True)
+        ref = torch.nn.functional.conv2d((x * A[:, :, None, None]).double(), w.double()) + bb.double()[:, :, None, None] + add1.double()
+        assert rel_l2(got, ref) < tol
+    finally:
+        msfno_b200.set_precision("fp32")

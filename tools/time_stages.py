@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--precision", default="fp32")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
+    msfno_b200.set_precision(a.precision)
     B, C = a.B, a.C
     flush = torch.empty(256 * 1024 * 1024 // 4, device=dev)
     out = {}
