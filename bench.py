@@ -284,6 +284,13 @@ def run_ours(args):
     with torch.no_grad():
         y = net(x_dev)
         y_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+        eager = net
+        if not args.no_graph:
+            import msfno_b200
+            l_one = _lib.lib.msfno_launch_count()
+            eager(x_dev)
+            launches_per_step = _lib.lib.msfno_launch_count() - l_one   # kernels one replay contains
+            net = msfno_b200.GraphedForward(eager, x_dev)
         for _ in range(max(args.warmup - 1, 0)):
             net(x_dev)
         # ---- device-resident leg ---------------------------------------------------------------
@@ -294,11 +301,17 @@ def run_ours(args):
         l0 = _lib.lib.msfno_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            y = net(x_dev)
+        if args.no_graph:
+            for _ in range(args.steps):
+                y = net(x_dev)
+        else:  # the input already sits in the graph's static input buffer (resident in HBM)
+            for _ in range(args.steps):
+                y = net()
         e1.record()
         sync_all()
         launches = _lib.lib.msfno_launch_count() - l0
+        if not args.no_graph:
+            launches = launches_per_step * args.steps  # replayed inside the graph: the library counter does not see replays
         ms_dev = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop() if rank == 0 else None
         # ---- end-to-end leg: host buffers in, host buffers out, through the public HostPipeline API ----------
@@ -315,7 +328,7 @@ def run_ours(args):
         sync_all()
         ms_e2e = max_over_ranks(e0.elapsed_time(e1))
 
-        roof = dominant_kernel_roofline(args, net, dev, pk) if rank == 0 else None
+        roof = dominant_kernel_roofline(args, eager, dev, pk) if rank == 0 else None
 
     bad = not torch.isfinite(y_host).all()
     if world > 1:
@@ -352,6 +365,7 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu_baseline,
         "output_finite": not bad,
+        "cuda_graph": not args.no_graph,
     }
     print(json.dumps(line))
     if world > 1:
@@ -368,6 +382,7 @@ def main():
     ap.add_argument("--workload", default="sfno12_nonlinear", choices=["sfno12_nonlinear", "sfno12_linear", "filter_linear"])
     ap.add_argument("--precision", default=os.environ.get("MSFNO_PRECISION", "fp32"), choices=["fp32", "tf32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

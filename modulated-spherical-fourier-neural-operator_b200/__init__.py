@@ -18,10 +18,11 @@ from .sfnonet import (FeedForward, FiLM, Film_wrapper, FourierNeuralOperatorBloc
                       FourierNeuralOperatorNet, FourierNeuralOperatorNet_Filmed, SpectralFilterLayer)
 from . import harmonics
 from .pipeline import HostPipeline
+from .graph import GraphedForward
 
 __all__ = [
     "RealSHT", "InverseRealSHT", "quadrature", "legendre", "harmonics", "set_precision", "get_precision",
     "SpectralConvS2", "SpectralAttentionS2", "ComplexReLU", "MLP", "DropPath", "trunc_normal_",
     "SpectralFilterLayer", "FiLM", "FourierNeuralOperatorBlock", "FourierNeuralOperatorBlock_Filmed",
-    "FourierNeuralOperatorNet", "FourierNeuralOperatorNet_Filmed", "Film_wrapper", "FeedForward", "HostPipeline",
+    "FourierNeuralOperatorNet", "FourierNeuralOperatorNet_Filmed", "Film_wrapper", "FeedForward", "HostPipeline", "GraphedForward",
 ]

@@ -40,6 +40,9 @@ extern "C" int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const 
     const long long a_rows = (long long)(B - 1) * (w_bstride / ldw) + Cout;
     const long long b_rows = (long long)(B - 1) * (x_bstride / HW) + Cin;
     const long long b2_rows = x2 ? (long long)(B - 1) * (x2_bstride / HW) + Cin2 : 0;
+    int handled = 0;
+    int rc = launch_conv_tc(g, a_rows, ldw, b_rows, HW, Cout, ldw2, b2_rows, HW, &handled, st);
+    if (rc || handled) return rc;
     return launch_gemm_tc(g, a_rows, ldw, b_rows, HW, 0, st, Cout, ldw2, b2_rows, HW);
   }
   return launch_gemm_ffma(g, st);

@@ -1,0 +1,293 @@
+// Persistent, weight-stationary TF32 tensor-core kernel for the 1x1 convolutions in NCHW (tensor-core tier of
+// msfno_conv1x1_fwd).  A CTA owns 128 output channels and a strided set of 128-pixel tiles:
+//   * the weight slab [128 x K] (both operand pairs of the big-skip form) is loaded ONCE by TMA and stays in smem;
+//   * activations stream through a small TMA ring as MN-major operands (SWIZZLE_128B_BASE32B, the only layout
+//     tcgen05 accepts for MN-major 32-bit data);
+//   * two 128-column TMEM accumulators alternate, so the epilogue (bias, exact GELU, residual / pos-embed add,
+//     128-byte row stores) of tile i overlaps the MMAs of tile i+1.
+// SM fill traffic per launch drops from (weights + activations) per tile to activations only.
+//
+// replaces: nn.Conv2d(.., 1) + bias + nn.GELU + residual adds + torch.cat in the reference's channel MLPs
+//   (/root/reference MSFNO/Models/sfno/layers.py:161-168; sfnonet.py:232,249,671,682-684).
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+// (TMEM lane quarter w % 4, column half (w - 2) / 4).
+// Output path: NCHW rows are HW*4 bytes (4 MB at 721x1440) apart, so a per-lane row store touches 32 pages per
+// instruction and runs at ~0.6 TB/s (measured); instead each epilogue warp writes 32x16 granules into a swizzled
+// smem staging buffer and hands them to the TMA engine (cp.async.bulk.tensor store), which writes 64-byte row
+// segments at DRAM speed.
+#include "plan.h"
+#include "tc_common.cuh"
+
+namespace msfno {
+
+static constexpr int CT_BM = 128, CT_BN = 128;
+static constexpr int CT_KB_BYTES = CT_BM * TC_BK * 4;  // one 128 x 32 fp32 operand block = 16 KB
+static constexpr int CT_MAX_KB = 11;                    // resident weight k-blocks (K1 + K2 <= 352)
+
+struct ConvTcParams {
+  float* D;
+  long long lda, lda2, ldb, ldb2, ldd;
+  long long sa, sb, sb2, sd;   // per-sample strides (floats): weights, x, x2, y
+  const float* bias; long long sbias;
+  const float* add; long long ldadd, sadd;
+  int M, N, K1, K2;
+  int act_gelu;
+  int nstages;   // ring depth for the streamed activation blocks
+  int tilesN;
+  int nbuf;      // staging buffers per epilogue warp (1 or 2)
+};
+
+__global__ void __launch_bounds__(320, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmD, ConvTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * CT_BM;
+  const int b = blockIdx.z;
+  const int nkb1 = (p.K1 + TC_BK - 1) / TC_BK, nkb2 = (p.K2 + TC_BK - 1) / TC_BK, nkb = nkb1 + nkb2;
+  const int NS = p.nstages;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* a_res = tiles;                                  // nkb resident weight blocks
+  uint8_t* ring = tiles + (size_t)nkb * CT_KB_BYTES;       // NS activation blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)NS * CT_KB_BYTES);
+  uint64_t* full = bars;               // [NS]
+  uint64_t* empty = bars + 8;          // [NS]
+  uint64_t* a_full = bars + 16;
+  uint64_t* tmem_full = bars + 17;     // [2]
+  uint64_t* tmem_empty = bars + 19;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  // epilogue staging: 8 warps x nbuf x [32 rows][16 fp32] (2 KB, 64-byte swizzle), 1024-byte aligned
+  uint8_t* stage_base = ring + (size_t)NS * CT_KB_BYTES + 1024;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(a_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(2 * CT_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      const long long aoff = (long long)b * p.sa;
+      mbar_arrive_expect_tx(a_full, (uint32_t)(nkb * CT_KB_BYTES));
+      for (int kb = 0; kb < nkb; ++kb) {
+        const bool second = kb >= nkb1;
+        const int kk = (second ? kb - nkb1 : kb) * TC_BK;
+        if (!second) tma_load_2d(a_res + (size_t)kb * CT_KB_BYTES, &tmA, a_full, (int)(aoff % p.lda) + kk, (int)(aoff / p.lda) + m0);
+        else tma_load_2d(a_res + (size_t)kb * CT_KB_BYTES, &tmA2, a_full, kk, m0);
+      }
+      const int krow1 = (int)(((long long)b * p.sb) / p.ldb);
+      const int krow2 = p.K2 ? (int)(((long long)b * p.sb2) / p.ldb2) : 0;
+      uint32_t kc = 0;
+      for (int t = blockIdx.x; t < p.tilesN; t += gridDim.x) {
+        const int n0 = t * CT_BN;
+        for (int kb = 0; kb < nkb; ++kb, ++kc) {
+          const int s = kc % NS;
+          const uint32_t ph = (kc / NS) & 1u;
+          const bool second = kb >= nkb1;
+          const int krow = second ? krow2 + (kb - nkb1) * TC_BK : krow1 + kb * TC_BK;
+          const CUtensorMap* mb = second ? &tmB2 : &tmB;
+          mbar_wait_bounded(&empty[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full[s], CT_KB_BYTES);
+          uint8_t* dst = ring + (size_t)s * CT_KB_BYTES;
+#pragma unroll
+          for (int j = 0; j < CT_BN / 32; ++j) tma_load_2d(dst + j * (TC_BK * 128), mb, &full[s], n0 + 32 * j, krow);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(CT_BN >> 3) << 17) |
+                             ((uint32_t)(CT_BM >> 4) << 24);
+      mbar_wait_bounded(a_full, 0);
+      tc_fence_after();
+      uint32_t kc = 0, it = 0;
+      const uint32_t a_addr = base, r_addr = base + (uint32_t)nkb * CT_KB_BYTES;
+      for (int t = blockIdx.x; t < p.tilesN; t += gridDim.x, ++it) {
+        const uint32_t acc = it & 1u, use = it >> 1;
+        mbar_wait_bounded(&tmem_empty[acc], (use & 1u) ^ 1u);
+        tc_fence_after();
+        for (int kb = 0; kb < nkb; ++kb, ++kc) {
+          const int s = kc % NS;
+          const uint32_t ph = (kc / NS) & 1u;
+          mbar_wait_bounded(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = a_addr + (uint32_t)kb * CT_KB_BYTES, sb = r_addr + (uint32_t)s * CT_KB_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32(tmem_base + acc * CT_BN, make_smem_desc(sa + 32 * k, 16, 1024),
+                        make_smem_desc(sb + 1024 * k, TC_BK * 128, 512, 1), idesc, (kb | k) ? 1u : 0u);
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 2..9: TMEM lane quarter w % 4, column half (w - 2) / 4 ----------------
+    const int q = warp & 3, chalf = (warp - 2) >> 2;
+    const int row = m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const float bv = (p.bias && row_ok) ? p.bias[(long long)b * p.sbias + row] : 0.0f;
+    const float* arow = p.add ? p.add + (long long)b * p.sadd + (long long)row * p.ldadd : nullptr;
+    uint8_t* my_stage = stage_base + (size_t)(warp - 2) * p.nbuf * 2048;
+    const uint32_t sw = (uint32_t)((lane >> 1) & 3);   // 64-byte swizzle: 16-byte chunk index ^= (row >> 1) & 3
+    uint32_t it = 0, gcount = 0;
+    for (int t = blockIdx.x; t < p.tilesN; t += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u, use = it >> 1;
+      const int n0 = t * CT_BN;
+      mbar_wait_bounded(&tmem_full[acc], use & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int gq = 0; gq < 4; ++gq, ++gcount) {
+        const int c0 = chalf * 64 + gq * 16;
+        uint32_t r[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CT_BN + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (gq == 3) {
+          // all TMEM reads of this warp for accumulator `acc` are done: hand it back to the MMA issuer early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        const int gn = n0 + c0;
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float tv = __uint_as_float(r[j]) + bv;
+          if (p.act_gelu) tv = gelu_fast(tv);
+          v[j] = tv;
+        }
+        if (arow && row_ok) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (gn + j < p.N) v[j] += arow[gn + j];
+        }
+        // staging buffer: wait until the TMA store that last used it has finished READING it
+        uint8_t* buf = my_stage + (gcount % p.nbuf) * 2048;
+        if (gcount >= (uint32_t)p.nbuf) {
+          if (lane == 0) {
+            if (p.nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+          }
+          __syncwarp();
+        }
+        float4* rowp = reinterpret_cast<float4*>(buf + lane * 64);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) rowp[ch ^ sw] = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(
+                           reinterpret_cast<uint64_t>(&tmD)),
+                       "r"(smem_u32(buf)), "r"(gn), "r"(m0 + q * 32), "r"(b)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+    __syncwarp();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * CT_BN));
+  }
+}
+
+// Returns MSFNO_OK and sets *handled = 1 when the persistent kernel took the problem; *handled = 0 means "use the
+// generic engine" (shape outside what the weight-stationary layout supports).
+int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
+                   long long a2_rows, long long a2_cols, long long b2_rows, long long b2_cols, int* handled,
+                   cudaStream_t st) {
+  *handled = 0;
+  const int K1 = g.single.K, K2 = g.A2 ? g.K2 : 0;
+  const int nkb = (K1 + TC_BK - 1) / TC_BK + (K2 + TC_BK - 1) / TC_BK;
+  if (g.b_kmajor || !g.use_single || g.relu_even || nkb < 1 || nkb > CT_MAX_KB) return MSFNO_OK;
+  if (g.sa % g.lda != 0 || g.sb % g.ldb != 0 || (g.A2 && (g.sa2 != 0 || g.sb2 % g.ldb2 != 0))) return MSFNO_OK;
+  // smem: [align 1024][nkb resident weight blocks][ns ring blocks][barriers, 1024][8 warps x nbuf x 2 KB staging]
+  const size_t total = 227 * 1024, fixed = 1024 + 1024 + (size_t)nkb * CT_KB_BYTES;
+  int nbuf = 2;
+  if (fixed + 2 * CT_KB_BYTES + 8 * 2 * 2048 > total) nbuf = 1;
+  const size_t stage_bytes = (size_t)8 * nbuf * 2048;
+  if (fixed + 2 * CT_KB_BYTES + stage_bytes > total) return MSFNO_OK;
+  int ns = (int)((total - fixed - stage_bytes) / CT_KB_BYTES);
+  if (ns > 4) ns = 4;
+  const size_t smem = fixed + (size_t)ns * CT_KB_BYTES + stage_bytes;
+  if ((reinterpret_cast<uintptr_t>(g.D) & 15) || (g.ldd & 3) || (g.sd & 3)) return MSFNO_OK;
+
+  CUtensorMap tmA, tmB, tmA2, tmB2;
+  int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, CT_BM);
+  if (rc) return rc;
+  rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, TC_BK, true);
+  if (rc) return rc;
+  if (g.A2) {
+    rc = make_map(&tmA2, g.A2, a2_rows, a2_cols, g.lda2, CT_BM);
+    if (rc) return rc;
+    rc = make_map(&tmB2, g.B2, b2_rows, b2_cols, g.ldb2, TC_BK, true);
+    if (rc) return rc;
+  } else {
+    tmA2 = tmA;
+    tmB2 = tmB;
+  }
+  // output: 3-D tensor [batch][rows = out channels][cols = pixels], box 16 cols x 32 rows x 1, 64-byte swizzle;
+  // rows >= M and cols >= N are clipped by the TMA engine
+  CUtensorMap tmD;
+  {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+    cuuint64_t dims[3] = {(cuuint64_t)g.single.N, (cuuint64_t)g.single.M, (cuuint64_t)g.ngroups};
+    cuuint64_t strides[2] = {(cuuint64_t)g.ldd * 4, (cuuint64_t)(g.ngroups > 1 ? g.sd : (long long)g.single.M * g.ldd) * 4};
+    cuuint32_t box[3] = {16, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, g.D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed");
+  }
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  MSFNO_CUDA_OK(attr_err);
+  ConvTcParams p{};
+  p.D = g.D; p.lda = g.lda; p.lda2 = g.A2 ? g.lda2 : 4; p.ldb = g.ldb; p.ldb2 = g.A2 ? g.ldb2 : 4; p.ldd = g.ldd;
+  p.sa = g.sa; p.sb = g.sb; p.sb2 = g.sb2; p.sd = g.sd;
+  p.bias = g.bias; p.sbias = g.sbias; p.add = g.add; p.ldadd = g.ldadd; p.sadd = g.sadd;
+  p.M = g.single.M; p.N = g.single.N; p.K1 = K1; p.K2 = K2; p.act_gelu = g.act_gelu; p.nstages = ns; p.nbuf = nbuf;
+  p.tilesN = (p.N + CT_BN - 1) / CT_BN;
+  const int tilesM = (p.M + CT_BM - 1) / CT_BM;
+  int sms = 148;
+  int gx = sms / (tilesM * g.ngroups);
+  if (gx < 1) gx = 1;
+  if (gx > p.tilesN) gx = p.tilesN;
+  dim3 grid(gx, tilesM, g.ngroups);
+  conv_tc_kernel<<<grid, 320, smem, st>>>(tmA, tmB, tmA2, tmB2, tmD, p);
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  *handled = 1;
+  return MSFNO_OK;
+}
+
+}  // namespace msfno

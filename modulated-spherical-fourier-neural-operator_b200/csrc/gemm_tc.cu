@@ -16,16 +16,12 @@
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator; afterwards all
 // 8 warps drain the accumulator (TMEM lane quarter q = warp % 4, column half = warp / 4).  BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32 fp32
 // (= one 128-byte swizzle span = 4 UMMA K-steps of 8).
-#include <cuda.h>
-
-#include <mutex>
-
-#include "common.cuh"
 #include "plan.h"
+#include "tc_common.cuh"
 
 namespace msfno {
 
-static constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 3;  // 3 x 32 KB stages -> two CTAs per SM (one's epilogue overlaps the other's main loop)
+static constexpr int TC_BM = 128, TC_BN = 128, TC_STAGES = 3;  // 3 x 32 KB stages -> two CTAs per SM (one's epilogue overlaps the other's main loop)
 static constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 static constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;  // 16 KB
 static constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
@@ -47,69 +43,6 @@ struct TcParams {
   long long lda2, ldb2, sa2, sb2;
   int K2;
 };
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
-          smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-// try_wait in a bounded loop: a faulty descriptor traps (error surfaced to the host) instead of hanging the SM
-__device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
-  const uint32_t addr = smem_u32(bar);
-  for (uint32_t it = 0; it < (1u << 24); ++it) {
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
-        "selp.b32 %0, 1, 0, P1;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-  }
-  __trap();
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// Shared-memory matrix descriptor, 128-byte swizzle, descriptor version 1.
-//   K-major : rows of 128 B (32 tf32 along K), 8-row atoms of 1024 B -> SBO = 1024, LBO unused (= 1)
-//   MN-major: k-rows of 128 B (32 tf32 along N), 8-k-row atoms of 1024 B -> SBO = 1024 (next 8 k),
-//             LBO = byte distance between consecutive 32-element N blocks
-//   layout_type: 2 = SWIZZLE_128B (16-byte swizzle atomicity), 1 = SWIZZLE_128B_BASE32B (32-byte atomicity: the only
-//   layout the tensor core accepts for MN-major 32-bit operands; its atoms are 4 k-rows of 128 B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
-                                                   uint32_t layout_type = 2) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)layout_type << 61;
-  return d;
-}
-__device__ __forceinline__ float round_to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
 
 template <bool B_MN>
 __global__ void __launch_bounds__(256, 2)
@@ -254,7 +187,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float t = __uint_as_float(r[j]) + bv;
-          if (p.act_gelu) t = gelu_erf(t);
+          if (p.act_gelu) t = gelu_fast(t);
           v[j] = t;
         }
         if (arow) {
@@ -295,40 +228,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  static std::once_flag once;
-  std::call_once(once, [] {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  });
-  return fn;
-}
-
-// 2-D fp32 tensor [rows][ld] (cols valid), box = 32 columns x box_rows rows, 128-byte swizzle
-static int make_map(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows,
-                    bool atom32 = false) {
-  EncodeTiledFn enc = get_encode();
-  if (!enc) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, atom32 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled failed");
-  return MSFNO_OK;
-}
-
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool gemm_tc_supported(const GemmLaunch& g) {

@@ -107,4 +107,9 @@ int launch_rfft2d(const msfno_plan* p, const float* x, float* Xt, const float* m
 int launch_irfft2d(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
                    const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st);
 
+// persistent weight-stationary conv kernel (conv_tc.cu); *handled = 0 -> caller falls back to launch_gemm_tc
+int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
+                   long long a2_rows, long long a2_cols, long long b2_rows, long long b2_cols, int* handled,
+                   cudaStream_t st);
+
 }  // namespace msfno

@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_tc.py -q -m gpu --tb=line -k "conv1x1 or small_net" > gpurun_out/test_gpu_tc.log 2>&1; echo "tc exit $?" >> gpurun_out/summary.txt
+tail -8 gpurun_out/test_gpu_tc.log
+timeout 600 python tools/time_convs.py > gpurun_out/convs.json 2> gpurun_out/convs.err; echo "convs exit $?" >> gpurun_out/summary.txt
+grep "tf32_ours" gpurun_out/convs.json; tail -3 gpurun_out/convs.err
+timeout 600 python bench.py --steps 10 --warmup 3 --precision tf32 --no-cpu-baseline > gpurun_out/bench_tf32.json 2> gpurun_out/bench_tf32.err; echo "bench exit $?" >> gpurun_out/summary.txt
+tail -3 gpurun_out/bench_tf32.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench_tf32.json')); print('tf32', d['ms_per_step'], d['value'], d['e2e'], d['gpu_launches'], d['output_finite'])"
+cat gpurun_out/summary.txt
