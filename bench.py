@@ -380,7 +380,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sfno12_nonlinear", choices=["sfno12_nonlinear", "sfno12_linear", "filter_linear"])
-    ap.add_argument("--precision", default=os.environ.get("MSFNO_PRECISION", "fp32"), choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default=os.environ.get("MSFNO_PRECISION", "tf32"), choices=["fp32", "tf32"],
+                    help="tf32: tensor-core tier (<= 2e-3 rel-L2 vs the reference, tests/test_gpu_tc.py); fp32: exact tier (<= 1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

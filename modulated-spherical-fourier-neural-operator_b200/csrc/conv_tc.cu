@@ -13,9 +13,9 @@
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
 // (TMEM lane quarter w % 4, column half (w - 2) / 4).
 // Output path: NCHW rows are HW*4 bytes (4 MB at 721x1440) apart, so a per-lane row store touches 32 pages per
-// instruction and runs at ~0.6 TB/s (measured); instead each epilogue warp writes 32x16 granules into a swizzled
-// smem staging buffer and hands them to the TMA engine (cp.async.bulk.tensor store), which writes 64-byte row
-// segments at DRAM speed.
+// instruction and runs at ~0.6 TB/s (measured); instead each epilogue warp writes 32x32 granules into a swizzled
+// smem staging buffer and hands them to the TMA engine (cp.async.bulk.tensor store), which writes 128-byte row
+// segments.
 #include "plan.h"
 #include "tc_common.cuh"
 
@@ -23,7 +23,8 @@ namespace msfno {
 
 static constexpr int CT_BM = 128, CT_BN = 128;
 static constexpr int CT_KB_BYTES = CT_BM * TC_BK * 4;  // one 128 x 32 fp32 operand block = 16 KB
-static constexpr int CT_MAX_KB = 11;                    // resident weight k-blocks (K1 + K2 <= 352)
+static constexpr int CT_MAX_KB = 8;                     // resident weight k-blocks of the first pair (K1 <= 256)
+static constexpr int CT_MAX_KB2 = 4;                    // streamed weight k-blocks of the second pair (K2 <= 128)
 
 struct ConvTcParams {
   float* D;
@@ -36,6 +37,7 @@ struct ConvTcParams {
   int nstages;   // ring depth for the streamed activation blocks
   int tilesN;
   int nbuf;      // staging buffers per epilogue warp (1 or 2)
+  int slot_bytes;  // ring slot: 16 KB (activations) or 32 KB (second-pair weights + activations)
 };
 
 __global__ void __launch_bounds__(320, 1)
@@ -51,17 +53,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
-  uint8_t* a_res = tiles;                                  // nkb resident weight blocks
-  uint8_t* ring = tiles + (size_t)nkb * CT_KB_BYTES;       // NS activation blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)NS * CT_KB_BYTES);
+  uint8_t* a_res = tiles;                                  // nkb1 resident weight blocks (first operand pair)
+  uint8_t* ring = tiles + (size_t)nkb1 * CT_KB_BYTES;      // NS slots: [optional second-pair weight block][activation block]
+  const int SLOT = p.slot_bytes, BOFF = SLOT - CT_KB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)NS * SLOT);
   uint64_t* full = bars;               // [NS]
   uint64_t* empty = bars + 8;          // [NS]
   uint64_t* a_full = bars + 16;
   uint64_t* tmem_full = bars + 17;     // [2]
   uint64_t* tmem_empty = bars + 19;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
-  // epilogue staging: 8 warps x nbuf x [32 rows][16 fp32] (2 KB, 64-byte swizzle), 1024-byte aligned
-  uint8_t* stage_base = ring + (size_t)NS * CT_KB_BYTES + 1024;
+  // epilogue staging: 8 warps x nbuf x [32 rows][32 fp32] (4 KB, 128-byte swizzle), 1024-byte aligned
+  uint8_t* stage_base = ring + (size_t)NS * SLOT + 1024;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -82,13 +85,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       // ---------------- TMA producer ----------------
       const long long aoff = (long long)b * p.sa;
-      mbar_arrive_expect_tx(a_full, (uint32_t)(nkb * CT_KB_BYTES));
-      for (int kb = 0; kb < nkb; ++kb) {
-        const bool second = kb >= nkb1;
-        const int kk = (second ? kb - nkb1 : kb) * TC_BK;
-        if (!second) tma_load_2d(a_res + (size_t)kb * CT_KB_BYTES, &tmA, a_full, (int)(aoff % p.lda) + kk, (int)(aoff / p.lda) + m0);
-        else tma_load_2d(a_res + (size_t)kb * CT_KB_BYTES, &tmA2, a_full, kk, m0);
-      }
+      mbar_arrive_expect_tx(a_full, (uint32_t)(nkb1 * CT_KB_BYTES));
+      for (int kb = 0; kb < nkb1; ++kb)
+        tma_load_2d(a_res + (size_t)kb * CT_KB_BYTES, &tmA, a_full, (int)(aoff % p.lda) + kb * TC_BK, (int)(aoff / p.lda) + m0);
       const int krow1 = (int)(((long long)b * p.sb) / p.ldb);
       const int krow2 = p.K2 ? (int)(((long long)b * p.sb2) / p.ldb2) : 0;
       uint32_t kc = 0;
@@ -101,8 +100,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int krow = second ? krow2 + (kb - nkb1) * TC_BK : krow1 + kb * TC_BK;
           const CUtensorMap* mb = second ? &tmB2 : &tmB;
           mbar_wait_bounded(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], CT_KB_BYTES);
-          uint8_t* dst = ring + (size_t)s * CT_KB_BYTES;
+          mbar_arrive_expect_tx(&full[s], second ? 2 * CT_KB_BYTES : CT_KB_BYTES);
+          uint8_t* slot = ring + (size_t)s * SLOT;
+          if (second) tma_load_2d(slot, &tmA2, &full[s], (kb - nkb1) * TC_BK, m0);   // streamed weight block of pair 2
+          uint8_t* dst = slot + BOFF;
 #pragma unroll
           for (int j = 0; j < CT_BN / 32; ++j) tma_load_2d(dst + j * (TC_BK * 128), mb, &full[s], n0 + 32 * j, krow);
         }
@@ -116,7 +117,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait_bounded(a_full, 0);
       tc_fence_after();
       uint32_t kc = 0, it = 0;
-      const uint32_t a_addr = base, r_addr = base + (uint32_t)nkb * CT_KB_BYTES;
+      const uint32_t a_addr = base, r_addr = base + (uint32_t)nkb1 * CT_KB_BYTES;
       for (int t = blockIdx.x; t < p.tilesN; t += gridDim.x, ++it) {
         const uint32_t acc = it & 1u, use = it >> 1;
         mbar_wait_bounded(&tmem_empty[acc], (use & 1u) ^ 1u);
@@ -126,7 +127,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t ph = (kc / NS) & 1u;
           mbar_wait_bounded(&full[s], ph);
           tc_fence_after();
-          const uint32_t sa = a_addr + (uint32_t)kb * CT_KB_BYTES, sb = r_addr + (uint32_t)s * CT_KB_BYTES;
+          const uint32_t slot = r_addr + (uint32_t)s * (uint32_t)SLOT;
+          const uint32_t sa = (kb < nkb1) ? a_addr + (uint32_t)kb * CT_KB_BYTES : slot, sb = slot + (uint32_t)BOFF;
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k)
             tc_mma_tf32(tmem_base + acc * CT_BN, make_smem_desc(sa + 32 * k, 16, 1024),
@@ -143,8 +145,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool row_ok = row < p.M;
     const float bv = (p.bias && row_ok) ? p.bias[(long long)b * p.sbias + row] : 0.0f;
     const float* arow = p.add ? p.add + (long long)b * p.sadd + (long long)row * p.ldadd : nullptr;
-    uint8_t* my_stage = stage_base + (size_t)(warp - 2) * p.nbuf * 2048;
-    const uint32_t sw = (uint32_t)((lane >> 1) & 3);   // 64-byte swizzle: 16-byte chunk index ^= (row >> 1) & 3
+    uint8_t* my_stage = stage_base + (size_t)(warp - 2) * p.nbuf * 4096;
+    const uint32_t sw = (uint32_t)(lane & 7);   // 128-byte swizzle: 16-byte chunk index ^= row & 7
     uint32_t it = 0, gcount = 0;
     for (int t = blockIdx.x; t < p.tilesN; t += gridDim.x, ++it) {
       const uint32_t acc = it & 1u, use = it >> 1;
@@ -152,38 +154,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait_bounded(&tmem_full[acc], use & 1u);
       tc_fence_after();
 #pragma unroll 1
-      for (int gq = 0; gq < 4; ++gq, ++gcount) {
-        const int c0 = chalf * 64 + gq * 16;
-        uint32_t r[16];
+      for (int gq = 0; gq < 2; ++gq, ++gcount) {
+        const int c0 = chalf * 64 + gq * 32;
+        uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CT_BN + (uint32_t)c0;
         asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (gq == 3) {
+        if (gq == 1) {
           // all TMEM reads of this warp for accumulator `acc` are done: hand it back to the MMA issuer early
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
         const int gn = n0 + c0;
-        float v[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float tv = __uint_as_float(r[j]) + bv;
-          if (p.act_gelu) tv = gelu_fast(tv);
-          v[j] = tv;
-        }
-        if (arow && row_ok) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (gn + j < p.N) v[j] += arow[gn + j];
-        }
         // staging buffer: wait until the TMA store that last used it has finished READING it
-        uint8_t* buf = my_stage + (gcount % p.nbuf) * 2048;
+        uint8_t* buf = my_stage + (gcount % p.nbuf) * 4096;
         if (gcount >= (uint32_t)p.nbuf) {
           if (lane == 0) {
             if (p.nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
@@ -191,9 +184,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           __syncwarp();
         }
-        float4* rowp = reinterpret_cast<float4*>(buf + lane * 64);
+        float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) rowp[ch ^ sw] = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
+        for (int ch = 0; ch < 8; ++ch) {
+          float v[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float tv = __uint_as_float(r[4 * ch + j]) + bv;
+            if (p.act_gelu) tv = gelu_fast(tv);
+            if (arow && row_ok && gn + 4 * ch + j < p.N) tv += arow[gn + 4 * ch + j];
+            v[j] = tv;
+          }
+          rowp[ch ^ sw] = make_float4(v[0], v[1], v[2], v[3]);
+        }
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
@@ -223,18 +226,19 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
                    cudaStream_t st) {
   *handled = 0;
   const int K1 = g.single.K, K2 = g.A2 ? g.K2 : 0;
-  const int nkb = (K1 + TC_BK - 1) / TC_BK + (K2 + TC_BK - 1) / TC_BK;
-  if (g.b_kmajor || !g.use_single || g.relu_even || nkb < 1 || nkb > CT_MAX_KB) return MSFNO_OK;
+  const int nkb1 = (K1 + TC_BK - 1) / TC_BK, nkb2 = (K2 + TC_BK - 1) / TC_BK;
+  if (g.b_kmajor || !g.use_single || g.relu_even || nkb1 < 1 || nkb1 > CT_MAX_KB || nkb2 > CT_MAX_KB2) return MSFNO_OK;
   if (g.sa % g.lda != 0 || g.sb % g.ldb != 0 || (g.A2 && (g.sa2 != 0 || g.sb2 % g.ldb2 != 0))) return MSFNO_OK;
-  // smem: [align 1024][nkb resident weight blocks][ns ring blocks][barriers, 1024][8 warps x nbuf x 2 KB staging]
-  const size_t total = 227 * 1024, fixed = 1024 + 1024 + (size_t)nkb * CT_KB_BYTES;
+  // smem: [align 1024][nkb1 resident weight blocks][ns ring slots][barriers, 1024][8 warps x nbuf x 4 KB staging]
+  const size_t total = 227 * 1024, fixed = 1024 + 1024 + (size_t)nkb1 * CT_KB_BYTES;
+  const size_t slot = nkb2 ? 2 * CT_KB_BYTES : CT_KB_BYTES;
   int nbuf = 2;
-  if (fixed + 2 * CT_KB_BYTES + 8 * 2 * 2048 > total) nbuf = 1;
-  const size_t stage_bytes = (size_t)8 * nbuf * 2048;
-  if (fixed + 2 * CT_KB_BYTES + stage_bytes > total) return MSFNO_OK;
-  int ns = (int)((total - fixed - stage_bytes) / CT_KB_BYTES);
+  if (fixed + 2 * slot + 8 * 2 * 4096 > total) nbuf = 1;
+  const size_t stage_bytes = (size_t)8 * nbuf * 4096;
+  if (fixed + 2 * slot + stage_bytes > total) return MSFNO_OK;
+  int ns = (int)((total - fixed - stage_bytes) / slot);
   if (ns > 4) ns = 4;
-  const size_t smem = fixed + (size_t)ns * CT_KB_BYTES + stage_bytes;
+  const size_t smem = fixed + (size_t)ns * slot + stage_bytes;
   if ((reinterpret_cast<uintptr_t>(g.D) & 15) || (g.ldd & 3) || (g.sd & 3)) return MSFNO_OK;
 
   CUtensorMap tmA, tmB, tmA2, tmB2;
@@ -251,7 +255,7 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     tmA2 = tmA;
     tmB2 = tmB;
   }
-  // output: 3-D tensor [batch][rows = out channels][cols = pixels], box 16 cols x 32 rows x 1, 64-byte swizzle;
+  // output: 3-D tensor [batch][rows = out channels][cols = pixels], box 32 cols x 32 rows x 1, 128-byte swizzle;
   // rows >= M and cols >= N are clipped by the TMA engine
   CUtensorMap tmD;
   {
@@ -259,10 +263,10 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     if (!enc) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     cuuint64_t dims[3] = {(cuuint64_t)g.single.N, (cuuint64_t)g.single.M, (cuuint64_t)g.ngroups};
     cuuint64_t strides[2] = {(cuuint64_t)g.ldd * 4, (cuuint64_t)(g.ngroups > 1 ? g.sd : (long long)g.single.M * g.ldd) * 4};
-    cuuint32_t box[3] = {16, 32, 1};
+    cuuint32_t box[3] = {32, 32, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, g.D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed");
   }
   static std::once_flag once;
@@ -275,7 +279,7 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   p.D = g.D; p.lda = g.lda; p.lda2 = g.A2 ? g.lda2 : 4; p.ldb = g.ldb; p.ldb2 = g.A2 ? g.ldb2 : 4; p.ldd = g.ldd;
   p.sa = g.sa; p.sb = g.sb; p.sb2 = g.sb2; p.sd = g.sd;
   p.bias = g.bias; p.sbias = g.sbias; p.add = g.add; p.ldadd = g.ldadd; p.sadd = g.sadd;
-  p.M = g.single.M; p.N = g.single.N; p.K1 = K1; p.K2 = K2; p.act_gelu = g.act_gelu; p.nstages = ns; p.nbuf = nbuf;
+  p.M = g.single.M; p.N = g.single.N; p.K1 = K1; p.K2 = K2; p.act_gelu = g.act_gelu; p.nstages = ns; p.nbuf = nbuf; p.slot_bytes = (int)slot;
   p.tilesN = (p.N + CT_BN - 1) / CT_BN;
   const int tilesM = (p.M + CT_BM - 1) / CT_BM;
   int sms = 148;
