@@ -134,7 +134,8 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
   }
 }
 
-template <int P1, int P2, int RW>
+// NZ > 0: only the first and last NZ rows of the P1 x P2 spectrum matrix can be non-zero (mlim <= NZ * P2).
+template <int P1, int P2, int RW, int NZ>
 __global__ void __launch_bounds__(256, 1)
 irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __restrict__ g_tw,
                const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ skip,
@@ -164,11 +165,23 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
   for (int i = threadIdx.x; i < H; i += blockDim.x) tw[i] = g_tw[i];
   for (int i = threadIdx.x; i <= mlim; i += blockDim.x) tw2[i] = g_tw2[i];
   const int nvalid = min(ROWS_PER_TILE2, nlat - k0);
-  for (int seg = warp; seg < 2 * mlim; seg += nw) {
-    const int m = seg >> 1, ri = seg & 1;
-    float v = 0.0f;
-    if (lane < nvalid) v = Yt[(((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane] * mscale[m];
-    istage[seg * OST2 + lane] = v;
+  // staging fill: 8 independent 128-byte segment loads in flight per lane
+  for (int seg0 = warp; seg0 < 2 * mlim; seg0 += nw * 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int seg = seg0 + u * nw;
+      v[u] = 0.0f;
+      if (seg < 2 * mlim && lane < nvalid) {
+        const int m = seg >> 1, ri = seg & 1;
+        v[u] = __ldg(Yt + (((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane) * mscale[m];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int seg = seg0 + u * nw;
+      if (seg < 2 * mlim) istage[seg * OST2 + lane] = v[u];
+    }
   }
   __syncthreads();
 
@@ -193,7 +206,9 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
         return v;
       };
       cf* wr = work + r * P1 * WP;
-      for (int k = lane; k < H; k += 32) {
+      constexpr int NBUILD = (NZ > 0) ? 2 * NZ * P2 : H;   // bins that can be non-zero: [0, NZ*P2) and [H - NZ*P2, H)
+      for (int kb = lane; kb < NBUILD; kb += 32) {
+        const int k = (NZ > 0 && kb >= NZ * P2) ? kb + (P1 - 2 * NZ) * P2 : kb;
         const int kk = H - k;
         cf o{0.0f, 0.0f};
         if (k < mlim || kk < mlim) {
@@ -209,7 +224,7 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
     __syncwarp();
     for (int t = lane; t < RW * P2; t += 32) {
       const int r = t / P2, n2 = t - r * P2;
-      if (r < nv) fft2d_step1<P1, P2, +1>(work + r * P1 * WP, WP, work + r * P1 * WP, tw, n2);
+      if (r < nv) fft2d_step1<P1, P2, +1, (NZ > 0 ? NZ : 0), (NZ > 0 ? P1 - NZ : 0)>(work + r * P1 * WP, WP, work + r * P1 * WP, tw, n2);
     }
     __syncwarp();
     for (int t = lane; t < RW * P1; t += 32) {
@@ -291,7 +306,7 @@ static int launch_fwd(const msfno_plan* p, const float* x, float* Xt, const floa
   return MSFNO_OK;
 }
 
-template <int P1, int P2, int RW>
+template <int P1, int P2, int RW, int NZ = 0>
 static int launch_inv(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
                       const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st) {
   constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
@@ -300,7 +315,12 @@ static int launch_inv(const msfno_plan* p, const float* Yt, float* y, const floa
   int nw; size_t smem;
   if (!pick_warps2(fixed, per_warp, ROWS_PER_TILE2 / RW, &nw, &smem))
     return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT does not fit in shared memory");
-  auto kern = irfft2d_kernel<P1, P2, RW>;
+  // prefer two resident CTAs per SM (one CTA's staging fill overlaps another's FFT phase) when 4 warps allow it
+  if (nw == 8) {
+    const size_t t4 = fixed + 512 + 4 * (((per_warp + 127) & ~(size_t)127) + 32);
+    if (t4 <= 112 * 1024 && RW == 1) { nw = 4; smem = t4; }   // (measured: helps the 1440-point rows, hurts RW = 4)
+  }
+  auto kern = irfft2d_kernel<P1, P2, RW, NZ>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p->nlat + ROWS_PER_TILE2 - 1) / ROWS_PER_TILE2, B * C);
   kern<<<grid, nw * 32, smem, st>>>(Yt, y, reinterpret_cast<const cf*>(p->d_tw), reinterpret_cast<const cf*>(p->d_tw2),
@@ -325,7 +345,9 @@ int launch_rfft2d(const msfno_plan* p, const float* x, float* Xt, const float* m
 int launch_irfft2d(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
                    const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st) {
   switch (p->nlon) {
-    case 1440: return launch_inv<24, 30, 1>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
+    case 1440:
+      if (p->mlim <= 4 * 30) return launch_inv<24, 30, 1, 4>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
+      return launch_inv<24, 30, 1>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
     case 240: return launch_inv<15, 8, 4>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
     case 2880: return launch_inv<36, 40, 1>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
     default: return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT: unsupported nlon");

@@ -13,14 +13,17 @@ namespace msfno {
 template <int P2> struct WorkPitch { static constexpr int value = P2 | 1; };
 
 // tw[t] = exp(-2 pi i t / H), t < H.
-template <int P1, int P2, int SGN>
+// Rows n1 in [ZLO, ZHI) of the input matrix are known to be zero (truncated spectrum of the inverse transform): they
+// are neither stored by the caller nor loaded here.
+template <int P1, int P2, int SGN, int ZLO = 0, int ZHI = 0>
 MSFNO_HD void fft2d_step1(const cf* __restrict__ in, int in_n1_stride, cf* __restrict__ work, const cf* __restrict__ tw,
                           int n2) {
   constexpr int WP = WorkPitch<P2>::value;
   cf v[P1];
   static_for<0, P1>([&](auto c) {
     constexpr int n1 = decltype(c)::value;
-    v[n1] = in[n1 * in_n1_stride + n2];
+    if constexpr (n1 >= ZLO && n1 < ZHI) v[n1] = cf{0.0f, 0.0f};
+    else v[n1] = in[n1 * in_n1_stride + n2];
   });
   RegDft<P1, SGN>::run(v);
   static_for<0, P1>([&](auto c) {

@@ -10,7 +10,7 @@
 #include "FFT2D_CORE_HOST"
 using namespace msfno;
 
-template <int P1, int P2>
+template <int P1, int P2, int NZ = 0>
 static int run(int mode, int N, int M) {
   constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
   std::vector<cf> tw(H), tw2(M + 1), raw(H), work(P1 * WP), xs(H), out(H);
@@ -30,7 +30,10 @@ static int run(int mode, int N, int M) {
     std::vector<cf> X(M);
     for (int i = 0; i < M; ++i) if (scanf("%f %f", &X[i].x, &X[i].y) != 2) return 1;
     auto Xh = [&](int q) -> cf { if (q >= mlim) return cf{0, 0}; cf v = X[q]; if (q == 0 || q == H) v.y = 0; return v; };
-    for (int k = 0; k < H; ++k) {
+    for (auto& w : work) w = cf{NAN, NAN};   // rows the pruned variant must never read
+    const int NBUILD = (NZ > 0) ? 2 * NZ * P2 : H;
+    for (int kb = 0; kb < NBUILD; ++kb) {
+      const int k = (NZ > 0 && kb >= NZ * P2) ? kb + (P1 - 2 * NZ) * P2 : kb;
       const int kk = H - k;
       cf o{0, 0};
       if (k < mlim || kk < mlim) {
@@ -40,7 +43,7 @@ static int run(int mode, int N, int M) {
       }
       work[(k / P2) * WP + (k % P2)] = o;   // Zt laid out as [n1][n2] with the padded pitch
     }
-    for (int n2 = 0; n2 < P2; ++n2) fft2d_step1<P1, P2, +1>(work.data(), WP, work.data(), tw.data(), n2);
+    for (int n2 = 0; n2 < P2; ++n2) fft2d_step1<P1, P2, +1, (NZ > 0 ? NZ : 0), (NZ > 0 ? P1 - NZ : 0)>(work.data(), WP, work.data(), tw.data(), n2);
     for (int k1 = 0; k1 < P1; ++k1) {
       cf v[P2];
       fft2d_step2<P1, P2, +1>(work.data(), k1, v);
@@ -55,7 +58,7 @@ int main() {
   int mode, N, M;
   if (scanf("%d %d %d", &mode, &N, &M) != 3) return 1;
   switch (N / 2) {
-    case 720: return run<24, 30>(mode, N, M);
+    case 720: return (M <= 120) ? run<24, 30, 4>(mode, N, M) : run<24, 30>(mode, N, M);
     case 120: return run<15, 8>(mode, N, M);
     case 1440: return run<36, 40>(mode, N, M);
     case 24: return run<4, 6>(mode, N, M);

@@ -118,3 +118,32 @@ def test_fft_core_host_emulation(tmp_path):
         goti = run(1, N, M, np.stack([X.real, X.imag], 1))
         refi = np.fft.irfft(X.astype(np.complex128), n=N, norm="forward")
         assert np.linalg.norm(goti - refi) / np.linalg.norm(refi) < 1e-6
+
+
+def test_fft2d_core_host_emulation(tmp_path):
+    """csrc/fft2d_core.cuh + fft_reg.cuh (four-step FFT with in-register DFTs and compile-time twiddles, including the
+    pruned inverse that never reads the all-zero spectrum rows) compiled for the host, against numpy.fft."""
+    csrc = os.path.join(ROOT, "modulated-spherical-fourier-neural-operator_b200", "csrc")
+    for f in ("fft_core.cuh", "fft_reg.cuh", "fft2d_core.cuh"):
+        (tmp_path / f).write_text(open(os.path.join(csrc, f)).read().replace("#include <cuda_runtime.h>", ""))
+    src = open(os.path.join(ROOT, "tests", "host_emul", "fft2d_emul.cpp")).read()
+    cpp = tmp_path / "emul2d.cpp"
+    cpp.write_text(src.replace('"FFT2D_CORE_HOST"', '"%s"' % (tmp_path / "fft2d_core.cuh")))
+    exe = str(tmp_path / "emul2d")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, str(cpp)], check=True)
+
+    def run(mode, N, M, vals):
+        inp = "%d %d %d\n" % (mode, N, M) + "\n".join("%.9g %.9g" % (a, b) for a, b in vals)
+        out = subprocess.run([exe], input=inp, capture_output=True, text=True, check=True).stdout.split()
+        return np.array(out, dtype=np.float64)
+
+    rng = np.random.default_rng(0)
+    for N, M in ((1440, 120), (1440, 121), (240, 120), (2880, 240), (48, 25), (72, 9)):
+        x = rng.standard_normal(N).astype(np.float32)
+        got = run(0, N, M, x.reshape(-1, 2)).reshape(-1, 2)
+        ref = np.fft.rfft(x.astype(np.float64))[:M]
+        assert np.linalg.norm(got[:, 0] + 1j * got[:, 1] - ref) / np.linalg.norm(ref) < 1e-6
+        X = (rng.standard_normal(M) + 1j * rng.standard_normal(M)).astype(np.complex64)
+        goti = run(1, N, M, np.stack([X.real, X.imag], 1))
+        refi = np.fft.irfft(X.astype(np.complex128), n=N, norm="forward")
+        assert np.linalg.norm(goti - refi) / np.linalg.norm(refi) < 1e-6
