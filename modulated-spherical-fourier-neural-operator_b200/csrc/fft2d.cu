@@ -156,6 +156,8 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
   off = (off + 15) & ~(size_t)15;
   double* red = reinterpret_cast<double*>(smem_raw + off);
   off += sizeof(double) * 2 * nw;
+  float* msc = reinterpret_cast<float*>(smem_raw + off);   // per-order scale
+  off += sizeof(float) * mlim;
   off = (off + 127) & ~(size_t)127;
   const size_t per_warp = sizeof(cf) * ((size_t)RW * P1 * WP + (size_t)RW * H);
   unsigned char* wbase = smem_raw + off + (size_t)warp * ((per_warp + 127) & ~(size_t)127);
@@ -165,24 +167,20 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
   for (int i = threadIdx.x; i < H; i += blockDim.x) tw[i] = g_tw[i];
   for (int i = threadIdx.x; i <= mlim; i += blockDim.x) tw2[i] = g_tw2[i];
   const int nvalid = min(ROWS_PER_TILE2, nlat - k0);
-  // staging fill: 8 independent 128-byte segment loads in flight per lane
-  for (int seg0 = warp; seg0 < 2 * mlim; seg0 += nw * 8) {
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int seg = seg0 + u * nw;
-      v[u] = 0.0f;
-      if (seg < 2 * mlim && lane < nvalid) {
-        const int m = seg >> 1, ri = seg & 1;
-        v[u] = __ldg(Yt + (((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane) * mscale[m];
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int seg = seg0 + u * nw;
-      if (seg < 2 * mlim) istage[seg * OST2 + lane] = v[u];
+  // staging fill: every 128-byte segment is fetched with fire-and-forget cp.async (LDGSTS), so all ~2*mlim/nw loads
+  // of a lane are in flight at once instead of one DRAM round trip per batch (the profile showed half of the kernel's
+  // stall samples on the first use of these loads); the per-order scale is applied when the spectrum is read
+  for (int seg = warp; seg < 2 * mlim; seg += nw) {
+    const int m = seg >> 1, ri = seg & 1;
+    if (lane < nvalid) {
+      const float* src = Yt + (((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(istage + seg * OST2 + lane)), "l"(src) : "memory");
+    } else {
+      istage[seg * OST2 + lane] = 0.0f;
     }
   }
+  for (int i = threadIdx.x; i < mlim; i += blockDim.x) msc[i] = mscale[i];
+  asm volatile("cp.async.wait_all;\n" ::: "memory");
   __syncthreads();
 
   const float osc = out_scale ? out_scale[bc] : 1.0f;
@@ -201,7 +199,8 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
       const int rr = g * RW + r;
       auto Xh = [&](int q) -> cf {
         if (q >= mlim) return cf{0.0f, 0.0f};
-        cf v{istage[(2 * q) * OST2 + rr], istage[(2 * q + 1) * OST2 + rr]};
+        const float ms = msc[q];
+        cf v{istage[(2 * q) * OST2 + rr] * ms, istage[(2 * q + 1) * OST2 + rr] * ms};
         if (q == 0 || q == H) v.y = 0.0f;
         return v;
       };
@@ -310,7 +309,7 @@ template <int P1, int P2, int RW, int NZ = 0>
 static int launch_inv(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
                       const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st) {
   constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
-  const size_t fixed = sizeof(cf) * (H + p->mlim + 1) + sizeof(float) * 2 * p->mlim * OST2 + 16 * 8;
+  const size_t fixed = sizeof(cf) * (H + p->mlim + 1) + sizeof(float) * 2 * p->mlim * OST2 + 16 * 8 + sizeof(float) * p->mlim + 128;
   const size_t per_warp = sizeof(cf) * ((size_t)RW * P1 * WP + (size_t)RW * H);
   int nw; size_t smem;
   if (!pick_warps2(fixed, per_warp, ROWS_PER_TILE2 / RW, &nw, &smem))
