@@ -16,7 +16,9 @@ namespace msfno {
 static constexpr int ROWS_PER_TILE2 = 32;
 static constexpr int OST2 = 33;
 
-template <int P1, int P2, int RW>
+// NZ2 > 0: mlim <= NZ2 * P1, so only output columns k2 in [0, NZ2) and [P2 - NZ2, P2) of the second step are ever
+// needed by the real split -- a compile-time set: the other outputs of the in-register DFT are dead code.
+template <int P1, int P2, int RW, int NZ2>
 __global__ void __launch_bounds__(256, 1)
 rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __restrict__ g_tw,
               const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ in_scale,
@@ -28,7 +30,9 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
   const int bc = blockIdx.y;
   const int b = bc / C, c = bc - b * C;
   const int k0 = blockIdx.x * ROWS_PER_TILE2;
-  const int XS = xs_size(H, mlim);
+  constexpr int KEEP_STATIC = NZ2 * P1;                 // bins [0, KEEP) and [H - KEEP, H) are stored
+  const int keep = (NZ2 > 0) ? KEEP_STATIC : mlim;
+  const int XS = xs_size(H, keep);
 
   cf* tw = reinterpret_cast<cf*>(smem_raw);
   cf* tw2 = tw + H;
@@ -100,8 +104,13 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
         cf* xr = xs + r * XS;
         static_for<0, P2>([&](auto cc) {
           constexpr int k2 = decltype(cc)::value;
-          const int xi = xs_index(k1 + P1 * k2, H, mlim);
-          if (xi >= 0) xr[xi] = v[k2];
+          if constexpr (NZ2 > 0) {
+            if constexpr (k2 < NZ2) xr[k1 + P1 * k2] = v[k2];
+            else if constexpr (k2 >= P2 - NZ2) xr[k1 + P1 * k2 - (H - 2 * KEEP_STATIC)] = v[k2];
+          } else {
+            const int xi = xs_index(k1 + P1 * k2, H, mlim);
+            if (xi >= 0) xr[xi] = v[k2];
+          }
         });
       }
     }
@@ -110,7 +119,7 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
     for (int r = 0; r < nv; ++r) {
       const int rr = g * RW + r;  // row inside the 32-row tile
       for (int m = lane; m < mlim; m += 32) {
-        cf X = r2c_split_xs(xs + r * XS, tw2, H, mlim, m);
+        cf X = r2c_split_xs(xs + r * XS, tw2, H, keep, m);
         const float ms = mscale[m];
         X.x *= ms * sc_in;
         X.y *= ms * sc_in;
@@ -285,17 +294,17 @@ static bool pick_warps2(size_t fixed, size_t per_warp, int max_groups, int* nwar
   return false;
 }
 
-template <int P1, int P2, int RW>
+template <int P1, int P2, int RW, int NZ2 = 0>
 static int launch_fwd(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
                       const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st) {
   constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
-  const int XS = xs_size(H, p->mlim);
+  const int XS = xs_size(H, NZ2 > 0 ? NZ2 * P1 : p->mlim);
   const size_t fixed = sizeof(cf) * (H + p->mlim + 1) + sizeof(float) * 2 * p->mlim * OST2;
   const size_t per_warp = sizeof(cf) * ((size_t)2 * RW * H + (size_t)RW * P1 * WP + (size_t)RW * XS);
   int nw; size_t smem;
   if (!pick_warps2(fixed, per_warp, ROWS_PER_TILE2 / RW, &nw, &smem))
     return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT does not fit in shared memory");
-  auto kern = rfft2d_kernel<P1, P2, RW>;
+  auto kern = rfft2d_kernel<P1, P2, RW, NZ2>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p->nlat + ROWS_PER_TILE2 - 1) / ROWS_PER_TILE2, B * C);
   kern<<<grid, nw * 32, smem, st>>>(x, Xt, reinterpret_cast<const cf*>(p->d_tw), reinterpret_cast<const cf*>(p->d_tw2),
@@ -334,7 +343,9 @@ bool fft2d_supported(int nlon) { return nlon == 1440 || nlon == 240 || nlon == 2
 int launch_rfft2d(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
                   const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st) {
   switch (p->nlon) {
-    case 1440: return launch_fwd<24, 30, 1>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
+    case 1440:
+      if (p->mlim <= 5 * 24) return launch_fwd<24, 30, 1, 5>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
+      return launch_fwd<24, 30, 1>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
     case 240: return launch_fwd<15, 8, 4>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
     case 2880: return launch_fwd<36, 40, 1>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
     default: return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT: unsupported nlon");
