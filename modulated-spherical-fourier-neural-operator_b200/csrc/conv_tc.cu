@@ -10,12 +10,15 @@
 // replaces: nn.Conv2d(.., 1) + bias + nn.GELU + residual adds + torch.cat in the reference's channel MLPs
 //   (/root/reference MSFNO/Models/sfno/layers.py:161-168; sfnonet.py:232,249,671,682-684).
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
-// (TMEM lane quarter w % 4, column half (w - 2) / 4).
-// Output path: NCHW rows are HW*4 bytes (4 MB at 721x1440) apart, so a per-lane row store touches 32 pages per
-// instruction and runs at ~0.6 TB/s (measured); instead each epilogue warp writes 32x32 granules into a swizzled
-// smem staging buffer and hands them to the TMA engine (cp.async.bulk.tensor store), which writes 128-byte row
-// segments.
+// Operand roles: the ACTIVATION tile is the MN-major A operand (M = 128 pixels -> TMEM lanes), the resident weight slab
+// is the K-major B operand (N = 128 output channels -> TMEM columns).  With pixels on the lanes every epilogue warp
+// instruction reads / writes 32 CONSECUTIVE pixels of ONE channel: a coalesced 128-byte access that touches one page.
+// (Channels-on-lanes made each lane own a row; NCHW rows are HW*4 bytes = 4 MB apart, so one STG touched 32 pages and
+// ran at 0.6 TB/s, a staged TMA store reached 1.2 TB/s and the strided `add` loads doubled the kernel time --
+// profiles/r01_conv_experiments_*.json.)
+//
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-17 = epilogue
+// (TMEM lane quarter w % 4 = 32-pixel block, 32-channel chunk (w - 2) / 4).
 #include "plan.h"
 #include "tc_common.cuh"
 
@@ -36,14 +39,12 @@ struct ConvTcParams {
   int act_gelu;
   int nstages;   // ring depth for the streamed activation blocks
   int tilesN;
-  int nbuf;      // staging buffers per epilogue warp (1 or 2)
   int slot_bytes;  // ring slot: 16 KB (activations) or 32 KB (second-pair weights + activations)
 };
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(576, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
-               const __grid_constant__ CUtensorMap tmD, ConvTcParams p) {
+               const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * CT_BM;
@@ -63,14 +64,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tmem_full = bars + 17;     // [2]
   uint64_t* tmem_empty = bars + 19;    // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
-  // epilogue staging: 8 warps x nbuf x [32 rows][32 fp32] (4 KB, 128-byte swizzle), 1024-byte aligned
-  uint8_t* stage_base = ring + (size_t)NS * SLOT + 1024;
+  float* bias_s = reinterpret_cast<float*>(ring + (size_t)NS * SLOT + 512);   // [128] bias of this CTA's channels
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(a_full, 1);
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 16); }
     fence_mbar_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + CT_BM) {
+    const int ch = m0 + (int)threadIdx.x - 64;
+    bias_s[threadIdx.x - 64] = (p.bias && ch < p.M) ? p.bias[(long long)b * p.sbias + ch] : 0.0f;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(2 * CT_BN));
@@ -112,8 +116,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(CT_BN >> 3) << 17) |
-                             ((uint32_t)(CT_BM >> 4) << 24);
+      // D=f32, A=B=tf32, A MN-major (bit 15: activations, pixels contiguous), B K-major (weights), N = 128 channels
+      // at bit 17, M = 128 pixels at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(CT_BM >> 3) << 17) |
+                             ((uint32_t)(CT_BN >> 4) << 24);
       mbar_wait_bounded(a_full, 0);
       tc_fence_after();
       uint32_t kc = 0, it = 0;
@@ -131,85 +137,75 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t sa = (kb < nkb1) ? a_addr + (uint32_t)kb * CT_KB_BYTES : slot, sb = slot + (uint32_t)BOFF;
 #pragma unroll
           for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32(tmem_base + acc * CT_BN, make_smem_desc(sa + 32 * k, 16, 1024),
-                        make_smem_desc(sb + 1024 * k, TC_BK * 128, 512, 1), idesc, (kb | k) ? 1u : 0u);
+            tc_mma_tf32(tmem_base + acc * CT_BN, make_smem_desc(sb + 1024 * k, TC_BK * 128, 512, 1),
+                        make_smem_desc(sa + 32 * k, 16, 1024), idesc, (kb | k) ? 1u : 0u);
           tc_commit(&empty[s]);
         }
         tc_commit(&tmem_full[acc]);
       }
     }
   } else {
-    // ---------------- epilogue warps 2..9: TMEM lane quarter w % 4, column half (w - 2) / 4 ----------------
-    const int q = warp & 3, chalf = (warp - 2) >> 2;
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const float bv = (p.bias && row_ok) ? p.bias[(long long)b * p.sbias + row] : 0.0f;
-    const float* arow = p.add ? p.add + (long long)b * p.sadd + (long long)row * p.ldadd : nullptr;
-    uint8_t* my_stage = stage_base + (size_t)(warp - 2) * p.nbuf * 4096;
-    const uint32_t sw = (uint32_t)(lane & 7);   // 128-byte swizzle: 16-byte chunk index ^= row & 7
-    uint32_t it = 0, gcount = 0;
+    // ---------------- epilogue warps 2..17: lane = pixel (TMEM lane quarter w % 4), 32-channel chunk (w - 2) / 4 ------
+    const int q = warp & 3, cq = (warp - 2) >> 2;
+    const int c0 = cq * 32;                                  // first channel (accumulator column) of this warp
+    const int nch = min(32, p.M - m0 - c0);                  // valid channels of the chunk (<= 0: nothing to store)
+    uint32_t it = 0;
     for (int t = blockIdx.x; t < p.tilesN; t += gridDim.x, ++it) {
       const uint32_t acc = it & 1u, use = it >> 1;
-      const int n0 = t * CT_BN;
+      const int pix = t * CT_BN + q * 32 + lane;
+      const bool pix_ok = pix < p.N;
+      float* dptr = p.D + (long long)b * p.sd + (long long)(m0 + c0) * p.ldd + pix;
+      const float* aptr = p.add ? p.add + (long long)b * p.sadd + (long long)(m0 + c0) * p.ldadd + pix : nullptr;
       mbar_wait_bounded(&tmem_full[acc], use & 1u);
       tc_fence_after();
-#pragma unroll 1
-      for (int gq = 0; gq < 2; ++gq, ++gcount) {
-        const int c0 = chalf * 64 + gq * 32;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CT_BN + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (gq == 1) {
-          // all TMEM reads of this warp for accumulator `acc` are done: hand it back to the MMA issuer early
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        const int gn = n0 + c0;
-        // staging buffer: wait until the TMA store that last used it has finished READING it
-        uint8_t* buf = my_stage + (gcount % p.nbuf) * 4096;
-        if (gcount >= (uint32_t)p.nbuf) {
-          if (lane == 0) {
-            if (p.nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-          }
-          __syncwarp();
-        }
-        float4* rowp = reinterpret_cast<float4*>(buf + lane * 128);
+      uint32_t r[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * CT_BN + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      // this warp's TMEM reads of accumulator `acc` are done: hand it back to the MMA issuer before the math
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (pix_ok && nch > 0) {
+        // two halves of 16 channels keep the live register set small (576 threads per CTA)
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-          float v[4];
+        for (int h = 0; h < 2; ++h) {
+          const int jb = h * 16;
+          if (nch >= jb + 16) {
+            float av[16];
+            if (aptr) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float tv = __uint_as_float(r[4 * ch + j]) + bv;
-            if (p.act_gelu) tv = gelu_fast(tv);
-            if (arow && row_ok && gn + 4 * ch + j < p.N) tv += arow[gn + 4 * ch + j];
-            v[j] = tv;
+              for (int j = 0; j < 16; ++j) av[j] = __ldg(aptr + (long long)(jb + j) * p.ldadd);   // coalesced over lanes
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float tv = __uint_as_float(r[jb + j]) + bias_s[c0 + jb + j];
+              if (p.act_gelu) tv = gelu_fast(tv);
+              if (aptr) tv += av[j];
+              __stcs(dptr + (long long)(jb + j) * p.ldd, tv);                                       // coalesced over lanes
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (jb + j < nch) {
+                float tv = __uint_as_float(r[jb + j]) + bias_s[c0 + jb + j];
+                if (p.act_gelu) tv = gelu_fast(tv);
+                if (aptr) tv += __ldg(aptr + (long long)(jb + j) * p.ldadd);
+                __stcs(dptr + (long long)(jb + j) * p.ldd, tv);
+              }
+            }
           }
-          rowp[ch ^ sw] = make_float4(v[0], v[1], v[2], v[3]);
-        }
-        fence_proxy_async();
-        __syncwarp();
-        if (lane == 0) {
-          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(
-                           reinterpret_cast<uint64_t>(&tmD)),
-                       "r"(smem_u32(buf)), "r"(gn), "r"(m0 + q * 32), "r"(b)
-                       : "memory");
-          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
-    __syncwarp();
   }
   tc_fence_before();
   __syncthreads();
@@ -229,17 +225,13 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   const int nkb1 = (K1 + TC_BK - 1) / TC_BK, nkb2 = (K2 + TC_BK - 1) / TC_BK;
   if (g.b_kmajor || !g.use_single || g.relu_even || nkb1 < 1 || nkb1 > CT_MAX_KB || nkb2 > CT_MAX_KB2) return MSFNO_OK;
   if (g.sa % g.lda != 0 || g.sb % g.ldb != 0 || (g.A2 && (g.sa2 != 0 || g.sb2 % g.ldb2 != 0))) return MSFNO_OK;
-  // smem: [align 1024][nkb1 resident weight blocks][ns ring slots][barriers, 1024][8 warps x nbuf x 4 KB staging]
+  // smem: [align 1024][nkb1 resident weight blocks][ns ring slots][barriers + bias, 1024]
   const size_t total = 227 * 1024, fixed = 1024 + 1024 + (size_t)nkb1 * CT_KB_BYTES;
   const size_t slot = nkb2 ? 2 * CT_KB_BYTES : CT_KB_BYTES;
-  int nbuf = 2;
-  if (fixed + 2 * slot + 8 * 2 * 4096 > total) nbuf = 1;
-  const size_t stage_bytes = (size_t)8 * nbuf * 4096;
-  if (fixed + 2 * slot + stage_bytes > total) return MSFNO_OK;
-  int ns = (int)((total - fixed - stage_bytes) / slot);
-  if (ns > 4) ns = 4;
-  const size_t smem = fixed + (size_t)ns * slot + stage_bytes;
-  if ((reinterpret_cast<uintptr_t>(g.D) & 15) || (g.ldd & 3) || (g.sd & 3)) return MSFNO_OK;
+  if (fixed + 2 * slot > total) return MSFNO_OK;
+  int ns = (int)((total - fixed) / slot);
+  if (ns > 6) ns = 6;
+  const size_t smem = fixed + (size_t)ns * slot;
 
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, CT_BM);
@@ -255,20 +247,6 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     tmA2 = tmA;
     tmB2 = tmB;
   }
-  // output: 3-D tensor [batch][rows = out channels][cols = pixels], box 32 cols x 32 rows x 1, 128-byte swizzle;
-  // rows >= M and cols >= N are clipped by the TMA engine
-  CUtensorMap tmD;
-  {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
-    cuuint64_t dims[3] = {(cuuint64_t)g.single.N, (cuuint64_t)g.single.M, (cuuint64_t)g.ngroups};
-    cuuint64_t strides[2] = {(cuuint64_t)g.ldd * 4, (cuuint64_t)(g.ngroups > 1 ? g.sd : (long long)g.single.M * g.ldd) * 4};
-    cuuint32_t box[3] = {32, 32, 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&tmD, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, g.D, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled (output) failed");
-  }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
@@ -279,7 +257,7 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   p.D = g.D; p.lda = g.lda; p.lda2 = g.A2 ? g.lda2 : 4; p.ldb = g.ldb; p.ldb2 = g.A2 ? g.ldb2 : 4; p.ldd = g.ldd;
   p.sa = g.sa; p.sb = g.sb; p.sb2 = g.sb2; p.sd = g.sd;
   p.bias = g.bias; p.sbias = g.sbias; p.add = g.add; p.ldadd = g.ldadd; p.sadd = g.sadd;
-  p.M = g.single.M; p.N = g.single.N; p.K1 = K1; p.K2 = K2; p.act_gelu = g.act_gelu; p.nstages = ns; p.nbuf = nbuf; p.slot_bytes = (int)slot;
+  p.M = g.single.M; p.N = g.single.N; p.K1 = K1; p.K2 = K2; p.act_gelu = g.act_gelu; p.nstages = ns; p.slot_bytes = (int)slot;
   p.tilesN = (p.N + CT_BN - 1) / CT_BN;
   const int tilesM = (p.M + CT_BM - 1) / CT_BM;
   int sms = 148;
@@ -287,7 +265,7 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   if (gx < 1) gx = 1;
   if (gx > p.tilesN) gx = p.tilesN;
   dim3 grid(gx, tilesM, g.ngroups);
-  conv_tc_kernel<<<grid, 320, smem, st>>>(tmA, tmB, tmA2, tmB2, tmD, p);
+  conv_tc_kernel<<<grid, 576, smem, st>>>(tmA, tmB, tmA2, tmB2, p);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   *handled = 1;

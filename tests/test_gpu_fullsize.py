@@ -1,0 +1,127 @@
+"""GPU parity at BASELINE.json's FULL sizes (721x1440 grid, lmax 120 / mmax 121, 256 channels, 73 variables):
+size-independent properties (adjointness, linearity) and direct comparison with the oracle where it finishes in
+seconds on the host cores."""
+import pytest
+import torch
+
+from conftest import TOL_FP32, TOL_TF32, rel_l2
+from oracle import sfno_oracle, th_shim
+
+pytestmark = pytest.mark.gpu
+
+import msfno_b200
+
+NLAT, NLON, L, M = 721, 1440, 120, 121
+
+
+def _full_transforms():
+    sht = msfno_b200.RealSHT(NLAT, NLON, lmax=L, mmax=M, grid="equiangular").float().cuda()
+    isht = msfno_b200.InverseRealSHT(NLAT, NLON, lmax=L, mmax=M, grid="equiangular").float().cuda()
+    sht.weights = sht.weights * 1e5
+    isht.pct = isht.pct / 1e5
+    return sht, isht
+
+
+def _dot(a, b):
+    return float((a.double() * b.double()).sum())
+
+
+def test_adjointness_and_linearity_full_grid():
+    """<A x, c> == <x, A^T c> for the forward SHT and the inverse SHT (their backward kernels are the adjoints), and
+    A(a x1 + b x2) == a A x1 + b A x2, at 721x1440 with 32 channels."""
+    sht, isht = _full_transforms()
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 32, NLAT, NLON, generator=g).cuda().requires_grad_(True)
+    c = torch.randn(1, 32, L, M, 2, generator=g).cuda()
+    y = torch.view_as_real(sht(x))
+    y.backward(c)
+    lhs, rhs = _dot(y, c), _dot(x, x.grad)
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), float(y.double().norm() * c.double().norm()) * 1e-2)
+    cin = (torch.randn(1, 32, L, M, 2, generator=g) * 1e3).cuda().requires_grad_(True)
+    gy = torch.randn(1, 32, NLAT, NLON, generator=g).cuda()
+    out = isht(torch.view_as_complex(cin))
+    out.backward(gy)
+    lhs, rhs = _dot(out, gy), _dot(cin, cin.grad)
+    assert abs(lhs - rhs) <= 1e-5 * max(abs(lhs), abs(rhs), float(out.double().norm() * gy.double().norm()) * 1e-2)
+    with torch.no_grad():
+        x1, x2 = x.detach(), torch.randn(1, 32, NLAT, NLON, generator=g).cuda()
+        lin = torch.view_as_real(sht(0.5 * x1 - 2.0 * x2))
+        ref = 0.5 * torch.view_as_real(sht(x1)) - 2.0 * torch.view_as_real(sht(x2))
+        assert rel_l2(lin, ref) < 1e-5
+
+
+@pytest.mark.parametrize("tier,tol", [("fp32", TOL_FP32), ("tf32", TOL_TF32)])
+def test_full_size_nonlinear_filter_vs_oracle(tier, tol):
+    """BASELINE config-1 shape with the filter main.py actually runs: RealSHT -> SpectralAttentionS2 MLP ->
+    InverseRealSHT on 721x1440, 256 channels, batch 1 (oracle: a few seconds on the host cores)."""
+    msfno_b200.set_precision(tier)
+    try:
+        C = 256
+        o_s = th_shim.RealSHT(NLAT, NLON, lmax=L, mmax=M, grid="equiangular").float()
+        o_i = th_shim.InverseRealSHT(NLAT, NLON, lmax=L, mmax=M, grid="equiangular").float()
+        o_s.weights = o_s.weights * 1e5
+        o_i.pct = o_i.pct / 1e5
+        sht, isht = _full_transforms()
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(1, C, NLAT, NLON, generator=g)
+        ws = [0.02 * torch.randn(C, 2 * C, 2, generator=g), 0.02 * torch.randn(2 * C, 2 * C, 2, generator=g),
+              0.02 * torch.randn(2 * C, 2 * C, 2, generator=g)]
+        wout = 0.02 * torch.randn(2 * C, C, 2, generator=g)
+        with torch.no_grad():
+            want = sfno_oracle.spectral_attention_s2(x, ws, wout, o_s, o_i)
+        mod = msfno_b200.SpectralAttentionS2(sht, isht, C, hidden_size_factor=2, spectral_layers=3).cuda()
+        with torch.no_grad():
+            for p, w in zip(mod.w, ws):
+                p.copy_(w)
+            mod.wout.copy_(wout)
+            got = mod(x.cuda())
+        assert rel_l2(got, want) < tol
+    finally:
+        msfno_b200.set_precision("fp32")
+
+
+def test_full_size_linear_filter_vs_oracle():
+    """BASELINE configs[0]: RealSHT -> SpectralConvS2 -> InverseRealSHT on 721x1440 (64 channels so the oracle's einsum
+    stays in seconds; the kernel is channel-count agnostic), plus linearity in the weight at that size."""
+    C = 64
+    o_s = th_shim.RealSHT(NLAT, NLON, lmax=L, mmax=M, grid="equiangular").float()
+    o_i = th_shim.InverseRealSHT(NLAT, NLON, lmax=L, mmax=M, grid="equiangular").float()
+    o_s.weights = o_s.weights * 1e5
+    o_i.pct = o_i.pct / 1e5
+    sht, isht = _full_transforms()
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, C, NLAT, NLON, generator=g)
+    w = 0.02 * torch.randn(C, C, 7260, 2, generator=g)
+    with torch.no_grad():
+        want = sfno_oracle.spectral_conv_s2(x, w, o_s, o_i)
+    mod = msfno_b200.SpectralConvS2(sht, isht, C, use_complex_kernels=True).cuda()
+    with torch.no_grad():
+        mod.w.copy_(w)
+        got = mod(x.cuda())
+        assert rel_l2(got, want) < TOL_FP32
+        mod.w.mul_(-3.0)
+        assert rel_l2(mod(x.cuda()), -3.0 * got) < 1e-6
+
+
+@pytest.mark.parametrize("tier,tol", [("fp32", TOL_FP32), ("tf32", TOL_TF32)])
+def test_full_sfno_12_blocks_vs_oracle(tier, tol):
+    """BASELINE configs[1]: the full 12-block SFNO forward (73 variables, embed 256, 721x1440), identical random-init
+    weights in the oracle and in the CUDA path (state_dict copied)."""
+    msfno_b200.set_precision(tier)
+    try:
+        sd = sfno_oracle.make_state_dict(filter_type="non-linear", seed=0)
+        tr = sfno_oracle.Transforms()
+        g = torch.Generator().manual_seed(3)
+        x = torch.randn(1, 73, NLAT, NLON, generator=g)
+        with torch.no_grad():
+            want = sfno_oracle.sfno_forward(x, sd, tr, "non-linear", 12)
+        net = msfno_b200.FourierNeuralOperatorNet("cuda", None, filter_type="non-linear")
+        full = dict(net.state_dict())
+        full.update(sd)
+        net.load_state_dict(full, strict=True)
+        net = net.cuda().eval()
+        with torch.no_grad():
+            got = net(x.cuda())
+        assert rel_l2(got, want) < tol
+    finally:
+        msfno_b200.set_precision("fp32")
