@@ -98,7 +98,8 @@ int msfno_sht_bwd(msfno_plan* plan, const float* g_pm, const float* in_scale, fl
  * replaces: torch_harmonics.InverseRealSHT.forward (2 einsum '...lm,mlk->...km' + stack +
  *           irfft(n=nlon, norm="forward")), called from layers.py:421 and :638.
  * coef_cm (CM layout) -> y [B][C][nlat][nlon].  Fused epilogue, all optional:
- *   y = act( isht(coef) + skip_add ),  act = exact GELU when act_gelu != 0
+ *   y = act( isht(coef) + skip_add ),  act = exact GELU when (act_gelu & 1); (act_gelu & 2) additionally rounds y to
+ *   TF32 (round-to-nearest) because the next consumer is a tensor-core GEMM (tensor-core tier only)
  *   stats[b*C+c] += (sum y, sum y^2) in fp64 (feeds InstanceNorm norm1, sfnonet.py:237/376)
  * replaces additionally: `x + inner_skip(residual)` (sfnonet.py:232/371), act_layer (:235/374)
  * and the statistics pass of nn.InstanceNorm2d. */
@@ -188,7 +189,8 @@ int msfno_plane_affine(const float* x, const float* A, const float* S, float* y,
  * x: [B][Cin][HW] with batch stride x_bstride (floats); w: [Cout][ldw] row-major, ldw >= Cin, ldw % 4 == 0, columns
  * >= Cin zero; w_bstride != 0 selects per-sample weights (InstanceNorm/FiLM affine folded into the conv).
  * x2 / w2 (optional): second input accumulated into the same output (the decoder's concat of x and the big skip).
- * bias (optional, [Cout], bias_bstride 0 or Cout), add (optional, [Cout][HW], add_bstride 0 or Cout*HW). */
+ * bias (optional, [Cout], bias_bstride 0 or Cout), add (optional, [Cout][HW], add_bstride 0 or Cout*HW).
+ * precision: MSFNO_PREC_FP32 or MSFNO_PREC_TF32, optionally | 2 to round the outputs to TF32 (feeds another MMA). */
 int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const float* w, long ldw, long w_bstride,
                       const float* x2, long x2_bstride, int Cin2, const float* w2, long ldw2, const float* bias,
                       long bias_bstride, const float* add, long add_bstride, float* y, int B, int Cout, long HW,

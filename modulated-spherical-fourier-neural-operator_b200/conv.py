@@ -11,9 +11,18 @@ from ._lib import check, lib, ptr
 _pad_cache = {}
 
 
+def round_tf32(t):
+    """Round-to-nearest (ties away) to TF32, as cvt.rna.tf32.f32 does: tensor-core operands are otherwise truncated,
+    which biases every dot product towards zero."""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def padded_weight(weight):
-    """[Cout, Cin, 1, 1] (or [Cout, Cin]) -> contiguous [Cout, ceil4(Cin)] with zero padding, cached per version."""
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device))
+    """[Cout, Cin, 1, 1] (or [Cout, Cin]) -> contiguous [Cout, ceil4(Cin)] with zero padding (TF32-rounded in the
+    tensor-core tier), cached per version and tier."""
+    tf32 = _precision.get_precision() == "tf32"
+    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device), tf32)
     hit = _pad_cache.get(key)
     if hit is not None:
         return hit
@@ -23,6 +32,8 @@ def padded_weight(weight):
     if ld != cin:
         w2 = torch.nn.functional.pad(w2, (0, ld - cin))
     w2 = w2.contiguous()
+    if tf32:
+        w2 = round_tf32(w2)
     if len(_pad_cache) > 256:
         _pad_cache.clear()
     _pad_cache[key] = w2
@@ -30,7 +41,7 @@ def padded_weight(weight):
 
 
 def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, cin2=0, per_sample_w=False,
-            per_sample_bias=False):
+            per_sample_bias=False, final=False):
     """y = act(conv1x1(x, w) [+ conv1x1(x2, w2)] + bias) + add   for contiguous NCHW fp32 CUDA tensors.
     w: [Cout, ld] (or [B, Cout, ld] with per_sample_w) zero-padded rows; bias [Cout] (or [B, Cout]);
     add: [B or 1, Cout, H, W]."""
@@ -38,7 +49,11 @@ def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, ci
     HW = H * W
     cout = w.shape[-2]
     y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
-    prec = _lib.PREC_TF32 if _precision.get_precision() == "tf32" else _lib.PREC_FP32
+    prec = _lib.PREC_FP32
+    if _precision.get_precision() == "tf32":
+        prec = _lib.PREC_TF32 | (0 if final else 2)   # bit 1: TF32-round the output (it feeds another tensor-core GEMM)
+        if per_sample_w:
+            w = round_tf32(w)
     add_bs = 0
     if add is not None:
         add = add.contiguous()

@@ -6,12 +6,19 @@ OUT=../libmsfno_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 mkdir -p build
+SRCS="fft fft2d plan gemm_ffma specconv specattn sht elementwise gemm_tc conv_tc conv1x1"
 pids=()
-for f in fft fft2d plan gemm_ffma specconv specattn sht elementwise gemm_tc conv_tc conv1x1; do
-  [ -f $f.cu ] || continue
-  ( $NVCC $FLAGS -c $f.cu -o build/$f.o > build/$f.log 2>&1 || { cat build/$f.log; exit 1; } ) &
+for f in $SRCS; do
+  rm -f build/$f.o
+  ( $NVCC $FLAGS -c $f.cu -o build/$f.o > build/$f.log 2>&1 ) &
   pids+=($!)
 done
-for p in "${pids[@]}"; do wait $p; done
-$NVCC -shared -o $OUT build/*.o -lcudart
+fail=0
+for p in "${pids[@]}"; do wait $p || fail=1; done
+for f in $SRCS; do
+  if [ ! -f build/$f.o ]; then echo "=== nvcc failed on $f.cu ==="; grep -v "^ptxas info\|Function properties\|bytes stack frame\|Compiling entry\|^$" build/$f.log | head -30; fail=1; fi
+done
+[ $fail -eq 0 ] || { echo "BUILD FAILED"; exit 1; }
+OBJS=""; for f in $SRCS; do OBJS="$OBJS build/$f.o"; done
+$NVCC -shared -o $OUT $OBJS -lcudart
 echo "built $OUT"

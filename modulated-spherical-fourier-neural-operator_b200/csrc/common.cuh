@@ -48,6 +48,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ float rna_tf32_dev(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 // GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7 absolute): 2 MUFU + ~12 FMA instead of the ~40
 // instructions of erff.  Used by the tensor-core kernels, whose tier tolerance (2e-3) it undercuts by four orders.

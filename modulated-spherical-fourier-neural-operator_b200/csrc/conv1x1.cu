@@ -17,6 +17,9 @@ extern "C" int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const 
                                  const float* x2, long x2_bstride, int Cin2, const float* w2, long ldw2,
                                  const float* bias, long bias_bstride, const float* add, long add_bstride, float* y,
                                  int B, int Cout, long HW, int act_gelu, int precision, void* stream) {
+  // bit 1 of `precision`: round the outputs to TF32 (they feed another tensor-core GEMM)
+  const int round_out = (precision >> 1) & 1;
+  precision &= 1;
   if (!x || !w || !y || B < 1 || Cin < 1 || Cout < 1 || HW < 1 || ldw < Cin || (x2 && (!w2 || Cin2 < 1 || ldw2 < Cin2)))
     return record_error(MSFNO_ERR_BAD_SHAPE, "conv1x1_fwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
@@ -41,9 +44,9 @@ extern "C" int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const 
     const long long b_rows = (long long)(B - 1) * (x_bstride / HW) + Cin;
     const long long b2_rows = x2 ? (long long)(B - 1) * (x2_bstride / HW) + Cin2 : 0;
     int handled = 0;
-    int rc = launch_conv_tc(g, a_rows, ldw, b_rows, HW, Cout, ldw2, b2_rows, HW, &handled, st);
+    int rc = launch_conv_tc(g, a_rows, ldw, b_rows, HW, Cout, ldw2, b2_rows, HW, &handled, st, round_out);
     if (rc || handled) return rc;
-    return launch_gemm_tc(g, a_rows, ldw, b_rows, HW, 0, st, Cout, ldw2, b2_rows, HW);
+    return launch_gemm_tc(g, a_rows, ldw, b_rows, HW, round_out, st, Cout, ldw2, b2_rows, HW);
   }
   return launch_gemm_ffma(g, st);
 }

@@ -40,6 +40,7 @@ struct ConvTcParams {
   int nstages;   // ring depth for the streamed activation blocks
   int tilesN;
   int slot_bytes;  // ring slot: 16 KB (activations) or 32 KB (second-pair weights + activations)
+  int round_tf32;  // round outputs to TF32 (they feed another tensor-core GEMM)
 };
 
 __global__ void __launch_bounds__(576, 1)
@@ -190,6 +191,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               float tv = __uint_as_float(r[jb + j]) + bias_s[c0 + jb + j];
               if (p.act_gelu) tv = gelu_fast(tv);
               if (aptr) tv += av[j];
+              if (p.round_tf32) tv = round_to_tf32(tv);
               __stcs(dptr + (long long)(jb + j) * p.ldd, tv);                                       // coalesced over lanes
             }
           } else {
@@ -199,6 +201,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 float tv = __uint_as_float(r[jb + j]) + bias_s[c0 + jb + j];
                 if (p.act_gelu) tv = gelu_fast(tv);
                 if (aptr) tv += __ldg(aptr + (long long)(jb + j) * p.ldadd);
+                if (p.round_tf32) tv = round_to_tf32(tv);
                 __stcs(dptr + (long long)(jb + j) * p.ldd, tv);
               }
             }
@@ -219,7 +222,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // generic engine" (shape outside what the weight-stationary layout supports).
 int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
                    long long a2_rows, long long a2_cols, long long b2_rows, long long b2_cols, int* handled,
-                   cudaStream_t st) {
+                   cudaStream_t st, int round_tf32) {
   *handled = 0;
   const int K1 = g.single.K, K2 = g.A2 ? g.K2 : 0;
   const int nkb1 = (K1 + TC_BK - 1) / TC_BK, nkb2 = (K2 + TC_BK - 1) / TC_BK;
@@ -257,7 +260,7 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   p.D = g.D; p.lda = g.lda; p.lda2 = g.A2 ? g.lda2 : 4; p.ldb = g.ldb; p.ldb2 = g.A2 ? g.ldb2 : 4; p.ldd = g.ldd;
   p.sa = g.sa; p.sb = g.sb; p.sb2 = g.sb2; p.sd = g.sd;
   p.bias = g.bias; p.sbias = g.sbias; p.add = g.add; p.ldadd = g.ldadd; p.sadd = g.sadd;
-  p.M = g.single.M; p.N = g.single.N; p.K1 = K1; p.K2 = K2; p.act_gelu = g.act_gelu; p.nstages = ns; p.slot_bytes = (int)slot;
+  p.M = g.single.M; p.N = g.single.N; p.K1 = K1; p.K2 = K2; p.act_gelu = g.act_gelu; p.nstages = ns; p.slot_bytes = (int)slot; p.round_tf32 = round_tf32;
   p.tilesN = (p.N + CT_BN - 1) / CT_BN;
   const int tilesM = (p.M + CT_BM - 1) / CT_BM;
   int sms = 148;

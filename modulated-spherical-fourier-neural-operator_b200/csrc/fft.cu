@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(256, 1)
 rfft_trunc_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __restrict__ g_tw,
                   const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ in_scale,
                   const float* __restrict__ in_shift, FftSchedule sched, int nlat, int nlon, int mlim, int kpad, int C,
-                  int zero_imag, int use_bulk) {
+                  int zero_imag, int use_bulk, int round_tf32) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int H = nlon >> 1;
   const int nw = blockDim.x >> 5;
@@ -113,7 +113,8 @@ rfft_trunc_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf*
   const int nvalid = min(ROWS_PER_TILE, nlat - k0);
   for (int seg = warp; seg < 2 * mlim; seg += nw) {
     const int m = seg >> 1, ri = seg & 1;
-    const float v = (lane < nvalid) ? ostage[seg * OST + lane] : 0.0f;
+    float v = (lane < nvalid) ? ostage[seg * OST + lane] : 0.0f;
+    if (round_tf32) { uint32_t rr; asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(rr) : "f"(v)); v = __uint_as_float(rr); }
     Xt[(((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane] = v;
   }
 }
@@ -195,7 +196,8 @@ irfft_trunc_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf
         float4 v = row4[i];
         v.x *= osc; v.y *= osc; v.z *= osc; v.w *= osc;
         if (skip4) { const float4 s = skip4[i]; v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w; }
-        if (act_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+        if (act_gelu & 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+        if (act_gelu & 2) { v.x = rna_tf32_dev(v.x); v.y = rna_tf32_dev(v.y); v.z = rna_tf32_dev(v.z); v.w = rna_tf32_dev(v.w); }
         lsum += (v.x + v.y) + (v.z + v.w);
         lsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         y4[i] = v;
@@ -204,7 +206,8 @@ irfft_trunc_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf
       for (int i = lane; i < nlon; i += 32) {
         float v = row[i] * osc;
         if (skip) v += skip[goff + i];
-        if (act_gelu) v = gelu_erf(v);
+        if (act_gelu & 1) v = gelu_erf(v);
+        if (act_gelu & 2) v = rna_tf32_dev(v);
         lsum += v;
         lsq += v * v;
         y[goff + i] = v;
@@ -259,7 +262,8 @@ int launch_rfft_trunc(const msfno_plan* p, const float* x, float* Xt, const floa
   dim3 grid((p->nlat + ROWS_PER_TILE - 1) / ROWS_PER_TILE, B * C);
   rfft_trunc_kernel<<<grid, nw * 32, smem, st>>>(x, Xt, reinterpret_cast<const cf*>(p->d_tw),
                                                  reinterpret_cast<const cf*>(p->d_tw2), mscale, in_scale, in_shift,
-                                                 p->sched, p->nlat, p->nlon, p->mlim, p->kpad, C, zero_imag, use_bulk);
+                                                 p->sched, p->nlat, p->nlon, p->mlim, p->kpad, C, zero_imag, use_bulk,
+                                                 (p->precision == MSFNO_PREC_TF32 && !zero_imag) ? 1 : 0);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

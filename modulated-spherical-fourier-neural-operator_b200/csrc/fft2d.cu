@@ -22,7 +22,7 @@ template <int P1, int P2, int RW, int NZ2>
 __global__ void __launch_bounds__(256, 1)
 rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __restrict__ g_tw,
               const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ in_scale,
-              const float* __restrict__ in_shift, int nlat, int mlim, int kpad, int C, int zero_imag) {
+              const float* __restrict__ in_shift, int nlat, int mlim, int kpad, int C, int zero_imag, int round_tf32) {
   constexpr int H = P1 * P2, NLON = 2 * H, WP = WorkPitch<P2>::value;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nw = blockDim.x >> 5;
@@ -138,7 +138,8 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
   const int nvalid = min(ROWS_PER_TILE2, nlat - k0);
   for (int seg = warp; seg < 2 * mlim; seg += nw) {
     const int m = seg >> 1, ri = seg & 1;
-    const float v = (lane < nvalid) ? ostage[seg * OST2 + lane] : 0.0f;
+    float v = (lane < nvalid) ? ostage[seg * OST2 + lane] : 0.0f;
+    if (round_tf32) { uint32_t rr; asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(rr) : "f"(v)); v = __uint_as_float(rr); }
     Xt[(((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane] = v;
   }
 }
@@ -258,7 +259,8 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
         float4 v = row4[i];
         v.x *= osc; v.y *= osc; v.z *= osc; v.w *= osc;
         if (skip4) { const float4 s = skip4[i]; v.x += s.x; v.y += s.y; v.z += s.z; v.w += s.w; }
-        if (act_gelu) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+        if (act_gelu & 1) { v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w); }
+        if (act_gelu & 2) { v.x = rna_tf32_dev(v.x); v.y = rna_tf32_dev(v.y); v.z = rna_tf32_dev(v.z); v.w = rna_tf32_dev(v.w); }
         lsum += (v.x + v.y) + (v.z + v.w);
         lsq += (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
         y4[i] = v;
@@ -308,7 +310,8 @@ static int launch_fwd(const msfno_plan* p, const float* x, float* Xt, const floa
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p->nlat + ROWS_PER_TILE2 - 1) / ROWS_PER_TILE2, B * C);
   kern<<<grid, nw * 32, smem, st>>>(x, Xt, reinterpret_cast<const cf*>(p->d_tw), reinterpret_cast<const cf*>(p->d_tw2),
-                                    mscale, in_scale, in_shift, p->nlat, p->mlim, p->kpad, C, zero_imag);
+                                    mscale, in_scale, in_shift, p->nlat, p->mlim, p->kpad, C, zero_imag,
+                                    (p->precision == MSFNO_PREC_TF32 && !zero_imag) ? 1 : 0);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

@@ -30,27 +30,36 @@ int record_cuda_error(cudaError_t e, const char* file, int line) {
 
 // ---- table re-layout --------------------------------------------------------------------
 // T: [mmax][lmax][nlat] (reference layout).  tab_lk[m][j][k] = T[m][m+j][k], zero padded.
+__device__ __forceinline__ float rna_tf32_f(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// round_tf32: store round-to-nearest TF32 values (tensor-core tier: the MMA truncates its fp32 operands, which would bias
+// every Legendre sum towards zero; rounding the tables and the other operand at their producers removes the bias)
 __global__ void relayout_lk_kernel(const float* __restrict__ T, float* __restrict__ out, int lmax, int nlat, int mlim,
-                                   int Lj, int kpad) {
+                                   int Lj, int kpad, int round_tf32) {
   const long long total = (long long)mlim * Lj * kpad;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int k = (int)(i % kpad);
     const long long r = i / kpad;
     const int j = (int)(r % Lj), m = (int)(r / Lj);
     const int l = m + j;
-    out[i] = (l < lmax && k < nlat) ? T[((long long)m * lmax + l) * nlat + k] : 0.0f;
+    const float v = (l < lmax && k < nlat) ? T[((long long)m * lmax + l) * nlat + k] : 0.0f;
+    out[i] = round_tf32 ? rna_tf32_f(v) : v;
   }
 }
 // tab_kl[m][k][j] = T[m][m+j][k], zero padded in j.
 __global__ void relayout_kl_kernel(const float* __restrict__ T, float* __restrict__ out, int lmax, int nlat, int mlim,
-                                   int Lj) {
+                                   int Lj, int round_tf32) {
   const long long total = (long long)mlim * nlat * Lj;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int j = (int)(i % Lj);
     const long long r = i / Lj;
     const int k = (int)(r % nlat), m = (int)(r / nlat);
     const int l = m + j;
-    out[i] = (l < lmax) ? T[((long long)m * lmax + l) * nlat + k] : 0.0f;
+    const float v = (l < lmax) ? T[((long long)m * lmax + l) * nlat + k] : 0.0f;
+    out[i] = round_tf32 ? rna_tf32_f(v) : v;
   }
 }
 // flag != 0 if any entry with l < m (or m >= mlim) is non-zero
@@ -272,10 +281,12 @@ int msfno_plan_set_table(msfno_plan* p, const float* table, int analysis, void* 
   check_triangular_kernel<<<592, 256, 0, st>>>(table, p->d_flag, p->mmax, p->lmax, p->nlat);
   if (analysis) {
     if (!p->d_tab_lk) MSFNO_CUDA_OK(cudaMalloc(&p->d_tab_lk, sizeof(float) * (size_t)p->mlim * p->Lj * p->kpad));
-    relayout_lk_kernel<<<592, 256, 0, st>>>(table, p->d_tab_lk, p->lmax, p->nlat, p->mlim, p->Lj, p->kpad);
+    relayout_lk_kernel<<<592, 256, 0, st>>>(table, p->d_tab_lk, p->lmax, p->nlat, p->mlim, p->Lj, p->kpad,
+                                            p->precision == MSFNO_PREC_TF32);
   } else {
     if (!p->d_tab_kl) MSFNO_CUDA_OK(cudaMalloc(&p->d_tab_kl, sizeof(float) * (size_t)p->mlim * p->nlat * p->Lj));
-    relayout_kl_kernel<<<592, 256, 0, st>>>(table, p->d_tab_kl, p->lmax, p->nlat, p->mlim, p->Lj);
+    relayout_kl_kernel<<<592, 256, 0, st>>>(table, p->d_tab_kl, p->lmax, p->nlat, p->mlim, p->Lj,
+                                            p->precision == MSFNO_PREC_TF32);
   }
   count_launch(2);
   MSFNO_CUDA_OK(cudaGetLastError());

@@ -110,6 +110,6 @@ int launch_irfft2d(const msfno_plan* p, const float* Yt, float* y, const float* 
 // persistent weight-stationary conv kernel (conv_tc.cu); *handled = 0 -> caller falls back to launch_gemm_tc
 int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
                    long long a2_rows, long long a2_cols, long long b2_rows, long long b2_cols, int* handled,
-                   cudaStream_t st);
+                   cudaStream_t st, int round_tf32 = 0);
 
 }  // namespace msfno

@@ -137,7 +137,7 @@ int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* cons
   g.single = GemmGroup{0, 0, 0, 2 * C, p->P, 2 * hid, 0};
   g.sa = 0; g.sb = (long long)p->P * 2 * hid; g.sd = (long long)2 * C * p->P;
   int rc;
-  if (tc && gemm_tc_supported(g)) rc = launch_gemm_tc(g, 2 * C, 2 * hid, (long long)B * p->P, 2 * hid, 0, st);
+  if (tc && gemm_tc_supported(g)) rc = launch_gemm_tc(g, 2 * C, 2 * hid, (long long)B * p->P, 2 * hid, /*round_tf32=*/1, st);
   else rc = launch_gemm_ffma(g, st);
   if (rc) return rc;
   MSFNO_CUDA_OK(cudaGetLastError());

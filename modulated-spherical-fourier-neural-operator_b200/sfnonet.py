@@ -461,7 +461,7 @@ class FourierNeuralOperatorNet(nn.Module):
             bias_b = bias_b + dec[0].bias
         h = conv1x1(y, Wb, E, bias=bias_b.contiguous(), act_gelu=True, x2=residual.contiguous().float(), w2=W2,
                     cin2=self.in_chans, per_sample_w=True, per_sample_bias=True)
-        return conv1x1(h, padded_weight(dec[2].weight), dec[2].in_channels, bias=dec[2].bias)
+        return conv1x1(h, padded_weight(dec[2].weight), dec[2].in_channels, bias=dec[2].bias, final=True)
 
     def _forward_fused(self, x, film=None):
         """film: None or (gamma [B, film_layers, C], beta, scale, first_filmed_block_index)."""

@@ -180,11 +180,12 @@ class _SHTBase(nn.Module):
         if table.device != device:
             raise RuntimeError("%s.%s lives on %s but the input is on %s" % (type(self).__name__, self._table_name,
                                                                              table.device, device))
-        plan.set_table(table, self._analysis)
         tier = _lib.PREC_TF32 if _precision.get_precision() == "tf32" else _lib.PREC_FP32
         if tier != plan.precision:
             check(lib.msfno_plan_set_precision(plan.h, tier), "plan_set_precision")
             plan.precision = tier
+            plan.table_key = None   # the re-laid tables are TF32-rounded in the tensor-core tier: rebuild them
+        plan.set_table(table, self._analysis)
         return plan
 
     def __deepcopy__(self, memo):
@@ -253,7 +254,8 @@ class InverseRealSHT(_SHTBase):
         if skip_add is not None:
             skip_add = skip_add.contiguous().float()
             assert skip_add.shape == y.shape
-        check(lib.msfno_isht_fwd(plan.h, ptr(coef_cm), ptr(y), ptr(ws), B, C, ptr(skip_add), 1 if act_gelu else 0,
+        flags = (1 if act_gelu else 0) | (2 if _precision.get_precision() == "tf32" else 0)   # bit 1: TF32-round y
+        check(lib.msfno_isht_fwd(plan.h, ptr(coef_cm), ptr(y), ptr(ws), B, C, ptr(skip_add), flags,
                                  ptr(stats), _stream()), "isht_fwd")
         return y
 
