@@ -150,7 +150,9 @@ int msfno_specconv_bwd_w(const msfno_plan* plan, const float* a_pm, const float*
  * w[l]: [Cin_l][hidden][2] (l = 0: Cin = C, else hidden); wout: [hidden][C][2].
  * a_pm (PM, C channels) -> out_cm (CM, C channels).
  * ws: msfno_specattn_ws_floats() floats; after the call it holds the packed real weights and
- * the post-activation hidden states needed by msfno_specattn_bwd (keep it alive until then). */
+ * the post-activation hidden states needed by msfno_specattn_bwd (keep it alive until then).
+ * precision: MSFNO_PREC_*, optionally | 4 when `ws` still holds the packed weights of the same parameters from a
+ * previous call (inference with frozen weights: skips the re-pack kernels). */
 size_t msfno_specattn_ws_floats(const msfno_plan* plan, int B, int C, int hidden, int nlayers);
 int msfno_specattn_fwd(const msfno_plan* plan, const float* a_pm, const float* const* w, int nlayers,
                        const float* wout, float* out_cm, float* ws, int B, int C, int hidden,

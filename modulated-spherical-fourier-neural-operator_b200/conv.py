@@ -2,13 +2,15 @@
 
 Mirrors what the reference does with nn.Conv2d(.., 1) + bias + nn.GELU + residual adds + torch.cat
 (/root/reference MSFNO/Models/sfno/layers.py:161-168, sfnonet.py:232,249,671,682-684) in ONE kernel launch."""
+import weakref
+
 import torch
 
 from . import _lib
 from . import precision as _precision
 from ._lib import check, lib, ptr
 
-_pad_cache = {}
+_pad_cache = {}   # id(weight tensor) -> (weakref to it, {(version, tier, cols): padded tensor})
 
 
 def round_tf32(t):
@@ -18,15 +20,23 @@ def round_tf32(t):
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def padded_weight(weight):
-    """[Cout, Cin, 1, 1] (or [Cout, Cin]) -> contiguous [Cout, ceil4(Cin)] with zero padding (TF32-rounded in the
-    tensor-core tier), cached per version and tier."""
+def padded_weight(weight, cols=None):
+    """[Cout, Cin, 1, 1] (or [Cout, Cin]) -> contiguous [Cout, ceil4(n)] of the input-channel columns `cols` = (lo, hi)
+    (default all), zero padded, TF32-rounded in the tensor-core tier.  Cached per tensor OBJECT (weak reference),
+    version and tier -- never per address: freed parameter memory is routinely reused by the next model."""
     tf32 = _precision.get_precision() == "tf32"
-    key = (weight.data_ptr(), weight._version, tuple(weight.shape), str(weight.device), tf32)
-    hit = _pad_cache.get(key)
+    ent = _pad_cache.get(id(weight))
+    if ent is None or ent[0]() is not weight:
+        wid = id(weight)
+        ent = (weakref.ref(weight, lambda _r, k=wid: _pad_cache.pop(k, None)), {})
+        _pad_cache[wid] = ent
+    key = (weight._version, tf32, cols)
+    hit = ent[1].get(key)
     if hit is not None:
         return hit
     w2 = weight.detach().reshape(weight.shape[0], -1).float()
+    if cols is not None:
+        w2 = w2[:, cols[0]:cols[1]]
     cin = w2.shape[1]
     ld = (cin + 3) // 4 * 4
     if ld != cin:
@@ -34,9 +44,9 @@ def padded_weight(weight):
     w2 = w2.contiguous()
     if tf32:
         w2 = round_tf32(w2)
-    if len(_pad_cache) > 256:
-        _pad_cache.clear()
-    _pad_cache[key] = w2
+    for k in [k for k in ent[1] if k[0] != weight._version]:
+        del ent[1][k]   # drop entries of older versions of this tensor
+    ent[1][key] = w2
     return w2
 
 

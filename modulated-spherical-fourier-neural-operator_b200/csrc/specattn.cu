@@ -113,20 +113,25 @@ int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* cons
   cudaStream_t st = (cudaStream_t)stream;
   const AttnWs L = attn_layout(p->P, B, C, hid, nl);
   const int rows = B * p->P;
-  const int tc = (precision == MSFNO_PREC_TF32);
+  const int skip_pack = (precision >> 2) & 1;   // bit 2: ws already holds the packed weights of these parameters
+  const int tc = ((precision & 1) == MSFNO_PREC_TF32);
   const float* in = a_pm;
   int cin = C;
   for (int l = 0; l < nl; ++l) {
-    pack_cweight_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(w[l], ws + L.wbig[l], cin, hid, tc);
-    count_launch();
+    if (!skip_pack) {
+      pack_cweight_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(w[l], ws + L.wbig[l], cin, hid, tc);
+      count_launch();
+    }
     int rc = gemm_nt_any(tc, in, 2 * cin, ws + L.wbig[l], 2 * cin, ws + L.h[l], 2 * hid, rows, 2 * hid, 2 * cin,
                          /*relu_even=*/1, /*round_tf32=*/tc, st);
     if (rc) return rc;
     in = ws + L.h[l];
     cin = hid;
   }
-  pack_cweight_kernel<<<(hid * C + 255) / 256, 256, 0, st>>>(wout, ws + L.wbig_out, hid, C, tc);
-  count_launch();
+  if (!skip_pack) {
+    pack_cweight_kernel<<<(hid * C + 255) / 256, 256, 0, st>>>(wout, ws + L.wbig_out, hid, C, tc);
+    count_launch();
+  }
   // out_cm[b][ch][p] = sum_k wbig_out[ch][k] * h[b*P + p][k]   (strided batch over b)
   GemmLaunch g{};
   g.A = ws + L.wbig_out; g.B = in; g.D = out_cm;

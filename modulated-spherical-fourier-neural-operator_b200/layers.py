@@ -237,7 +237,31 @@ class SpectralAttentionS2(nn.Module):
         tier = self.precision if self.precision is not None else _precision.get_precision()
         prec = _lib.PREC_TF32 if tier == "tf32" else _lib.PREC_FP32
         ws = [w.float().contiguous() for w in self.w]
-        return _SpecAttn.apply(a_pm, self._sht, prec, self.wout.float().contiguous(), *ws)
+        wout = self.wout.float().contiguous()
+        if not torch.is_grad_enabled():
+            return self._spectral_inference(a_pm, prec, wout, ws)
+        return _SpecAttn.apply(a_pm, self._sht, prec, wout, *ws)
+
+    def _spectral_inference(self, a_pm, prec, wout, ws):
+        """No-autograd path: the workspace (packed real weights + hidden activations) is kept per (batch, device, tier)
+        and the packed weights are reused while the parameters are unchanged (data_ptr / _version)."""
+        plan = self._sht._get_plan(a_pm.device)
+        B, C = a_pm.shape[0], a_pm.shape[2] // 2
+        hid, nl = wout.shape[0], len(ws)
+        key = (B, str(a_pm.device), prec)
+        wkey = tuple((id(w), w.data_ptr(), w._version) for w in (self.wout, *self.w))
+        cache = self.__dict__.setdefault("_ws_cache", {})
+        ent = cache.get(key)
+        if ent is None:
+            buf = torch.empty(lib.msfno_specattn_ws_floats(plan.h, B, C, hid, nl), dtype=torch.float32, device=a_pm.device)
+            ent = cache[key] = [buf, None]
+        flags = prec | (4 if ent[1] == wkey else 0)
+        out = torch.empty((B, 2 * C, plan.P), dtype=torch.float32, device=a_pm.device)
+        warr = (ctypes.c_void_p * nl)(*[w.data_ptr() for w in ws])
+        check(lib.msfno_specattn_fwd(plan.h, ptr(a_pm), warr, nl, ptr(wout), ptr(out), ptr(ent[0]), B, C, hid, flags,
+                                     _stream()), "specattn_fwd")
+        ent[1] = wkey
+        return out
 
     def forward_mlp(self, xr):
         """Reference-compatible entry: xr real view [B,C,L,M,2] -> [B,C,L,M,2]."""

@@ -19,6 +19,20 @@ def set_precision(tier):
     _TIER = tier
 
 
+_LEGENDRE_TC = True
+
+
+def set_legendre_on_tensor_cores(flag):
+    """tf32 tier only: run the Legendre contractions of the forward transforms on the tensor cores (default) or keep
+    them on the fp32 CUDA-core engine (more headroom under the 2e-3 tolerance, ~0.8 ms per step slower)."""
+    global _LEGENDRE_TC
+    _LEGENDRE_TC = bool(flag)
+
+
+def legendre_on_tensor_cores():
+    return _LEGENDRE_TC
+
+
 def get_precision():
     return _TIER
 

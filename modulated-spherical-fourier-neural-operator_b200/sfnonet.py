@@ -453,8 +453,8 @@ class FourierNeuralOperatorNet(nn.Module):
         weights, the concat is replaced by a second operand pair accumulating into the same tile."""
         dec = self.decoder.fwd
         E = self.embed_dim_sfno
-        Wd = dec[0].weight.view(dec[0].out_channels, -1)
-        W1, W2 = padded_weight(Wd[:, :E]), padded_weight(Wd[:, E:])
+        W1 = padded_weight(dec[0].weight, cols=(0, E))
+        W2 = padded_weight(dec[0].weight, cols=(E, dec[0].in_channels))
         Wb = (W1.unsqueeze(0) * torch.nn.functional.pad(A, (0, W1.shape[1] - E)).unsqueeze(1)).contiguous()
         bias_b = torch.matmul(S, W1[:, :E].t())
         if dec[0].bias is not None:

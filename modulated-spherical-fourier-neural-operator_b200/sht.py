@@ -49,17 +49,21 @@ class _Plan:
         self.P = lib.msfno_plan_query(self.h, _lib.Q_NPACK)
         self.ntril = lib.msfno_plan_query(self.h, _lib.Q_NTRIL)
         self.table_key = None
+        self.table_ref = None
         self.precision = _lib.PREC_FP32
 
     def set_table(self, table, analysis):
-        key = (table.data_ptr(), table._version, tuple(table.shape))
-        if key != self.table_key:
+        # identity + version of the tensor object; the plan keeps the tensor alive (self.table_ref) so its address
+        # cannot be recycled for a different table while the key is still in use
+        key = (id(table), table._version)
+        if key != self.table_key or self.table_ref is not table:
             t = table.detach()
             if t.dtype != torch.float32 or not t.is_contiguous():
                 t = t.float().contiguous()
             with torch.cuda.device(self.device):
                 check(lib.msfno_plan_set_table(self.h, ptr(t), 1 if analysis else 0, _stream()), "plan_set_table")
             self.table_key = key
+            self.table_ref = table
 
     def __del__(self):
         try:
@@ -180,7 +184,7 @@ class _SHTBase(nn.Module):
         if table.device != device:
             raise RuntimeError("%s.%s lives on %s but the input is on %s" % (type(self).__name__, self._table_name,
                                                                              table.device, device))
-        tier = _lib.PREC_TF32 if _precision.get_precision() == "tf32" else _lib.PREC_FP32
+        tier = _lib.PREC_TF32 if (_precision.get_precision() == "tf32" and _precision.legendre_on_tensor_cores()) else _lib.PREC_FP32
         if tier != plan.precision:
             check(lib.msfno_plan_set_precision(plan.h, tier), "plan_set_precision")
             plan.precision = tier

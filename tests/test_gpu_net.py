@@ -88,3 +88,23 @@ def test_filmed_net_matches_reference(fl):
     assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
     k = "blocks.%d.filter_layer.filter.w.0" % last
     assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
+
+
+def test_weight_caches_survive_address_reuse():
+    """Regression: caches of derived weights must be keyed on tensor identity, not on addresses -- a second model built
+    after the first one is freed reuses the same device addresses (in a different order) with different values."""
+    import gc
+    d = torch.load(os.path.join(GOLD, "net_nonlinear_small.pt"))
+    cfg = d["cfg"]
+    tr = sfno_oracle.Transforms(cfg["img_size"], cfg["scale_factor"])
+    x = d["x"]
+    for seed in (11, 12, 13):
+        sd = _oracle_sd(cfg, "non-linear", seed)
+        net = _load(msfno_b200.FourierNeuralOperatorNet("cuda", None, **cfg), sd).cuda().eval()
+        with torch.no_grad():
+            got = net(x.cuda())
+            want = sfno_oracle.sfno_forward(x, sd, tr, "non-linear", cfg["num_layers"])
+        assert rel_l2(got, want) < TOL_FP32, seed
+        del net
+        gc.collect()
+        torch.cuda.empty_cache()
