@@ -57,14 +57,17 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // GELU with erf from Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7 absolute): 2 MUFU + ~12 FMA instead of the ~40
 // instructions of erff.  Used by the tensor-core kernels, whose tier tolerance (2e-3) it undercuts by four orders.
 __device__ __forceinline__ float gelu_fast(float x) {
+  // 0.5 x (1 + erf(x / sqrt 2)) = hx + |hx| * erf(|x| / sqrt 2),  hx = x / 2
+  const float hx = 0.5f * x;
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));          // MUFU.RCP
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = 1.0f - poly * t * __expf(-z * z);   // erf(|x| / sqrt 2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  const float ex = exp2f(z * z * -1.44269504088896340736f);              // MUFU.EX2 (e^{-z^2})
+  const float e = fmaf(-poly * t, ex, 1.0f);                             // erf(z)
+  return fmaf(fabsf(hx), e, hx);
 }
 // d/dx of exact GELU
 __device__ __forceinline__ float gelu_erf_grad(float x) {

@@ -176,35 +176,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       if (pix_ok && nch > 0) {
-        // two halves of 16 channels keep the live register set small (576 threads per CTA)
+        // two halves of 16 channels keep the live register set small; the mode flags are tested once per half, not per
+        // element (the kernel is issue-bound in this loop: profiles/r01_ncu_full_conv_tc_pixelmajor_raw.csv)
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int jb = h * 16;
-          if (nch >= jb + 16) {
+          const int nv = nch - jb;   // valid channels in this half
+          if (nv <= 0) break;
+          float v[16];
+          const float4* b4 = reinterpret_cast<const float4*>(bias_s + c0 + jb);
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 bb = b4[j >> 2];
+            v[j] = __uint_as_float(r[jb + j]) + bb.x;
+            v[j + 1] = __uint_as_float(r[jb + j + 1]) + bb.y;
+            v[j + 2] = __uint_as_float(r[jb + j + 2]) + bb.z;
+            v[j + 3] = __uint_as_float(r[jb + j + 3]) + bb.w;
+          }
+          if (p.act_gelu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+          }
+          if (aptr) {
+            const float* ap = aptr + (long long)jb * p.ldadd;
             float av[16];
-            if (aptr) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) av[j] = __ldg(aptr + (long long)(jb + j) * p.ldadd);   // coalesced over lanes
-            }
+            for (int j = 0; j < 16; ++j) av[j] = (j < nv) ? __ldg(ap + (long long)j * p.ldadd) : 0.0f;   // coalesced over lanes
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float tv = __uint_as_float(r[jb + j]) + bias_s[c0 + jb + j];
-              if (p.act_gelu) tv = gelu_fast(tv);
-              if (aptr) tv += av[j];
-              if (p.round_tf32) tv = round_to_tf32(tv);
-              __stcs(dptr + (long long)(jb + j) * p.ldd, tv);                                       // coalesced over lanes
-            }
+            for (int j = 0; j < 16; ++j) v[j] += av[j];
+          }
+          if (p.round_tf32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = round_to_tf32(v[j]);
+          }
+          float* dp = dptr + (long long)jb * p.ldd;
+          if (nv >= 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) __stcs(dp + (long long)j * p.ldd, v[j]);                          // coalesced over lanes
           } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (jb + j < nch) {
-                float tv = __uint_as_float(r[jb + j]) + bias_s[c0 + jb + j];
-                if (p.act_gelu) tv = gelu_fast(tv);
-                if (aptr) tv += __ldg(aptr + (long long)(jb + j) * p.ldadd);
-                if (p.round_tf32) tv = round_to_tf32(tv);
-                __stcs(dptr + (long long)(jb + j) * p.ldd, tv);
-              }
-            }
+            for (int j = 0; j < 16; ++j)
+              if (j < nv) __stcs(dp + (long long)j * p.ldd, v[j]);
           }
         }
       }
