@@ -27,7 +27,7 @@ namespace msfno {
 static constexpr int CT_BM = 128, CT_BN = 128;
 static constexpr int CT_KB_BYTES = CT_BM * TC_BK * 4;  // one 128 x 32 fp32 operand block = 16 KB
 static constexpr int CT_MAX_KB = 8;                     // resident weight k-blocks of the first pair (K1 <= 256)
-static constexpr int CT_MAX_KB2 = 4;                    // streamed weight k-blocks of the second pair (K2 <= 128)
+static constexpr int CT_MAX_KB2 = 32;                   // streamed weight k-blocks (second pair, or a single pair too big to stay resident)
 
 struct ConvTcParams {
   float* D;
@@ -236,9 +236,12 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
                    long long a2_rows, long long a2_cols, long long b2_rows, long long b2_cols, int* handled,
                    cudaStream_t st, int round_tf32) {
   *handled = 0;
-  const int K1 = g.single.K, K2 = g.A2 ? g.K2 : 0;
+  int K1 = g.single.K, K2 = g.A2 ? g.K2 : 0;
+  // a single operand pair whose weight slab does not fit in smem is streamed entirely (it takes the role of pair 2)
+  const bool stream_all = !g.A2 && (K1 + TC_BK - 1) / TC_BK > CT_MAX_KB && g.sa == 0;
+  if (stream_all) { K2 = K1; K1 = 0; }
   const int nkb1 = (K1 + TC_BK - 1) / TC_BK, nkb2 = (K2 + TC_BK - 1) / TC_BK;
-  if (g.b_kmajor || !g.use_single || g.relu_even || nkb1 < 1 || nkb1 > CT_MAX_KB || nkb2 > CT_MAX_KB2) return MSFNO_OK;
+  if (g.b_kmajor || !g.use_single || g.relu_even || nkb1 + nkb2 < 1 || nkb1 > CT_MAX_KB || nkb2 > CT_MAX_KB2) return MSFNO_OK;
   if (g.sa % g.lda != 0 || g.sb % g.ldb != 0 || (g.A2 && (g.sa2 != 0 || g.sb2 % g.ldb2 != 0))) return MSFNO_OK;
   // smem: [align 1024][nkb1 resident weight blocks][ns ring slots][barriers + bias, 1024]
   const size_t total = 227 * 1024, fixed = 1024 + 1024 + (size_t)nkb1 * CT_KB_BYTES;
@@ -259,7 +262,7 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     rc = make_map(&tmB2, g.B2, b2_rows, b2_cols, g.ldb2, TC_BK, true);
     if (rc) return rc;
   } else {
-    tmA2 = tmA;
+    tmA2 = tmA;   // stream_all: pair 2 is the only pair and uses the same buffers
     tmB2 = tmB;
   }
   static std::once_flag once;
@@ -269,8 +272,8 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   });
   MSFNO_CUDA_OK(attr_err);
   ConvTcParams p{};
-  p.D = g.D; p.lda = g.lda; p.lda2 = g.A2 ? g.lda2 : 4; p.ldb = g.ldb; p.ldb2 = g.A2 ? g.ldb2 : 4; p.ldd = g.ldd;
-  p.sa = g.sa; p.sb = g.sb; p.sb2 = g.sb2; p.sd = g.sd;
+  p.D = g.D; p.lda = g.lda; p.lda2 = g.A2 ? g.lda2 : g.lda; p.ldb = g.ldb; p.ldb2 = g.A2 ? g.ldb2 : g.ldb; p.ldd = g.ldd;
+  p.sa = g.sa; p.sb = g.sb; p.sb2 = g.A2 ? g.sb2 : g.sb; p.sd = g.sd;
   p.bias = g.bias; p.sbias = g.sbias; p.add = g.add; p.ldadd = g.ldadd; p.sadd = g.sadd;
   p.M = g.single.M; p.N = g.single.N; p.K1 = K1; p.K2 = K2; p.act_gelu = g.act_gelu; p.nstages = ns; p.slot_bytes = (int)slot; p.round_tf32 = round_tf32;
   p.tilesN = (p.N + CT_BN - 1) / CT_BN;

@@ -117,7 +117,8 @@ def test_small_net_tf32_tier(tf32_tier, name, ftype):
 
 @pytest.mark.parametrize("tier,tol", [("fp32", 1e-5), ("tf32", TOL_TF32)])
 @pytest.mark.parametrize("B,Cin,Cout,H,W,Cin2", [(1, 73, 256, 37, 72, 0), (2, 256, 512, 12, 24, 0), (1, 256, 73, 31, 52, 0),
-                                                   (2, 64, 96, 16, 40, 73), (1, 8, 8, 4, 4, 0), (1, 256, 256, 120, 240, 73)])
+                                                   (2, 64, 96, 16, 40, 73), (1, 8, 8, 4, 4, 0), (1, 256, 256, 120, 240, 73),
+                                                   (2, 512, 256, 12, 24, 0), (1, 1000, 130, 120, 240, 0)])
 def test_conv1x1_fused(tier, tol, B, Cin, Cout, H, W, Cin2):
     """y = gelu(conv(x, w) [+ conv(x2, w2)] + bias) + add against torch fp64 (msfno_conv1x1_fwd, both engines)."""
     from msfno_b200.conv import conv1x1, padded_weight
