@@ -219,6 +219,21 @@ def dominant_kernel_roofline(args, net, dev, pk):
             ts.append(e0.elapsed_time(e1))
         return sum(ts) / len(ts)
 
+    stages = {}
+    if args.workload != "filter_linear":
+        # BASELINE metric (ii): SHT / ISHT achieved rate vs the HBM roof at the full grid (C = 256, B = 1)
+        import msfno_b200
+        x = torch.randn(1, EMBED, *IMG, device=dev)
+        sht, isht = net.trans_down, net.itrans_up
+        with torch.no_grad():
+            pm = sht.forward_packed(x)
+            cm = msfno_b200.sht.relayout(pm, sht, _lib.LAYOUT_PM, _lib.LAYOUT_CM, 1, EMBED)
+            gb = (4.0 * EMBED * IMG[0] * IMG[1] + 8.0 * EMBED * LMAX * MMAX + 4.0 * MMAX * LMAX * IMG[0]) / 1e9
+            for name, fn in (("sht_fwd_full", lambda: sht.forward_packed(x)), ("isht_fwd_full", lambda: isht.inverse_packed(cm))):
+                ms = timed(fn)
+                stages[name] = {"ms": ms, "algorithmic_GB": gb, "achieved_GBps": gb / ms * 1e3, "frac_of_hbm_peak": gb / ms * 1e3 / pk["hbm"],
+                                "launches": 2}
+        del x, pm, cm
     if args.workload == "sfno12_nonlinear":
         # spectral complex-MLP hidden layer: real GEMM [P x 1024] x [1024 x 1024] (2 of the 4 MLP launches per block)
         Pp = 7440
@@ -231,9 +246,11 @@ def dominant_kernel_roofline(args, net, dev, pk):
         ach = flops / (ms * 1e-3) / 1e12
         peak = pk["bf16_sustained"] / 2.0
         return {"kernel": "gemm (spectral complex-MLP hidden layer, M=7260 modes, N=K=1024 real)", "bound": "tensor",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 35.5e6,
+                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this launch (operands are L2 resident), "
+                                  "profiles/r01_ncu_full_fft_gemm_inner_raw.csv",
                 "peak_source": "%s bf16_tflops_sustained / 2 (TF32 = half of BF16, BASELINE.md section 2)" % pk["src"],
-                "ms_per_launch": ms}
+                "ms_per_launch": ms, "stages": stages}
     # linear workloads: the SpectralConvS2 weight stream
     import msfno_b200
     filt = net if args.workload == "filter_linear" else net.blocks[1].filter_layer.filter
@@ -247,7 +264,7 @@ def dominant_kernel_roofline(args, net, dev, pk):
     ach = by / (ms * 1e-3) / 1e9
     return {"kernel": "specconv_fwd_kernel (per-mode complex channel contraction, 3.8 GB weight stream)", "bound": "hbm",
             "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": None,
-            "peak_source": "%s hbm_gbs" % pk["src"], "ms_per_launch": ms}
+            "peak_source": "%s hbm_gbs" % pk["src"], "ms_per_launch": ms, "stages": stages}
 
 
 def run_ours(args):
