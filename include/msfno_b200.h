@@ -133,14 +133,19 @@ int msfno_coef_relayout(const msfno_plan* plan, const float* src, int src_layout
  * replaces: compl_contract_fwd_c  einsum("bin,kin->bkn") on complex64
  *           (MSFNO/Models/sfno/contractions.py:37-41 via layers.py:411) and its autograd.
  * w is the reference parameter layout [Co][Ci][n][2], n in torch.tril_indices order; it is
- * streamed exactly once per call.  a_pm: PM layout (Ci channels) -> out_cm: CM layout (Co). */
-int msfno_specconv_fwd(const msfno_plan* plan, const float* a_pm, const float* w, float* out_cm,
+ * streamed exactly once per call.  Activations in and out are PM layout (a mode's channels
+ * contiguous): a_pm (Ci channels) -> out_pm (Co); pad slots of the output are zero-filled.
+ * msfno_coef_relayout(PM -> CM) feeds the result to msfno_isht_fwd.
+ * ws: msfno_specconv_ws_floats() floats of scratch (the activations re-ordered to tril order so that every
+ * operand is a contiguous run for the TMA engine); NULL selects the slower register-load kernel. */
+size_t msfno_specconv_ws_floats(const msfno_plan* plan, int B, int Ci, int Co);
+int msfno_specconv_fwd(const msfno_plan* plan, const float* a_pm, const float* w, float* out_pm, float* ws,
                        int B, int Ci, int Co, void* stream);
-/* ga[b,i,n] = sum_k conj(w[k,i,n]) g[b,k,n] :  g_cm (CM, Co) -> ga_pm (PM, Ci) */
-int msfno_specconv_bwd_x(const msfno_plan* plan, const float* g_cm, const float* w, float* ga_pm,
+/* ga[b,i,n] = sum_k conj(w[k,i,n]) g[b,k,n] :  g_pm (PM, Co) -> ga_pm (PM, Ci) */
+int msfno_specconv_bwd_x(const msfno_plan* plan, const float* g_pm, const float* w, float* ga_pm, float* ws,
                          int B, int Ci, int Co, void* stream);
-/* gw[k,i,n] = sum_b conj(a[b,i,n]) g[b,k,n] :  writes gw [Co][Ci][n][2] */
-int msfno_specconv_bwd_w(const msfno_plan* plan, const float* a_pm, const float* g_cm, float* gw,
+/* gw[k,i,n] = sum_b conj(a[b,i,n]) g[b,k,n] :  a_pm, g_pm (PM) -> gw [Co][Ci][n][2] */
+int msfno_specconv_bwd_w(const msfno_plan* plan, const float* a_pm, const float* g_pm, float* gw, float* ws,
                          int B, int Ci, int Co, void* stream);
 
 /* ---- a6 / a7 / a8 / a14: SpectralAttentionS2 mode-shared complex MLP ----------------------

@@ -60,9 +60,10 @@ _SIGS = {
     "msfno_fft_stage": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P]),
     "msfno_legendre_stage": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "msfno_coef_relayout": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, _P]),
-    "msfno_specconv_fwd": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
-    "msfno_specconv_bwd_x": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
-    "msfno_specconv_bwd_w": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "msfno_specconv_ws_floats": (ctypes.c_size_t, [_P, c_int, c_int, c_int]),
+    "msfno_specconv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "msfno_specconv_bwd_x": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
+    "msfno_specconv_bwd_w": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "msfno_specattn_ws_floats": (c_size_t, [_P, c_int, c_int, c_int, c_int]),
     "msfno_specattn_fwd": (c_int, [_P, _P, ctypes.POINTER(c_void_p), c_int, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "msfno_specattn_bwd_scratch_floats": (c_size_t, [_P, c_int, c_int, c_int, c_int]),

@@ -87,7 +87,7 @@ class ComplexReLU(nn.Module):
 
 # ------------------------------------------------------------------------------- autograd functions
 class _SpecConv(torch.autograd.Function):
-    """a_pm [B,P,2Ci], w [Co,Ci,n,2] -> out_cm [B,2Co,P]  (msfno_specconv_fwd / bwd_x / bwd_w)."""
+    """a_pm [B,P,2Ci], w [Co,Ci,n,2] -> out_pm [B,P,2Co]  (msfno_specconv_fwd / bwd_x / bwd_w)."""
 
     @staticmethod
     def forward(ctx, a_pm, w, sht):
@@ -95,8 +95,9 @@ class _SpecConv(torch.autograd.Function):
         B, Ci, Co = a_pm.shape[0], w.shape[1], w.shape[0]
         if w.shape[2] != plan.ntril:
             raise RuntimeError("SpectralConvS2: weight has %d modes, transform has %d" % (w.shape[2], plan.ntril))
-        out = torch.empty((B, 2 * Co, plan.P), dtype=torch.float32, device=a_pm.device)
-        check(lib.msfno_specconv_fwd(plan.h, ptr(a_pm), ptr(w), ptr(out), B, Ci, Co, _stream()), "specconv_fwd")
+        out = torch.empty((B, plan.P, 2 * Co), dtype=torch.float32, device=a_pm.device)
+        ws = torch.empty(lib.msfno_specconv_ws_floats(plan.h, B, Ci, Co), dtype=torch.float32, device=a_pm.device)
+        check(lib.msfno_specconv_fwd(plan.h, ptr(a_pm), ptr(w), ptr(out), ptr(ws), B, Ci, Co, _stream()), "specconv_fwd")
         ctx.sht = sht
         ctx.save_for_backward(a_pm, w)
         return out
@@ -108,12 +109,13 @@ class _SpecConv(torch.autograd.Function):
         B, Ci, Co = a_pm.shape[0], w.shape[1], w.shape[0]
         g = g.contiguous()
         ga = gw = None
+        ws = torch.empty(lib.msfno_specconv_ws_floats(plan.h, B, Ci, Co), dtype=torch.float32, device=g.device)
         if ctx.needs_input_grad[0]:
             ga = torch.empty_like(a_pm)
-            check(lib.msfno_specconv_bwd_x(plan.h, ptr(g), ptr(w), ptr(ga), B, Ci, Co, _stream()), "specconv_bwd_x")
+            check(lib.msfno_specconv_bwd_x(plan.h, ptr(g), ptr(w), ptr(ga), ptr(ws), B, Ci, Co, _stream()), "specconv_bwd_x")
         if ctx.needs_input_grad[1]:
             gw = torch.empty_like(w)
-            check(lib.msfno_specconv_bwd_w(plan.h, ptr(a_pm), ptr(g), ptr(gw), B, Ci, Co, _stream()), "specconv_bwd_w")
+            check(lib.msfno_specconv_bwd_w(plan.h, ptr(a_pm), ptr(g), ptr(gw), ptr(ws), B, Ci, Co, _stream()), "specconv_bwd_w")
         return ga, gw, None
 
 
@@ -182,6 +184,7 @@ class SpectralConvS2(nn.Module):
         """PM coefficients -> CM coefficients (the contraction + optional soft-shrink)."""
         w = self.w if self.w.dtype == torch.float32 else self.w.float()
         out = _SpecConv.apply(a_pm, w.contiguous(), self.forward_transform)
+        out = relayout(out, self.forward_transform, _lib.LAYOUT_PM, _lib.LAYOUT_CM, a_pm.shape[0], self.w.shape[0])
         if self.sparsity_threshold != 0.0:
             out = nn.functional.softshrink(out, lambd=self.sparsity_threshold)
         return out
