@@ -16,6 +16,8 @@
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator; afterwards all
 // 8 warps drain the accumulator (TMEM lane quarter q = warp % 4, column half = warp / 4).  BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32 fp32
 // (= one 128-byte swizzle span = 4 UMMA K-steps of 8).
+#include <cstdlib>
+
 #include "plan.h"
 #include "tc_common.cuh"
 
@@ -228,6 +230,198 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two CTAs of a cluster (the two SMs of a TPC) compute one 256 x 256 tile.
+// Each CTA stages ITS 128 rows of A and ITS 128 rows of B (= 128 of the 256 output columns); the leader's single
+// thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256), which reads both CTAs' shared memory and writes each
+// CTA's 128 x 256 accumulator slice into that CTA's TMEM.  With 4-byte operands a single-CTA 128 x 128 tile needs
+// 128 B/clk of smem reads for the MMA plus 128 B/clk of TMA writes, twice what an SM's shared memory delivers; the
+// pair halves both (each operand byte is staged once per pair), which is what lets the TF32 MLP GEMMs leave the
+// 40 % plateau.  Barriers: full[s] lives in the leader (both producers' TMA bytes complete on it), empty[s] and
+// tmem_full exist in both CTAs and are signalled by multicast commits.  K-major B, single operand pair only.
+static constexpr int TC2_BN = 256;
+static constexpr int TC2_STAGE_BYTES = TC_A_BYTES + TC_A_BYTES;   // 128 rows of A + 128 rows of B per CTA
+static constexpr int TC2_SMEM_BYTES = TC_STAGES * TC2_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// TMA load whose completion bytes land on the LEADER CTA's barrier (peer bit of the barrier address cleared)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this shared-memory offset in BOTH CTAs once the MMAs issued so far have completed
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 2)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  GemmGroup grp;
+  if (p.use_single) {
+    grp = p.single;
+    grp.a_off += blockIdx.y * p.sa;
+    grp.b_off += blockIdx.y * p.sb;
+    grp.d_off += blockIdx.y * p.sd;
+  } else {
+    grp = p.groups[blockIdx.y];
+  }
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1;
+  const int tn = pair / p.tilesM, tm = pair - tn * p.tilesM;   // tilesM counts 256-row pair tiles here
+  const int m0 = tm * 256 + (int)rank * TC_BM;                 // this CTA's 128 rows
+  const int n0 = tn * TC2_BN;
+  if (tm * 256 >= grp.M || n0 >= grp.N) return;                // uniform for the PAIR
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * TC2_STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + TC_STAGES;
+  uint64_t* tmem_full = bars + 2 * TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (grp.K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(TC2_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n");
+  }
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs' barriers are initialised and both TMEM slices allocated before any signal crosses
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0 && lane == 0) {
+      // ---------------- TMA producer (both CTAs) ----------------
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
+        const int kk = kb * TC_BK;
+        mbar_wait_bounded(&empty[s], ph ^ 1u);
+        if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * TC2_STAGE_BYTES);   // bytes of both CTAs
+        uint8_t* sa = tiles + s * TC2_STAGE_BYTES;
+        tma_load_2d_pair(sa, &tmA, &full[s], (int)(grp.a_off % p.lda) + kk, (int)(grp.a_off / p.lda) + m0);
+        tma_load_2d_pair(sa + TC_A_BYTES, &tmB, &full[s], (int)(grp.b_off % p.ldb) + kk,
+                         (int)(grp.b_off / p.ldb) + n0 + (int)rank * TC_BM);
+      }
+    } else if (warp == 1 && lane == 0 && rank == 0) {
+      // ---------------- MMA issuer (leader CTA only) ----------------
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC2_BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
+        mbar_wait_bounded(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = base + s * TC2_STAGE_BYTES;
+        const uint32_t sb = sa + TC_A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k)
+          tc_mma_tf32_pair(tmem_base, make_smem_desc(sa + 32 * k, 16, 1024), make_smem_desc(sb + 32 * k, 16, 1024), idesc,
+                           (kb | k) ? 1u : 0u);
+        tc_commit_pair(&empty[s]);
+      }
+      tc_commit_pair(tmem_full);
+    }
+  }
+
+  __syncwarp();
+  {
+    // ---------------- epilogue: this CTA's 128 rows x 256 columns ----------------
+    const int q = warp & 3;
+    const int chalf = warp >> 2;
+    const int row = m0 + q * 32 + lane;
+    if (nkb > 0) {
+      mbar_wait_bounded(tmem_full, 0);
+      tc_fence_after();
+    }
+    float* drow = p.D + grp.d_off + (long long)row * p.ldd;
+    const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+    const float bv = (p.bias && row < grp.M) ? p.bias[blockIdx.y * p.sbias + row] : 0.0f;
+#pragma unroll 1
+    for (int c0 = chalf * (TC2_BN / 2); c0 < (chalf + 1) * (TC2_BN / 2); c0 += 32) {
+      uint32_t r[32];
+      if (nkb > 0) {
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      const int gn = n0 + c0;
+      if (row < grp.M && gn < grp.N) {
+        const bool full_vec = vec && gn + 31 < grp.N;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = __uint_as_float(r[j]) + bv;
+          if (p.act_gelu) t = gelu_fast(t);
+          if (p.relu_even && !(j & 1)) t = fmaxf(t, 0.f);
+          if (p.round_tf32) t = round_to_tf32(t);
+          v[j] = t;
+        }
+        if (full_vec) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(drow + gn + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gn + j < grp.N) drow[gn + j] = v[j];
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  cluster_sync_all();   // neither CTA may retire (or free TMEM) while its peer can still touch it
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TC2_BN));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool gemm_tc_supported(const GemmLaunch& g) {
@@ -244,6 +438,33 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
                    long long b2_cols) {
   if (g.ngroups <= 0 || g.maxM <= 0 || g.maxN <= 0) return MSFNO_OK;
   const bool bmn = !g.b_kmajor;
+  static const bool pair_off = getenv("MSFNO_GEMM_NO_PAIR") != nullptr;
+  // 256-column pair tiles: with N = 512 only 60 pairs exist for the 7440-row MLP (< 74 TPCs) and the single-CTA
+  // kernel's finer tiles win (tools/gemm_bench.py); MSFNO_GEMM_PAIR_MIN_N overrides for experiments
+  static const int pair_min_n = getenv("MSFNO_GEMM_PAIR_MIN_N") ? atoi(getenv("MSFNO_GEMM_PAIR_MIN_N")) : 768;
+  if (!bmn && !g.A2 && !g.add && g.maxM >= 1024 && g.maxN >= pair_min_n && !pair_off) {
+    CUtensorMap tmA, tmB;
+    int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, TC_BM);
+    if (rc) return rc;
+    rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, TC_BM);
+    if (rc) return rc;
+    static std::once_flag once2;
+    static cudaError_t attr_err2 = cudaSuccess;
+    std::call_once(once2, [] { attr_err2 = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES); });
+    MSFNO_CUDA_OK(attr_err2);
+    TcParams p{};
+    p.D = g.D; p.lda = g.lda; p.ldb = g.ldb; p.ldd = g.ldd;
+    p.groups = g.groups; p.single = g.single; p.sa = g.sa; p.sb = g.sb; p.sd = g.sd; p.use_single = g.use_single;
+    p.relu_even = g.relu_even; p.round_tf32 = round_tf32;
+    p.bias = g.bias; p.sbias = g.sbias; p.act_gelu = g.act_gelu;
+    p.tilesM = (g.maxM + 255) / 256;
+    p.tilesN = (g.maxN + TC2_BN - 1) / TC2_BN;
+    dim3 grid(2 * p.tilesM * p.tilesN, g.ngroups);
+    gemm_tc2_kernel<<<grid, 256, TC2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    count_launch();
+    MSFNO_CUDA_OK(cudaGetLastError());
+    return MSFNO_OK;
+  }
   CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, TC_BM);
   if (rc) return rc;

@@ -12,7 +12,9 @@ from msfno_b200._lib import PREC_TF32, check, lib, ptr
 
 
 @pytest.mark.parametrize("M,N,K,relu", [(128, 128, 32, 0), (128, 128, 64, 0), (128, 128, 256, 1), (256, 384, 1024, 0),
-                                         (7440, 1024, 1024, 1), (130, 72, 736, 0), (5, 8, 12, 0), (1000, 136, 100, 1)])
+                                         (7440, 1024, 1024, 1), (130, 72, 736, 0), (5, 8, 12, 0), (1000, 136, 100, 1),
+                                         # CTA-pair kernel (M >= 1024, N >= 256): exact, ragged and single-k-block shapes
+                                         (1024, 256, 32, 0), (1100, 520, 72, 1), (2048, 512, 512, 0), (7440, 512, 1024, 0)])
 def test_gemm_nt_tf32(M, N, K, relu):
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
     A, Bm = torch.randn(M, K, generator=g).cuda(), torch.randn(N, K, generator=g).cuda()
