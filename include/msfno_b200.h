@@ -203,6 +203,21 @@ int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const float* w, l
                       long bias_bstride, const float* add, long add_bstride, float* y, int B, int Cout, long HW,
                       int act_gelu, int precision, void* stream);
 
+/* ---- N2: fused two-layer 1x1-conv MLP (encoder / decoder at full resolution) ---------------
+ * replaces: MLP.fwd = Conv2d(1x1) -> GELU -> Conv2d(1x1) (MSFNO/Models/sfno/layers.py:161-168) together with the
+ *           pos_embed add (sfnonet.py:671) and the big-skip torch.cat (sfnonet.py:682-684).
+ *   y[b][o][p] = sum_h w2[o][h] * gelu( sum_c w1[h][c] x[b][c][p] + sum_c w1b[h][c] x2[b][c][p] + b1[h] )
+ *                + b2[o] + add[b][o][p]
+ * The Chid-channel hidden activation stays in tensor memory.  Tensor-core (TF32) tier only: returns
+ * MSFNO_ERR_UNSUPPORTED for shapes outside Chid % 32 == 0, Chid <= 256, Cout <= 256, HW % 4 == 0 (callers then
+ * use two msfno_conv1x1_fwd calls).  w1: [Chid][ldw1] (per-sample stride w1_bstride, 0 = shared), w1b: [Chid][ldw1b],
+ * w2: [Cout][ldw2], b1: [Chid] (stride b1_bstride), b2: [Cout] or NULL, add: [B or 1][Cout][HW] or NULL.
+ * flags bit 1: round y to TF32. */
+int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const float* w1, long ldw1, long w1_bstride,
+                     const float* x2, long x2_bstride, int Cin2, const float* w1b, long ldw1b, const float* b1,
+                     long b1_bstride, int Chid, const float* w2, long ldw2, const float* b2, const float* add,
+                     long add_bstride, float* y, int B, int Cout, long HW, int flags, void* stream);
+
 /* ---- generic K-major batched GEMM used by the Legendre and MLP stages ---------------------
  * D[M][N] = A[M][K] * B[N][K]^T (row-major D, ldd), optional ReLU on even columns.
  * Exposed for tests and for the 1x1-conv MLPs either side of the path. */

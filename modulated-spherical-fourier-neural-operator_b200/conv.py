@@ -74,3 +74,30 @@ def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, ci
                                 add_bs, ptr(y), B, cout, HW, 1 if act_gelu else 0, prec,
                                 torch.cuda.current_stream().cuda_stream), "conv1x1_fwd")
     return y
+
+
+def mlp1x1_supported(chid, cout, HW):
+    """Shapes the fused two-layer kernel (msfno_mlp1x1_fwd, tensor-core tier) takes."""
+    return _precision.get_precision() == "tf32" and chid % 32 == 0 and chid <= 256 and cout <= 256 and HW % 4 == 0
+
+
+def mlp1x1(x, w1, cin, b1, w2, b2=None, add=None, x2=None, w1b=None, cin2=0, per_sample_w1=False, per_sample_b1=False,
+           final=False):
+    """y = conv1x1(gelu(conv1x1(x, w1) [+ conv1x1(x2, w1b)] + b1), w2) + b2 + add in ONE kernel; the hidden activation
+    never reaches HBM.  w1: [Chid, ld] (or [B, Chid, ld]), w1b: [Chid, ld2], w2: [Cout, ld3] zero-padded rows."""
+    B, _, H, W = x.shape
+    HW = H * W
+    chid, cout = w1.shape[-2], w2.shape[-2]
+    y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
+    if per_sample_w1:
+        w1 = round_tf32(w1)
+    add_bs = 0
+    if add is not None:
+        add = add.contiguous()
+        add_bs = cout * HW if add.shape[0] == B and B > 1 else 0
+    check(lib.msfno_mlp1x1_fwd(ptr(x), x.shape[1] * HW, cin, ptr(w1), w1.shape[-1], (chid * w1.shape[-1]) if per_sample_w1 else 0,
+                               ptr(x2), (x2.shape[1] * HW) if x2 is not None else 0, cin2, ptr(w1b),
+                               w1b.shape[-1] if w1b is not None else 0, ptr(b1), chid if per_sample_b1 else 0, chid, ptr(w2),
+                               w2.shape[-1], ptr(b2), ptr(add), add_bs, ptr(y), B, cout, HW, 0 if final else 2,
+                               torch.cuda.current_stream().cuda_stream), "mlp1x1_fwd")
+    return y

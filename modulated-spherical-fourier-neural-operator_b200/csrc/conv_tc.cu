@@ -3,7 +3,7 @@
 //   * the weight slab [128 x K] (both operand pairs of the big-skip form) is loaded ONCE by TMA and stays in smem;
 //   * activations stream through a small TMA ring as MN-major operands (SWIZZLE_128B_BASE32B, the only layout
 //     tcgen05 accepts for MN-major 32-bit data);
-//   * two 128-column TMEM accumulators alternate, so the epilogue (bias, exact GELU, residual / pos-embed add,
+//   * two 128-column TMEM accumulators alternate, so the epilogue (bias, GELU (gelu_tanh3), residual / pos-embed add,
 //     128-byte row stores) of tile i overlaps the MMAs of tile i+1.
 // SM fill traffic per launch drops from (weights + activations) per tile to activations only.
 //
@@ -195,7 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
           if (p.act_gelu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = gelu_fast(v[j]);
+            for (int j = 0; j < 16; ++j) v[j] = gelu_tanh3(v[j]);
           }
           if (aptr) {
             const float* ap = aptr + (long long)jb * p.ldadd;

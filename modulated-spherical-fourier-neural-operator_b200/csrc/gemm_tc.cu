@@ -189,7 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float t = __uint_as_float(r[j]) + bv;
-          if (p.act_gelu) t = gelu_fast(t);
+          if (p.act_gelu) t = gelu_tanh3(t);
           v[j] = t;
         }
         if (arow) {
@@ -397,7 +397,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           float t = __uint_as_float(r[j]) + bv;
-          if (p.act_gelu) t = gelu_fast(t);
+          if (p.act_gelu) t = gelu_tanh3(t);
           if (p.relu_even && !(j & 1)) t = fmaxf(t, 0.f);
           if (p.round_tf32) t = round_to_tf32(t);
           v[j] = t;

@@ -1,0 +1,355 @@
+// Fused two-layer 1x1-conv MLP on the tensor cores (tensor-core tier of msfno_mlp1x1_fwd):
+//
+//   y[b][o][p] = sum_h w2[o][h] * gelu( sum_c w1[h][c] x[b][c][p] + sum_c w1b[h][c] x2[b][c][p] + b1[h] ) + b2[o] + add[b][o][p]
+//
+// replaces: MLP.fwd = Conv2d(1x1) -> GELU -> Conv2d(1x1) of the encoder and decoder at full resolution, plus the
+//   pos_embed add and the big-skip torch.cat (/root/reference MSFNO/Models/sfno/layers.py:161-168,
+//   sfnonet.py:671,682-684).  Run as two separate GEMM kernels the 256-channel hidden activation costs a 1.06 GB
+//   write and a 1.06 GB read per MLP at 721x1440; here it never leaves the SM.
+//
+// A persistent CTA walks 128-pixel tiles:
+//   GEMM1  acc1[128 px][Chid] = X[128 px][Cin (+Cin2)] * W1^T   -- activations are the MN-major A operand streamed by TMA
+//                                                                  (pixels on the TMEM lanes), weights the K-major B operand
+//   EPI1   acc1 <- tf32(gelu(acc1 + b1))  IN PLACE in TMEM (tcgen05.ld -> registers -> tcgen05.st)
+//   GEMM2  acc2[128 px][Cout] = acc1 * W2^T                     -- A operand read straight from TMEM
+//   EPI2   y = acc2 + b2 (+ add), coalesced 128-byte row stores (lane = pixel)
+// Both weight matrices stream through a shared-memory ring of 32 KB k-blocks (L2 resident: 0.3-0.4 MB in total);
+// the producer runs ahead across phases, so GEMM2 finds its blocks waiting.  EPI2 of tile t overlaps GEMM1 of t+1.
+//
+// Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-17 = epilogues
+// (TMEM lane quarter w % 4 = 32-pixel block; column quarter (w - 2) / 4).
+#include "plan.h"
+#include "tc_common.cuh"
+
+namespace msfno {
+
+static constexpr int ML_BM = 128;                       // pixels per tile
+static constexpr int ML_XBLK = ML_BM * TC_BK * 4;       // activation k-block: 32 channels x 128 pixels = 16 KB
+static constexpr int ML_WBLK = 256 * TC_BK * 4;         // weight k-block slot: up to 256 rows x 32 k = 32 KB
+static constexpr int ML_NSX = 3, ML_NSW = 5;
+static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + 2048 + 256;
+
+struct MlpTcParams {
+  float* D;
+  long long ldd, sd;               // output plane stride (= HW) and sample stride
+  const float* b1; long long sb1;  // hidden bias [Chid], per-sample stride
+  const float* b2;                 // output bias [Cout] or null
+  const float* add; long long ldadd, sadd;
+  long long x_rows_per_sample, x2_rows_per_sample, w1_rows_per_sample;   // row offsets (tensor-map rows) per sample
+  int HW, K1a, K1b, Chid, Cout, N2pad;
+  int tiles;
+  int round_tf32;
+};
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+#define MSFNO_TMEM_LD32(r, taddr)                                                                                        \
+  asm volatile(                                                                                                          \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                          \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                        \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),           \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                        \
+      : "r"(taddr))
+
+#define MSFNO_TMEM_ST32(taddr, r)                                                                                        \
+  asm volatile(                                                                                                          \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                                    \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "                                         \
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),                 \
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),      \
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),        \
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),        \
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                                     \
+      : "memory")
+
+__global__ void __launch_bounds__(576, 1)
+mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
+              const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW1b,
+              const __grid_constant__ CUtensorMap tmW2, MlpTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.z;
+  const int nkb1a = (p.K1a + TC_BK - 1) / TC_BK, nkb1b = (p.K1b + TC_BK - 1) / TC_BK, nkb1 = nkb1a + nkb1b;
+  const int nkb2 = p.Chid / TC_BK;
+  const uint32_t w2_bytes = (uint32_t)p.N2pad * TC_BK * 4, w1_bytes = (uint32_t)p.Chid * TC_BK * 4;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* xring = tiles;
+  uint8_t* wring = tiles + ML_NSX * ML_XBLK;
+  float* b1_s = reinterpret_cast<float*>(wring + ML_NSW * ML_WBLK);   // [256]
+  float* b2_s = b1_s + 256;                                           // [256]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b2_s + 256);
+  uint64_t* xfull = bars;            // [NSX]
+  uint64_t* xempty = bars + 4;       // [NSX]
+  uint64_t* wfull = bars + 8;        // [NSW]
+  uint64_t* wempty = bars + 16;      // [NSW]
+  uint64_t* acc1_full = bars + 24;   // GEMM1 of a tile complete
+  uint64_t* h_ready = bars + 25;     // EPI1 wrote the activated hidden tile back to TMEM (16 warps)
+  uint64_t* acc2_full = bars + 26;   // GEMM2 complete
+  uint64_t* acc2_empty = bars + 27;  // EPI2 finished reading acc2 (16 warps)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < ML_NSX; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
+    for (int s = 0; s < ML_NSW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
+    mbar_init(acc1_full, 1);
+    mbar_init(h_ready, 16);
+    mbar_init(acc2_full, 1);
+    mbar_init(acc2_empty, 16);
+    fence_mbar_init();
+  }
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
+    const int c = (int)threadIdx.x - 64;
+    b1_s[c] = (p.b1 && c < p.Chid) ? p.b1[(long long)b * p.sb1 + c] : 0.0f;
+    b2_s[c] = (p.b2 && c < p.Cout) ? p.b2[c] : 0.0f;
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer: activation ring + weight ring ----------------
+      const int xrow = (int)(b * p.x_rows_per_sample), x2row = (int)(b * p.x2_rows_per_sample);
+      const int w1row = (int)(b * p.w1_rows_per_sample);
+      uint32_t xc = 0, wc = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
+        const int n0 = t * ML_BM;
+        for (int kb = 0; kb < nkb1; ++kb, ++xc, ++wc) {
+          const bool second = kb >= nkb1a;
+          const int kk = (second ? kb - nkb1a : kb) * TC_BK;
+          {  // weight block of GEMM1: Chid rows x 32 k
+            const int s = wc % ML_NSW;
+            mbar_wait_bounded(&wempty[s], ((wc / ML_NSW) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&wfull[s], w1_bytes);
+            tma_load_2d(wring + (size_t)s * ML_WBLK, second ? &tmW1b : &tmW1, &wfull[s], kk, second ? 0 : w1row);
+          }
+          {  // activation block: 32 channels x 128 pixels as four 32 x 32 boxes
+            const int s = xc % ML_NSX;
+            mbar_wait_bounded(&xempty[s], ((xc / ML_NSX) & 1u) ^ 1u);
+            mbar_arrive_expect_tx(&xfull[s], ML_XBLK);
+            uint8_t* dst = xring + (size_t)s * ML_XBLK;
+#pragma unroll
+            for (int j = 0; j < ML_BM / 32; ++j)
+              tma_load_2d(dst + j * (TC_BK * 128), second ? &tmX2 : &tmX, &xfull[s], n0 + 32 * j, (second ? x2row : xrow) + kk);
+          }
+        }
+        for (int kb = 0; kb < nkb2; ++kb, ++wc) {  // weight blocks of GEMM2: N2pad rows x 32 k
+          const int s = wc % ML_NSW;
+          mbar_wait_bounded(&wempty[s], ((wc / ML_NSW) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&wfull[s], w2_bytes);
+          tma_load_2d(wring + (size_t)s * ML_WBLK, &tmW2, &wfull[s], kb * TC_BK, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      // GEMM1: A = activations (MN-major, bit 15), B = W1 (K-major), N = Chid, M = 128 pixels
+      const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(p.Chid >> 3) << 17) |
+                              ((uint32_t)(ML_BM >> 4) << 24);
+      // GEMM2: A = hidden tile in TMEM, B = W2 (K-major), N = N2pad
+      const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N2pad >> 3) << 17) | ((uint32_t)(ML_BM >> 4) << 24);
+      const uint32_t x_addr = base, w_addr = base + ML_NSX * ML_XBLK;
+      uint32_t xc = 0, wc = 0, it = 0;
+      for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+        // acc1 is free: the tensor pipe executes in issue order, GEMM2 of the previous tile (its last reader) is ahead
+        for (int kb = 0; kb < nkb1; ++kb, ++xc, ++wc) {
+          const int sx = xc % ML_NSX, sw = wc % ML_NSW;
+          mbar_wait_bounded(&wfull[sw], (wc / ML_NSW) & 1u);
+          mbar_wait_bounded(&xfull[sx], (xc / ML_NSX) & 1u);
+          tc_fence_after();
+          const uint32_t sa = x_addr + (uint32_t)sx * ML_XBLK, sb = w_addr + (uint32_t)sw * ML_WBLK;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32(tmem_acc1, make_smem_desc(sa + 1024 * k, TC_BK * 128, 512, 1), make_smem_desc(sb + 32 * k, 16, 1024),
+                        idesc1, (kb | k) ? 1u : 0u);
+          tc_commit(&xempty[sx]);
+          tc_commit(&wempty[sw]);
+        }
+        tc_commit(acc1_full);
+        mbar_wait_bounded(h_ready, it & 1u);                    // hidden tile activated in place
+        mbar_wait_bounded(acc2_empty, (it & 1u) ^ 1u);          // previous tile's EPI2 has drained acc2
+        tc_fence_after();
+        for (int kb = 0; kb < nkb2; ++kb, ++wc) {
+          const int sw = wc % ML_NSW;
+          mbar_wait_bounded(&wfull[sw], (wc / ML_NSW) & 1u);
+          tc_fence_after();
+          const uint32_t sb = w_addr + (uint32_t)sw * ML_WBLK;
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32_ts(tmem_acc2, tmem_acc1 + (uint32_t)(kb * TC_BK + k * 8), make_smem_desc(sb + 32 * k, 16, 1024), idesc2,
+                           (kb | k) ? 1u : 0u);
+          tc_commit(&wempty[sw]);
+        }
+        tc_commit(acc2_full);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps 2..17: lane = pixel, column quarter cq ----------------
+    const int q = warp & 3, cq = (warp - 2) >> 2;
+    const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
+      // ---- EPI1: hidden columns [cq*64, cq*64+64) of acc1, in place
+      mbar_wait_bounded(acc1_full, it & 1u);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = cq * 64 + h * 32;
+        if (c0 < p.Chid) {
+          uint32_t r[32];
+          const uint32_t taddr = tmem_acc1 + lane_off + (uint32_t)c0;
+          MSFNO_TMEM_LD32(r, taddr);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_to_tf32_pretrunc(gelu_tanh3(__uint_as_float(r[j]) + b1_s[c0 + j])));
+          MSFNO_TMEM_ST32(taddr, r);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(h_ready);
+
+      // ---- EPI2: output channels [cq*64, cq*64+64) of acc2
+      const int pix = t * ML_BM + q * 32 + lane;
+      const bool pix_ok = pix < p.HW;
+      mbar_wait_bounded(acc2_full, it & 1u);
+      tc_fence_after();
+      auto store_chunk = [&](const uint32_t (&r)[32], const int c0) {
+        const int nch = min(32, p.Cout - c0);
+        if (nch <= 0 || !pix_ok) return;
+        float* dptr = p.D + (long long)b * p.sd + (long long)c0 * p.ldd + pix;
+        const float* aptr = p.add ? p.add + (long long)b * p.sadd + (long long)c0 * p.ldadd + pix : nullptr;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int jb = g * 16, nv = nch - jb;
+          if (nv > 0) {
+            float v[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[jb + j]) + b2_s[c0 + jb + j];
+            if (aptr) {
+              float av[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) av[j] = (j < nv) ? __ldg(aptr + (long long)(jb + j) * p.ldadd) : 0.0f;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += av[j];
+            }
+            if (p.round_tf32) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = round_to_tf32(v[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j < nv) __stcs(dptr + (long long)(jb + j) * p.ldd, v[j]);
+          }
+        }
+      };
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        const int c0 = cq * 64 + h * 32;
+        uint32_t r[32];
+        if (c0 < p.N2pad) {
+          MSFNO_TMEM_LD32(r, tmem_acc2 + lane_off + (uint32_t)c0);
+          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        }
+        if (h == 1) {   // both chunks of this warp are out of acc2 (EPI1 of the next tile follows on these same warps)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc2_empty);
+        }
+        if (c0 < p.N2pad) store_chunk(r, c0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+// 2-D fp32 tensor [rows][ld] (cols valid) with an arbitrary box height (K-major weight blocks: 32 columns x box_rows rows)
+static int make_wmap(CUtensorMap* tm, const float* base, long long rows, long long cols, long long ld, int box_rows) {
+  return make_map(tm, base, rows, cols, ld, box_rows, false);
+}
+
+}  // namespace msfno
+
+using namespace msfno;
+
+extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const float* w1, long ldw1, long w1_bstride,
+                                const float* x2, long x2_bstride, int Cin2, const float* w1b, long ldw1b, const float* b1,
+                                long b1_bstride, int Chid, const float* w2, long ldw2, const float* b2, const float* add,
+                                long add_bstride, float* y, int B, int Cout, long HW, int flags, void* stream) {
+  if (!x || !w1 || !w2 || !y || B < 1 || Cin < 1 || Chid < 1 || Cout < 1 || HW < 1 || ldw1 < Cin || ldw2 < Chid ||
+      (x2 && (!w1b || Cin2 < 1 || ldw1b < Cin2)))
+    return record_error(MSFNO_ERR_BAD_SHAPE, "mlp1x1_fwd: bad argument");
+  auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+  if (Chid % 32 != 0 || Chid > 256 || Cout > 256 || HW % 4 != 0 || HW > 0x7fffffffL || (ldw1 & 3) || (ldw2 & 3) ||
+      (x2 && (ldw1b & 3)) || x_bstride % HW != 0 || (x2 && x2_bstride % HW != 0) || w1_bstride % ldw1 != 0 || !al16(x) ||
+      !al16(w1) || !al16(w2) || (x2 && (!al16(x2) || !al16(w1b))) || get_encode() == nullptr)
+    return record_error(MSFNO_ERR_UNSUPPORTED, "mlp1x1_fwd: shape / alignment outside the fused tensor-core kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N2pad = (Cout + 15) / 16 * 16;
+  CUtensorMap tmX, tmX2, tmW1, tmW1b, tmW2;
+  int rc = make_map(&tmX, x, (long long)(B - 1) * (x_bstride / HW) + Cin, HW, HW, TC_BK, true);
+  if (rc) return rc;
+  rc = make_wmap(&tmW1, w1, (long long)(B - 1) * (w1_bstride / ldw1) + Chid, Cin, ldw1, Chid);
+  if (rc) return rc;
+  if (x2) {
+    rc = make_map(&tmX2, x2, (long long)(B - 1) * (x2_bstride / HW) + Cin2, HW, HW, TC_BK, true);
+    if (rc) return rc;
+    rc = make_wmap(&tmW1b, w1b, Chid, Cin2, ldw1b, Chid);
+    if (rc) return rc;
+  } else {
+    tmX2 = tmX;
+    tmW1b = tmW1;
+  }
+  rc = make_wmap(&tmW2, w2, Cout, Chid, ldw2, N2pad);
+  if (rc) return rc;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM); });
+  MSFNO_CUDA_OK(attr_err);
+  MlpTcParams p{};
+  p.D = y; p.ldd = HW; p.sd = (long long)Cout * HW;
+  p.b1 = b1; p.sb1 = b1_bstride; p.b2 = b2;
+  p.add = add; p.ldadd = HW; p.sadd = add_bstride;
+  p.x_rows_per_sample = x_bstride / HW; p.x2_rows_per_sample = x2 ? x2_bstride / HW : 0; p.w1_rows_per_sample = w1_bstride / ldw1;
+  p.HW = (int)HW; p.K1a = Cin; p.K1b = x2 ? Cin2 : 0; p.Chid = Chid; p.Cout = Cout; p.N2pad = N2pad;
+  p.tiles = (int)((HW + ML_BM - 1) / ML_BM);
+  p.round_tf32 = (flags >> 1) & 1;
+  int dev = 0, sms = 0;
+  MSFNO_CUDA_OK(cudaGetDevice(&dev));
+  MSFNO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  int gx = sms / B;
+  if (gx < 1) gx = 1;
+  if (gx > p.tiles) gx = p.tiles;
+  mlp_tc_kernel<<<dim3(gx, 1, B), 576, ML_SMEM, st>>>(tmX, tmX2, tmW1, tmW1b, tmW2, p);
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}

@@ -68,11 +68,11 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   d |= (uint64_t)layout_type << 61;
   return d;
 }
-__device__ __forceinline__ float round_to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
-}
+// round to nearest (ties away) TF32, as cvt.rna.tf32.f32 for every finite input; two integer instructions instead of
+// the three (with an inf/nan test) the cvt expands to -- the epilogues that call it are issue-bound
+__device__ __forceinline__ float round_to_tf32(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+// operand that the tensor core itself will truncate (A operand written to TMEM): the add alone completes the rounding
+__device__ __forceinline__ float round_to_tf32_pretrunc(float x) { return __uint_as_float(__float_as_uint(x) + 0x1000u); }
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");

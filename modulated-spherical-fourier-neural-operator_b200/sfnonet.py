@@ -28,7 +28,7 @@ from torch.utils.checkpoint import checkpoint
 from . import _lib
 from . import precision as _precision
 from ._lib import check, lib, ptr
-from .conv import conv1x1, padded_weight
+from .conv import mlp1x1, mlp1x1_supported, conv1x1, padded_weight
 from .layers import MLP, DropPath, SpectralAttentionS2, SpectralConvS2, trunc_normal_
 from .sht import InverseRealSHT, RealSHT, _stream
 
@@ -445,6 +445,10 @@ class FourierNeuralOperatorNet(nn.Module):
     def _encode_fused(self, x):
         enc = self.encoder.fwd
         x = x.contiguous().float()
+        if enc[0].bias is not None and mlp1x1_supported(enc[0].out_channels, enc[2].out_channels, x.shape[2] * x.shape[3]):
+            # both layers and the pos_embed add in one kernel: the hidden activation stays in tensor memory
+            return mlp1x1(x, padded_weight(enc[0].weight), self.in_chans, enc[0].bias, padded_weight(enc[2].weight), enc[2].bias,
+                          add=self.pos_embed)
         h = conv1x1(x, padded_weight(enc[0].weight), self.in_chans, bias=enc[0].bias, act_gelu=True)
         return conv1x1(h, padded_weight(enc[2].weight), enc[2].in_channels, bias=enc[2].bias, add=self.pos_embed)
 
@@ -459,6 +463,10 @@ class FourierNeuralOperatorNet(nn.Module):
         bias_b = torch.matmul(S, W1[:, :E].t())
         if dec[0].bias is not None:
             bias_b = bias_b + dec[0].bias
+        if mlp1x1_supported(dec[0].out_channels, dec[2].out_channels, y.shape[2] * y.shape[3]):
+            return mlp1x1(y, Wb, E, bias_b.contiguous(), padded_weight(dec[2].weight), dec[2].bias,
+                          x2=residual.contiguous().float(), w1b=W2, cin2=self.in_chans, per_sample_w1=True,
+                          per_sample_b1=True, final=True)
         h = conv1x1(y, Wb, E, bias=bias_b.contiguous(), act_gelu=True, x2=residual.contiguous().float(), w2=W2,
                     cin2=self.in_chans, per_sample_w=True, per_sample_bias=True)
         return conv1x1(h, padded_weight(dec[2].weight), dec[2].in_channels, bias=dec[2].bias, final=True)

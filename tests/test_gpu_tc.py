@@ -152,3 +152,48 @@ def test_conv1x1_fused(tier, tol, B, Cin, Cout, H, W, Cin2):
         assert rel_l2(got, ref) < tol
     finally:
         msfno_b200.set_precision("fp32")
+
+
+def _mlp_ref(x, w1, b1, w2, b2, add=None, x2=None, w1b=None):
+    """fp64 restatement of Conv2d(1x1) -> GELU(erf) -> Conv2d(1x1) (+ big-skip second operand, + add), layers.py:161-168."""
+    B, _, H, W = x.shape
+    xd = x.double().flatten(2)
+    h = torch.einsum("bhc,bcp->bhp", w1.double() if w1.dim() == 3 else w1.double().expand(B, -1, -1), xd)
+    if x2 is not None:
+        h = h + torch.einsum("hc,bcp->bhp", w1b.double(), x2.double().flatten(2))
+    h = torch.nn.functional.gelu(h + (b1.double() if b1.dim() == 2 else b1.double().expand(B, -1)).unsqueeze(-1))
+    y = torch.einsum("oh,bhp->bop", w2.double(), h)
+    if b2 is not None:
+        y = y + b2.double().view(1, -1, 1)
+    y = y.reshape(B, -1, H, W)
+    return y + add.double() if add is not None else y
+
+
+@pytest.mark.parametrize("B,cin,cin2,chid,cout,H,W,with_add,per_sample", [
+    (1, 73, 0, 256, 256, 36, 100, True, False),     # encoder form: pos_embed add
+    (2, 256, 73, 256, 73, 25, 40, False, True),     # decoder form: big-skip second operand, per-sample folded weights
+    (1, 40, 0, 64, 24, 9, 12, False, False),        # small / ragged: one partial 128-pixel tile
+    (3, 16, 8, 128, 256, 31, 36, True, False)])
+def test_mlp1x1_fused_tf32(B, cin, cin2, chid, cout, H, W, with_add, per_sample):
+    from msfno_b200.conv import mlp1x1, padded_weight
+    msfno_b200.set_precision("tf32")
+    try:
+        g = torch.Generator().manual_seed(B * 1000 + cin + cout)
+        x = torch.randn(B, cin, H, W, generator=g).cuda()
+        x2 = torch.randn(B, cin2, H, W, generator=g).cuda() if cin2 else None
+        w1 = (torch.randn(B, chid, cin, generator=g) if per_sample else torch.randn(chid, cin, generator=g)).cuda() / cin ** 0.5
+        w1b = torch.randn(chid, cin2, generator=g).cuda() / cin ** 0.5 if cin2 else None
+        b1 = (torch.randn(B, chid, generator=g) if per_sample else torch.randn(chid, generator=g)).cuda()
+        w2 = torch.randn(cout, chid, generator=g).cuda() / chid ** 0.5
+        b2 = torch.randn(cout, generator=g).cuda()
+        add = torch.randn(1, cout, H, W, generator=g).cuda() if with_add else None
+        pad = lambda w: torch.nn.functional.pad(w, (0, (-w.shape[-1]) % 4)).contiguous()
+        y = mlp1x1(x, pad(w1), cin, b1.contiguous(), pad(w2), b2, add=add, x2=x2, w1b=pad(w1b) if cin2 else None, cin2=cin2,
+                   per_sample_w1=per_sample, per_sample_b1=per_sample, final=True)
+        torch.cuda.synchronize()
+        want = _mlp_ref(x, w1, b1, w2, b2, add, x2, w1b)
+        assert torch.isfinite(y).all()
+        err = rel_l2(y, want)
+        assert err < TOL_TF32, err
+    finally:
+        msfno_b200.set_precision("fp32")
