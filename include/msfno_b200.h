@@ -209,7 +209,8 @@ int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const float* w, l
  *   y[b][o][p] = sum_h w2[o][h] * gelu( sum_c w1[h][c] x[b][c][p] + sum_c w1b[h][c] x2[b][c][p] + b1[h] )
  *                + b2[o] + add[b][o][p]
  * The Chid-channel hidden activation stays in tensor memory.  Tensor-core (TF32) tier only: returns
- * MSFNO_ERR_UNSUPPORTED for shapes outside Chid % 32 == 0, Chid <= 256, Cout <= 256, HW % 4 == 0 (callers then
+ * MSFNO_ERR_UNSUPPORTED for shapes outside Chid % 32 == 0 (Chid <= 256, or a multiple of 256 up to 1024: processed
+ * in 256-channel chunks), Cout <= 256, HW % 4 == 0 (callers then
  * use two msfno_conv1x1_fwd calls).  w1: [Chid][ldw1] (per-sample stride w1_bstride, 0 = shared), w1b: [Chid][ldw1b],
  * w2: [Cout][ldw2], b1: [Chid] (stride b1_bstride), b2: [Cout] or NULL, add: [B or 1][Cout][HW] or NULL.
  * flags bit 1: round y to TF32. */

@@ -78,7 +78,8 @@ def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, ci
 
 def mlp1x1_supported(chid, cout, HW):
     """Shapes the fused two-layer kernel (msfno_mlp1x1_fwd, tensor-core tier) takes."""
-    return _precision.get_precision() == "tf32" and chid % 32 == 0 and chid <= 256 and cout <= 256 and HW % 4 == 0
+    ok_hid = chid % 32 == 0 and (chid <= 256 or (chid % 256 == 0 and chid <= 1024))
+    return _precision.get_precision() == "tf32" and ok_hid and cout <= 256 and HW % 4 == 0
 
 
 def mlp1x1(x, w1, cin, b1, w2, b2=None, add=None, x2=None, w1b=None, cin2=0, per_sample_w1=False, per_sample_b1=False,

@@ -13,6 +13,8 @@
 //   EPI1   acc1 <- tf32(gelu(acc1 + b1))  IN PLACE in TMEM (tcgen05.ld -> registers -> tcgen05.st)
 //   GEMM2  acc2[128 px][Cout] = acc1 * W2^T                     -- A operand read straight from TMEM
 //   EPI2   y = acc2 + b2 (+ add), coalesced 128-byte row stores (lane = pixel)
+// A hidden layer wider than the 256 TMEM columns (the 512-channel block MLPs) is processed in chunks of 256: GEMM1 /
+// EPI1 per chunk, GEMM2 accumulating the chunk's K range into acc2 (the activation blocks are re-streamed per chunk).
 // Both weight matrices stream through a shared-memory ring of 32 KB k-blocks (L2 resident: 0.3-0.4 MB in total);
 // the producer runs ahead across phases, so GEMM2 finds its blocks waiting.  EPI2 of tile t overlaps GEMM1 of t+1.
 //
@@ -27,7 +29,8 @@ static constexpr int ML_BM = 128;                       // pixels per tile
 static constexpr int ML_XBLK = ML_BM * TC_BK * 4;       // activation k-block: 32 channels x 128 pixels = 16 KB
 static constexpr int ML_WBLK = 256 * TC_BK * 4;         // weight k-block slot: up to 256 rows x 32 k = 32 KB
 static constexpr int ML_NSX = 3, ML_NSW = 5;
-static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + 2048 + 256;
+static constexpr int ML_MAX_HID = 1024;
+static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + (ML_MAX_HID + 256) * 4 + 256;
 
 struct MlpTcParams {
   float* D;
@@ -83,15 +86,16 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z;
   const int nkb1a = (p.K1a + TC_BK - 1) / TC_BK, nkb1b = (p.K1b + TC_BK - 1) / TC_BK, nkb1 = nkb1a + nkb1b;
-  const int nkb2 = p.Chid / TC_BK;
-  const uint32_t w2_bytes = (uint32_t)p.N2pad * TC_BK * 4, w1_bytes = (uint32_t)p.Chid * TC_BK * 4;
+  const int HC = min(p.Chid, 256), nh = p.Chid / HC;      // hidden chunk (TMEM columns of acc1) and chunk count
+  const int nkb2 = HC / TC_BK;                            // GEMM2 k-blocks per chunk
+  const uint32_t w2_bytes = (uint32_t)p.N2pad * TC_BK * 4, w1_bytes = (uint32_t)HC * TC_BK * 4;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* xring = tiles;
   uint8_t* wring = tiles + ML_NSX * ML_XBLK;
-  float* b1_s = reinterpret_cast<float*>(wring + ML_NSW * ML_WBLK);   // [256]
-  float* b2_s = b1_s + 256;                                           // [256]
+  float* b1_s = reinterpret_cast<float*>(wring + ML_NSW * ML_WBLK);   // [ML_MAX_HID]
+  float* b2_s = b1_s + ML_MAX_HID;                                    // [256]
   uint64_t* bars = reinterpret_cast<uint64_t*>(b2_s + 256);
   uint64_t* xfull = bars;            // [NSX]
   uint64_t* xempty = bars + 4;       // [NSX]
@@ -114,7 +118,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
     const int c = (int)threadIdx.x - 64;
-    b1_s[c] = (p.b1 && c < p.Chid) ? p.b1[(long long)b * p.sb1 + c] : 0.0f;
+    for (int h = c; h < ML_MAX_HID; h += 256) b1_s[h] = (p.b1 && h < p.Chid) ? p.b1[(long long)b * p.sb1 + h] : 0.0f;
     b2_s[c] = (p.b2 && c < p.Cout) ? p.b2[c] : 0.0f;
   }
   if (warp == 1) {
@@ -135,30 +139,32 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       uint32_t xc = 0, wc = 0;
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
         const int n0 = t * ML_BM;
-        for (int kb = 0; kb < nkb1; ++kb, ++xc, ++wc) {
-          const bool second = kb >= nkb1a;
-          const int kk = (second ? kb - nkb1a : kb) * TC_BK;
-          {  // weight block of GEMM1: Chid rows x 32 k
+        for (int hh = 0; hh < nh; ++hh) {
+          for (int kb = 0; kb < nkb1; ++kb, ++xc, ++wc) {
+            const bool second = kb >= nkb1a;
+            const int kk = (second ? kb - nkb1a : kb) * TC_BK;
+            {  // weight block of GEMM1: HC hidden rows x 32 k
+              const int s = wc % ML_NSW;
+              mbar_wait_bounded(&wempty[s], ((wc / ML_NSW) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&wfull[s], w1_bytes);
+              tma_load_2d(wring + (size_t)s * ML_WBLK, second ? &tmW1b : &tmW1, &wfull[s], kk, (second ? 0 : w1row) + hh * HC);
+            }
+            {  // activation block: 32 channels x 128 pixels as four 32 x 32 boxes
+              const int s = xc % ML_NSX;
+              mbar_wait_bounded(&xempty[s], ((xc / ML_NSX) & 1u) ^ 1u);
+              mbar_arrive_expect_tx(&xfull[s], ML_XBLK);
+              uint8_t* dst = xring + (size_t)s * ML_XBLK;
+#pragma unroll
+              for (int j = 0; j < ML_BM / 32; ++j)
+                tma_load_2d(dst + j * (TC_BK * 128), second ? &tmX2 : &tmX, &xfull[s], n0 + 32 * j, (second ? x2row : xrow) + kk);
+            }
+          }
+          for (int kb = 0; kb < nkb2; ++kb, ++wc) {  // weight blocks of GEMM2: N2pad rows x 32 k of this hidden chunk
             const int s = wc % ML_NSW;
             mbar_wait_bounded(&wempty[s], ((wc / ML_NSW) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&wfull[s], w1_bytes);
-            tma_load_2d(wring + (size_t)s * ML_WBLK, second ? &tmW1b : &tmW1, &wfull[s], kk, second ? 0 : w1row);
+            mbar_arrive_expect_tx(&wfull[s], w2_bytes);
+            tma_load_2d(wring + (size_t)s * ML_WBLK, &tmW2, &wfull[s], hh * HC + kb * TC_BK, 0);
           }
-          {  // activation block: 32 channels x 128 pixels as four 32 x 32 boxes
-            const int s = xc % ML_NSX;
-            mbar_wait_bounded(&xempty[s], ((xc / ML_NSX) & 1u) ^ 1u);
-            mbar_arrive_expect_tx(&xfull[s], ML_XBLK);
-            uint8_t* dst = xring + (size_t)s * ML_XBLK;
-#pragma unroll
-            for (int j = 0; j < ML_BM / 32; ++j)
-              tma_load_2d(dst + j * (TC_BK * 128), second ? &tmX2 : &tmX, &xfull[s], n0 + 32 * j, (second ? x2row : xrow) + kk);
-          }
-        }
-        for (int kb = 0; kb < nkb2; ++kb, ++wc) {  // weight blocks of GEMM2: N2pad rows x 32 k
-          const int s = wc % ML_NSW;
-          mbar_wait_bounded(&wempty[s], ((wc / ML_NSW) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&wfull[s], w2_bytes);
-          tma_load_2d(wring + (size_t)s * ML_WBLK, &tmW2, &wfull[s], kb * TC_BK, 0);
         }
       }
     }
@@ -166,41 +172,43 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
       // GEMM1: A = activations (MN-major, bit 15), B = W1 (K-major), N = Chid, M = 128 pixels
-      const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(p.Chid >> 3) << 17) |
+      const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(HC >> 3) << 17) |
                               ((uint32_t)(ML_BM >> 4) << 24);
       // GEMM2: A = hidden tile in TMEM, B = W2 (K-major), N = N2pad
       const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.N2pad >> 3) << 17) | ((uint32_t)(ML_BM >> 4) << 24);
       const uint32_t x_addr = base, w_addr = base + ML_NSX * ML_XBLK;
-      uint32_t xc = 0, wc = 0, it = 0;
+      uint32_t xc = 0, wc = 0, it = 0, seq = 0;
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
-        // acc1 is free: the tensor pipe executes in issue order, GEMM2 of the previous tile (its last reader) is ahead
-        for (int kb = 0; kb < nkb1; ++kb, ++xc, ++wc) {
-          const int sx = xc % ML_NSX, sw = wc % ML_NSW;
-          mbar_wait_bounded(&wfull[sw], (wc / ML_NSW) & 1u);
-          mbar_wait_bounded(&xfull[sx], (xc / ML_NSX) & 1u);
-          tc_fence_after();
-          const uint32_t sa = x_addr + (uint32_t)sx * ML_XBLK, sb = w_addr + (uint32_t)sw * ML_WBLK;
+        for (int hh = 0; hh < nh; ++hh, ++seq) {
+          // acc1 is free: the tensor pipe executes in issue order, the previous GEMM2 (its last reader) is ahead
+          for (int kb = 0; kb < nkb1; ++kb, ++xc, ++wc) {
+            const int sx = xc % ML_NSX, sw = wc % ML_NSW;
+            mbar_wait_bounded(&wfull[sw], (wc / ML_NSW) & 1u);
+            mbar_wait_bounded(&xfull[sx], (xc / ML_NSX) & 1u);
+            tc_fence_after();
+            const uint32_t sa = x_addr + (uint32_t)sx * ML_XBLK, sb = w_addr + (uint32_t)sw * ML_WBLK;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32(tmem_acc1, make_smem_desc(sa + 1024 * k, TC_BK * 128, 512, 1), make_smem_desc(sb + 32 * k, 16, 1024),
-                        idesc1, (kb | k) ? 1u : 0u);
-          tc_commit(&xempty[sx]);
-          tc_commit(&wempty[sw]);
-        }
-        tc_commit(acc1_full);
-        mbar_wait_bounded(h_ready, it & 1u);                    // hidden tile activated in place
-        mbar_wait_bounded(acc2_empty, (it & 1u) ^ 1u);          // previous tile's EPI2 has drained acc2
-        tc_fence_after();
-        for (int kb = 0; kb < nkb2; ++kb, ++wc) {
-          const int sw = wc % ML_NSW;
-          mbar_wait_bounded(&wfull[sw], (wc / ML_NSW) & 1u);
+            for (int k = 0; k < TC_BK / 8; ++k)
+              tc_mma_tf32(tmem_acc1, make_smem_desc(sa + 1024 * k, TC_BK * 128, 512, 1), make_smem_desc(sb + 32 * k, 16, 1024),
+                          idesc1, (kb | k) ? 1u : 0u);
+            tc_commit(&xempty[sx]);
+            tc_commit(&wempty[sw]);
+          }
+          tc_commit(acc1_full);
+          mbar_wait_bounded(h_ready, seq & 1u);                     // hidden chunk activated in place
+          if (hh == 0) mbar_wait_bounded(acc2_empty, (it & 1u) ^ 1u);   // previous tile's EPI2 has drained acc2
           tc_fence_after();
-          const uint32_t sb = w_addr + (uint32_t)sw * ML_WBLK;
+          for (int kb = 0; kb < nkb2; ++kb, ++wc) {
+            const int sw = wc % ML_NSW;
+            mbar_wait_bounded(&wfull[sw], (wc / ML_NSW) & 1u);
+            tc_fence_after();
+            const uint32_t sb = w_addr + (uint32_t)sw * ML_WBLK;
 #pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k)
-            tc_mma_tf32_ts(tmem_acc2, tmem_acc1 + (uint32_t)(kb * TC_BK + k * 8), make_smem_desc(sb + 32 * k, 16, 1024), idesc2,
-                           (kb | k) ? 1u : 0u);
-          tc_commit(&wempty[sw]);
+            for (int k = 0; k < TC_BK / 8; ++k)
+              tc_mma_tf32_ts(tmem_acc2, tmem_acc1 + (uint32_t)(kb * TC_BK + k * 8), make_smem_desc(sb + 32 * k, 16, 1024), idesc2,
+                             (hh | kb | k) ? 1u : 0u);
+            tc_commit(&wempty[sw]);
+          }
         }
         tc_commit(acc2_full);
       }
@@ -209,28 +217,31 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     // ---------------- epilogue warps 2..17: lane = pixel, column quarter cq ----------------
     const int q = warp & 3, cq = (warp - 2) >> 2;
     const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-    uint32_t it = 0;
+    uint32_t it = 0, seq = 0;
     for (int t = blockIdx.x; t < p.tiles; t += gridDim.x, ++it) {
-      // ---- EPI1: hidden columns [cq*64, cq*64+64) of acc1, in place
-      mbar_wait_bounded(acc1_full, it & 1u);
-      tc_fence_after();
+      // ---- EPI1 per hidden chunk: columns [cq*64, cq*64+64) of acc1, in place
+      for (int hh = 0; hh < nh; ++hh, ++seq) {
+        mbar_wait_bounded(acc1_full, seq & 1u);
+        tc_fence_after();
 #pragma unroll 1
-      for (int h = 0; h < 2; ++h) {
-        const int c0 = cq * 64 + h * 32;
-        if (c0 < p.Chid) {
-          uint32_t r[32];
-          const uint32_t taddr = tmem_acc1 + lane_off + (uint32_t)c0;
-          MSFNO_TMEM_LD32(r, taddr);
-          asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = cq * 64 + h * 32;
+          if (c0 < HC) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_acc1 + lane_off + (uint32_t)c0;
+            MSFNO_TMEM_LD32(r, taddr);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            const float* bb = b1_s + hh * HC + c0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_to_tf32_pretrunc(gelu_tanh3(__uint_as_float(r[j]) + b1_s[c0 + j])));
-          MSFNO_TMEM_ST32(taddr, r);
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_to_tf32_pretrunc(gelu_tanh3(__uint_as_float(r[j]) + bb[j])));
+            MSFNO_TMEM_ST32(taddr, r);
+          }
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(h_ready);
       }
-      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(h_ready);
 
       // ---- EPI2: output channels [cq*64, cq*64+64) of acc2
       const int pix = t * ML_BM + q * 32 + lane;
@@ -308,7 +319,7 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
       (x2 && (!w1b || Cin2 < 1 || ldw1b < Cin2)))
     return record_error(MSFNO_ERR_BAD_SHAPE, "mlp1x1_fwd: bad argument");
   auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
-  if (Chid % 32 != 0 || Chid > 256 || Cout > 256 || HW % 4 != 0 || HW > 0x7fffffffL || (ldw1 & 3) || (ldw2 & 3) ||
+  if (Chid % 32 != 0 || (Chid > 256 && Chid % 256 != 0) || Chid > ML_MAX_HID || Cout > 256 || HW % 4 != 0 || HW > 0x7fffffffL || (ldw1 & 3) || (ldw2 & 3) ||
       (x2 && (ldw1b & 3)) || x_bstride % HW != 0 || (x2 && x2_bstride % HW != 0) || w1_bstride % ldw1 != 0 || !al16(x) ||
       !al16(w1) || !al16(w2) || (x2 && (!al16(x2) || !al16(w1b))) || get_encode() == nullptr)
     return record_error(MSFNO_ERR_UNSUPPORTED, "mlp1x1_fwd: shape / alignment outside the fused tensor-core kernel");
@@ -317,12 +328,12 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
   CUtensorMap tmX, tmX2, tmW1, tmW1b, tmW2;
   int rc = make_map(&tmX, x, (long long)(B - 1) * (x_bstride / HW) + Cin, HW, HW, TC_BK, true);
   if (rc) return rc;
-  rc = make_wmap(&tmW1, w1, (long long)(B - 1) * (w1_bstride / ldw1) + Chid, Cin, ldw1, Chid);
+  rc = make_wmap(&tmW1, w1, (long long)(B - 1) * (w1_bstride / ldw1) + Chid, Cin, ldw1, Chid < 256 ? Chid : 256);
   if (rc) return rc;
   if (x2) {
     rc = make_map(&tmX2, x2, (long long)(B - 1) * (x2_bstride / HW) + Cin2, HW, HW, TC_BK, true);
     if (rc) return rc;
-    rc = make_wmap(&tmW1b, w1b, Chid, Cin2, ldw1b, Chid);
+    rc = make_wmap(&tmW1b, w1b, Chid, Cin2, ldw1b, Chid < 256 ? Chid : 256);
     if (rc) return rc;
   } else {
     tmX2 = tmX;

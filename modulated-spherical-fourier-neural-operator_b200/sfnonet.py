@@ -232,8 +232,13 @@ class FourierNeuralOperatorBlock(nn.Module):
             bias_b = torch.matmul(S1, W1[:, :C].t())
             if fc1.bias is not None:
                 bias_b = bias_b + fc1.bias
-            h = conv1x1(y, Wb, C, bias=bias_b.contiguous(), act_gelu=True, per_sample_w=True, per_sample_bias=True)
             fuse_res = no_drop and not self.concat_skip and isinstance(getattr(self, "outer_skip", None), nn.Identity)
+            if mlp1x1_supported(fc1.out_channels, fc2.out_channels, y.shape[2] * y.shape[3]):
+                # fc1 -> GELU -> fc2 (+ residual) in one kernel; the 512-channel hidden tile never leaves tensor memory
+                out = mlp1x1(y, Wb, C, bias_b.contiguous(), padded_weight(fc2.weight), fc2.bias,
+                             add=residual.contiguous().float() if fuse_res else None, per_sample_w1=True, per_sample_b1=True)
+                return out if fuse_res else self._tail(out, residual)
+            h = conv1x1(y, Wb, C, bias=bias_b.contiguous(), act_gelu=True, per_sample_w=True, per_sample_bias=True)
             out = conv1x1(h, padded_weight(fc2.weight), fc2.in_channels, bias=fc2.bias,
                           add=residual.contiguous().float() if fuse_res else None)
             return out if fuse_res else self._tail(out, residual)

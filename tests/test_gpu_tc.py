@@ -173,7 +173,8 @@ def _mlp_ref(x, w1, b1, w2, b2, add=None, x2=None, w1b=None):
     (1, 73, 0, 256, 256, 36, 100, True, False),     # encoder form: pos_embed add
     (2, 256, 73, 256, 73, 25, 40, False, True),     # decoder form: big-skip second operand, per-sample folded weights
     (1, 40, 0, 64, 24, 9, 12, False, False),        # small / ragged: one partial 128-pixel tile
-    (3, 16, 8, 128, 256, 31, 36, True, False)])
+    (3, 16, 8, 128, 256, 31, 36, True, False),
+    (2, 256, 0, 512, 256, 30, 64, True, True)])     # block MLP form: 512 hidden channels in two TMEM chunks, residual add
 def test_mlp1x1_fused_tf32(B, cin, cin2, chid, cout, H, W, with_add, per_sample):
     from msfno_b200.conv import mlp1x1, padded_weight
     msfno_b200.set_precision("tf32")
@@ -186,7 +187,7 @@ def test_mlp1x1_fused_tf32(B, cin, cin2, chid, cout, H, W, with_add, per_sample)
         b1 = (torch.randn(B, chid, generator=g) if per_sample else torch.randn(chid, generator=g)).cuda()
         w2 = torch.randn(cout, chid, generator=g).cuda() / chid ** 0.5
         b2 = torch.randn(cout, generator=g).cuda()
-        add = torch.randn(1, cout, H, W, generator=g).cuda() if with_add else None
+        add = torch.randn(B if per_sample else 1, cout, H, W, generator=g).cuda() if with_add else None
         pad = lambda w: torch.nn.functional.pad(w, (0, (-w.shape[-1]) % 4)).contiguous()
         y = mlp1x1(x, pad(w1), cin, b1.contiguous(), pad(w2), b2, add=add, x2=x2, w1b=pad(w1b) if cin2 else None, cin2=cin2,
                    per_sample_w1=per_sample, per_sample_b1=per_sample, final=True)
