@@ -1,0 +1,357 @@
+// Longitude transforms of the tensor-core tier as TF32 GEMMs against precomputed DFT matrices.
+//
+// replaces (tensor-core tier, forward direction only): the rfft / irfft stage of RealSHT / InverseRealSHT
+//   (torch_harmonics: x = 2 pi rfft(x, norm="forward") truncated to mmax; irfft(x, n=nlon, norm="forward")), i.e.
+//   launch_rfft2d / launch_irfft2d of the fp32 tier.  The truncated spectrum keeps only mlim <= 120 orders, so the
+//   transform is a [rows x nlon] x [nlon x 2 mlim] product: 0.5-1 kflop per input byte -- tensor-core work.  On this
+//   part the FP32 pipe limits the FFT kernels (52 / 60 us for a 30 MB inner grid, 0.55 / 0.74 ms at 721x1440); the
+//   same contraction on tcgen05 is bound by memory again.
+//
+//   forward : Xt[b][m][2c+ri][lat] = tf32( sc[b,c] * sum_j x[b,c,lat,j] F[2m+ri][j] + [m=0,ri=0] 2 pi sh[b,c] )
+//             A = x rows (K-major), B = F [2 mlim][nlon] (K-major); lat sits on the TMEM lanes, so the transposed
+//             store into the [m][2C][kpad] layout of the Legendre stage is a coalesced 128-byte access per column
+//   inverse : y[b,c,lat,j] = act( sum_n Yt[b][m][2c+ri][lat] G[j][n] + skip ), plane statistics on the way out
+//             A = Yt read in place as an MN-major operand through a 5-D tensor map (lat contiguous, n = (m, ri) rows),
+//             B = G [nlon][2 mlim] (K-major); the output tile is staged through shared memory (the pipeline stages are
+//             idle by then) so that every global access of y / skip is a contiguous row segment
+//
+// CTA tile: MT x 128 rows (lat of one (b, c) plane) by 256 columns, K blocks of 32; MT = 2 halves the re-reads of the
+// DFT matrix at 721x1440 (two accumulators = all 512 TMEM columns).  Warp roles as in gemm_tc.cu.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "plan.h"
+#include "tc_common.cuh"
+
+namespace msfno {
+
+static constexpr int DF_BN = 256;
+static constexpr int DF_A_BYTES = 128 * TC_BK * 4;      // 16 KB: 128 rows x 32 k
+static constexpr int DF_B_BYTES = DF_BN * TC_BK * 4;    // 32 KB: 256 rows x 32 k
+static constexpr int DF_TPITCH = DF_BN + 1;             // staging pitch (floats) of the inverse epilogue
+
+struct DftParams {
+  float* out;
+  const float* sc; const float* sh;     // forward: per-plane scale / shift (InstanceNorm affine) or null
+  const float* skip;                    // inverse: tensor added before the activation, or null
+  double* stats;                        // inverse: per-plane (sum, sum of squares) accumulators or null
+  int nlat, nlon, mlim, kpad, C;
+  int nkb;                              // k blocks
+  int flags;                            // forward: bit0 round to TF32; inverse: bit0 GELU, bit1 round to TF32
+  float dc;                             // forward: factor of the shift on the (m = 0, re) bin = 2 pi
+};
+
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
+#define MSFNO_DFT_LD32(r, taddr)                                                                                         \
+  asm volatile(                                                                                                          \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                          \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                        \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),           \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                        \
+      : "r"(taddr))
+
+// grid: (N tiles of 256 [inverse only], row tiles of MT*128, B*C planes)
+template <bool INV, int MT, int NS>
+__global__ void __launch_bounds__(256, 1)
+dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DftParams p) {
+  constexpr int STAGE = MT * DF_A_BYTES + DF_B_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bc = blockIdx.z, b = bc / p.C, c = bc - b * p.C;
+  const int lat0 = blockIdx.y * (MT * 128);
+  const int n0 = blockIdx.x * DF_BN;
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + NS * STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + NS;
+  uint64_t* tmem_full = bars + 2 * NS;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
+  double* red = reinterpret_cast<double*>(bars + 2 * NS + 2);   // [16]
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(MT * DF_BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- TMA producer ----------------
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int s = kb % NS;
+      mbar_wait_bounded(&empty[s], (uint32_t)(((kb / NS) & 1) ^ 1));
+      mbar_arrive_expect_tx(&full[s], STAGE);
+      uint8_t* sa = tiles + (size_t)s * STAGE;
+      if (!INV) {
+        // A: rows (plane, lat) of x, 32 longitudes per block
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) tma_load_2d(sa + mt * DF_A_BYTES, &tmA, &full[s], kb * TC_BK, bc * p.nlat + lat0 + mt * 128);
+      } else {
+        // A: Yt[b][m][2c+ri][lat]: box = 32 lat x (ri 2) x (c 1) x (m 16) x (b 1) = 32 k-rows of 128 bytes
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            tma_load_5d(sa + mt * DF_A_BYTES + j * (TC_BK * 128), &tmA, &full[s], lat0 + mt * 128 + 32 * j, 0, c, kb * (TC_BK / 2), b);
+      }
+      tma_load_2d(sa + MT * DF_A_BYTES, &tmB, &full[s], kb * TC_BK, n0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((INV ? 1u : 0u) << 15) | ((uint32_t)(DF_BN >> 3) << 17) |
+                           ((uint32_t)(128 >> 4) << 24);
+    for (int kb = 0; kb < p.nkb; ++kb) {
+      const int s = kb % NS;
+      mbar_wait_bounded(&full[s], (uint32_t)((kb / NS) & 1));
+      tc_fence_after();
+      const uint32_t sa = base + (uint32_t)s * STAGE;
+      const uint32_t sb = sa + MT * DF_A_BYTES;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint64_t adesc = INV ? make_smem_desc(sa + mt * DF_A_BYTES + 1024 * k, TC_BK * 128, 512, 1)
+                                     : make_smem_desc(sa + mt * DF_A_BYTES + 32 * k, 16, 1024);
+          tc_mma_tf32(tmem_base + mt * DF_BN, adesc, make_smem_desc(sb + 32 * k, 16, 1024), idesc, (kb | k) ? 1u : 0u);
+        }
+      tc_commit(&empty[s]);
+    }
+    tc_commit(tmem_full);
+  }
+  __syncwarp();
+
+  // ---------------- epilogue: all 8 warps; lane quarter q, column half ----------------
+  const int q = warp & 3, chalf = warp >> 2;
+  mbar_wait_bounded(tmem_full, 0);
+  tc_fence_after();
+  if (!INV) {
+    const float sc = p.sc ? p.sc[bc] : 1.0f;
+    const float dcv = p.sh ? p.dc * p.sh[bc] : 0.0f;
+    const int twoC = 2 * p.C;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int lat = lat0 + mt * 128 + q * 32 + lane;
+      const bool in_rows = lat < p.nlat, in_pad = lat < p.kpad;
+#pragma unroll 1
+      for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+        if (c0 >= 2 * p.mlim) break;
+        uint32_t r[32];
+        MSFNO_DFT_LD32(r, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * DF_BN + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (in_pad) {
+          float* o = p.out + (((size_t)b * p.mlim + (c0 >> 1)) * twoC + 2 * c) * p.kpad + lat;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (c0 + j < 2 * p.mlim) {
+              float v = __uint_as_float(r[j]) * sc;
+              if (c0 + j == 0) v += dcv;
+              if (p.flags & 1) v = round_to_tf32(v);
+              if (!in_rows) v = 0.0f;
+              // column n = 2m + ri of plane c -> row (m * 2C + 2c + ri) of the [mlim * 2C][kpad] matrix
+              o[((size_t)(j >> 1) * twoC + (j & 1)) * p.kpad] = v;
+            }
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    float* stage_t = reinterpret_cast<float*>(tiles);   // [128][DF_TPITCH]: the pipeline stages are idle now
+    float lsum = 0.0f, lsq = 0.0f;
+    const size_t plane = (size_t)bc * p.nlat;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      if (mt) __syncthreads();
+      // TMEM -> staging tile (lane = row: pitch 257 words keeps the 32 rows of a warp on distinct banks)
+#pragma unroll 1
+      for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+        uint32_t r[32];
+        MSFNO_DFT_LD32(r, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * DF_BN + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        float* trow = stage_t + (size_t)(q * 32 + lane) * DF_TPITCH + c0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) trow[j] = __uint_as_float(r[j]);
+      }
+      __syncthreads();
+      // staging tile -> global: a warp walks rows; a lane owns float4 groups (512 contiguous bytes per warp access).
+      // All global loads of a row (skip) are issued before any arithmetic: their latency overlaps instead of adding up.
+      const int ncol = min(DF_BN, p.nlon - n0);           // multiple of 4 (nlon % 4 == 0)
+      const bool has_skip = p.skip != nullptr;
+      for (int row = warp; row < 128; row += 8) {
+        const int lat = lat0 + mt * 128 + row;
+        if (lat >= p.nlat) break;
+        const size_t goff = (plane + lat) * p.nlon + n0;
+        const float* trow = stage_t + (size_t)row * DF_TPITCH;
+        float4 sk[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int col = 4 * (lane + 32 * i);
+          sk[i] = (has_skip && col < ncol) ? __ldg(reinterpret_cast<const float4*>(p.skip + goff + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int col = 4 * (lane + 32 * i);
+          if (col < ncol) {
+            float v[4] = {trow[col] + sk[i].x, trow[col + 1] + sk[i].y, trow[col + 2] + sk[i].z, trow[col + 3] + sk[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (p.flags & 1) v[e] = gelu_tanh3(v[e]);
+              if (p.flags & 2) v[e] = round_to_tf32(v[e]);
+              lsum += v[e];
+              lsq = fmaf(v[e], v[e], lsq);
+            }
+            *reinterpret_cast<float4*>(p.out + goff + col) = make_float4(v[0], v[1], v[2], v[3]);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    if (p.stats) {
+      double ds = (double)lsum, dq = (double)lsq;
+      for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+      }
+      if (lane == 0) { red[2 * warp] = ds; red[2 * warp + 1] = dq; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0.0, sq = 0.0;
+        for (int w = 0; w < 8; ++w) { s += red[2 * w]; sq += red[2 * w + 1]; }
+        atomicAdd(&p.stats[2 * bc], s);
+        atomicAdd(&p.stats[2 * bc + 1], sq);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(MT * DF_BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+static float host_round_tf32(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xffffe000u;
+  memcpy(&x, &u, 4);
+  return x;
+}
+
+bool dft_tc_supported(const msfno_plan* p) {
+  static const bool off = getenv("MSFNO_DFT_FFT") != nullptr;
+  return !off && p->nlon % 4 == 0 && 2 * p->mlim <= DF_BN && (2 * p->mlim) % 4 == 0 && p->mlim <= p->nlon / 2 && get_encode() != nullptr;
+}
+
+// F [2 mlim][nlon]: (2 pi / nlon) (cos, -sin)(2 pi m j / nlon);  G [nlon][2 mlim]: c_m (cos, -sin), c_0 = 1 (and the
+// Nyquist order), 2 otherwise; the imaginary parts of the DC and Nyquist bins do not contribute (irfft semantics)
+int dft_tc_build(msfno_plan* p) {
+  if (p->d_dft_fwd) return MSFNO_OK;
+  const int nlon = p->nlon, N = 2 * p->mlim;
+  std::vector<float> F((size_t)N * nlon), G((size_t)nlon * N);
+  for (int m = 0; m < p->mlim; ++m) {
+    const double cm = (m == 0 || 2 * m == nlon) ? 1.0 : 2.0;
+    const bool real_only = (m == 0 || 2 * m == nlon);
+    for (int j = 0; j < nlon; ++j) {
+      const double a = 2.0 * M_PI * (double)(((long long)m * j) % nlon) / nlon;
+      F[(size_t)(2 * m) * nlon + j] = host_round_tf32((float)(2.0 * M_PI / nlon * cos(a)));
+      F[(size_t)(2 * m + 1) * nlon + j] = host_round_tf32((float)(-2.0 * M_PI / nlon * sin(a)));
+      G[(size_t)j * N + 2 * m] = host_round_tf32((float)(cm * cos(a)));
+      G[(size_t)j * N + 2 * m + 1] = real_only ? 0.0f : host_round_tf32((float)(-cm * sin(a)));
+    }
+  }
+  MSFNO_CUDA_OK(cudaMalloc(&p->d_dft_fwd, F.size() * sizeof(float)));
+  MSFNO_CUDA_OK(cudaMalloc(&p->d_dft_inv, G.size() * sizeof(float)));
+  MSFNO_CUDA_OK(cudaMemcpy(p->d_dft_fwd, F.data(), F.size() * sizeof(float), cudaMemcpyHostToDevice));
+  MSFNO_CUDA_OK(cudaMemcpy(p->d_dft_inv, G.data(), G.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return MSFNO_OK;
+}
+
+static int make_map_5d(CUtensorMap* tm, const float* base, const cuuint64_t dims[5], const cuuint64_t strides_bytes[4],
+                       const cuuint32_t box[5]) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides_bytes, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled failed (dft 5-D map)");
+  return MSFNO_OK;
+}
+
+template <bool INV, int MT, int NS>
+static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const DftParams& prm, dim3 grid, cudaStream_t st) {
+  constexpr int smem = NS * (MT * DF_A_BYTES + DF_B_BYTES) + 1024 + 512;
+  static_assert(!INV || NS * (MT * DF_A_BYTES + DF_B_BYTES) >= 128 * DF_TPITCH * 4, "staging tile does not fit in the pipeline stages");
+  auto kern = dft_tc_kernel<INV, MT, NS>;
+  MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  kern<<<grid, 256, smem, st>>>(tmA, tmB, prm);
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+int launch_dft_fwd(msfno_plan* p, const float* x, float* Xt, const float* in_scale, const float* in_shift, int B, int C,
+                   cudaStream_t st) {
+  int rc = dft_tc_build(p);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  rc = make_map(&tmA, x, (long long)B * C * p->nlat, p->nlon, p->nlon, 128);
+  if (rc) return rc;
+  rc = make_map(&tmB, p->d_dft_fwd, 2 * p->mlim, p->nlon, p->nlon, DF_BN);
+  if (rc) return rc;
+  DftParams prm{};
+  prm.out = Xt; prm.sc = in_scale; prm.sh = in_shift;
+  prm.nlat = p->nlat; prm.nlon = p->nlon; prm.mlim = p->mlim; prm.kpad = p->kpad; prm.C = C;
+  prm.nkb = (p->nlon + TC_BK - 1) / TC_BK;
+  prm.flags = 1;
+  prm.dc = (float)(2.0 * M_PI);
+  if (p->kpad > 128) return launch_dft<false, 2, 3>(tmA, tmB, prm, dim3(1, (p->kpad + 255) / 256, B * C), st);
+  return launch_dft<false, 1, 2>(tmA, tmB, prm, dim3(1, 1, B * C), st);
+}
+
+int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, int act_flags, double* stats, int B, int C,
+                   cudaStream_t st) {
+  int rc = dft_tc_build(p);
+  if (rc) return rc;
+  CUtensorMap tmA, tmB;
+  const cuuint64_t kp = (cuuint64_t)p->kpad;
+  const cuuint64_t dims[5] = {kp, 2, (cuuint64_t)C, (cuuint64_t)p->mlim, (cuuint64_t)B};
+  const cuuint64_t strides[4] = {kp * 4, 2 * kp * 4, (cuuint64_t)2 * C * kp * 4, (cuuint64_t)p->mlim * 2 * C * kp * 4};
+  const cuuint32_t box[5] = {32, 2, 1, TC_BK / 2, 1};
+  rc = make_map_5d(&tmA, Yt, dims, strides, box);
+  if (rc) return rc;
+  rc = make_map(&tmB, p->d_dft_inv, p->nlon, 2 * p->mlim, 2 * p->mlim, DF_BN);
+  if (rc) return rc;
+  DftParams prm{};
+  prm.out = y; prm.skip = skip; prm.stats = stats;
+  prm.nlat = p->nlat; prm.nlon = p->nlon; prm.mlim = p->mlim; prm.kpad = p->kpad; prm.C = C;
+  prm.nkb = (2 * p->mlim + TC_BK - 1) / TC_BK;
+  prm.flags = act_flags;
+  const int tilesN = (p->nlon + DF_BN - 1) / DF_BN;
+  if (p->nlat > 128) return launch_dft<true, 2, 3>(tmA, tmB, prm, dim3(tilesN, (p->nlat + 255) / 256, B * C), st);
+  return launch_dft<true, 1, 3>(tmA, tmB, prm, dim3(tilesN, 1, B * C), st);
+}
+
+}  // namespace msfno

@@ -45,6 +45,8 @@ struct msfno_plan {
   float* d_tab_lk = nullptr;          // analysis table  [mlim][Lj][kpad]   (contract over lat)
   float* d_tab_kl = nullptr;          // synthesis table [mlim][nlat][Lj]   (contract over degree)
   int32_t* d_flag = nullptr;          // table validation flag
+  float* d_dft_fwd = nullptr;         // tensor-core tier: DFT matrix  [2 mlim][nlon]  (dft_tc.cu, built on first use)
+  float* d_dft_inv = nullptr;         //                   inverse DFT [nlon][2 mlim]
   // grouped-GEMM descriptors cached per (kind, B, C)
   std::mutex mu;
   std::map<std::vector<int>, msfno::GemmGroup*> groups;  // key: kind, B, C, m_lo, m_hi
@@ -102,6 +104,12 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
 
 // four-step in-register FFT kernels (fft2d.cu) for nlon in {240, 1440, 2880}
 bool fft2d_supported(int nlon);
+// tensor-core tier longitude transforms (dft_tc.cu)
+bool dft_tc_supported(const msfno_plan* p);
+int launch_dft_fwd(msfno_plan* p, const float* x, float* Xt, const float* in_scale, const float* in_shift, int B, int C,
+                   cudaStream_t st);
+int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, int act_flags, double* stats, int B, int C,
+                   cudaStream_t st);
 int launch_rfft2d(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
                   const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st);
 int launch_irfft2d(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,

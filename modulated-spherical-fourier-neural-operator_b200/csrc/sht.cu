@@ -11,7 +11,7 @@ using namespace msfno;
 
 static int legendre_gemm(msfno_plan* p, int kind, const float* A, long long lda, int a_k, const float* B, long long ldb,
                          int b_k, float* D, long long ldd, int maxM, int maxN, int Bsz, int C, cudaStream_t st,
-                         int m_lo = 0, int m_hi = -1) {
+                         int m_lo = 0, int m_hi = -1, int round_out = 0) {
   const GemmGroup* groups = nullptr;
   int ng = 0;
   int rc = plan_groups(p, kind, Bsz, C, &groups, &ng, m_lo, m_hi);
@@ -26,7 +26,7 @@ static int legendre_gemm(msfno_plan* p, int kind, const float* A, long long lda,
     const int mloc = (m_hi < 0 ? p->mlim : m_hi) - m_lo;
     if (kind == GK_ANALYSIS)
       return launch_gemm_tc(g, (long long)p->mlim * p->Lj, p->kpad, (long long)Bsz * mloc * 2 * C, p->kpad, 0, st);
-    return launch_gemm_tc(g, (long long)Bsz * 2 * C, lda, (long long)p->mlim * p->nlat, p->Lj, 0, st);
+    return launch_gemm_tc(g, (long long)Bsz * 2 * C, lda, (long long)p->mlim * p->nlat, p->Lj, round_out, st);
   }
   return launch_gemm_ffma(g, st);
 }
@@ -43,7 +43,10 @@ int msfno_sht_fwd(msfno_plan* p, const float* x, const float* in_scale, const fl
   if (!p || !x || !coef_pm || !ws || B < 1 || C < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "sht_fwd: bad argument");
   if (!p->d_tab_lk) return record_error(MSFNO_ERR_BAD_STATE, "sht_fwd: analysis table (RealSHT.weights) not set");
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = launch_rfft_trunc(p, x, ws, p->d_scale_rfft, 0, in_scale, in_shift, B, C, st);
+  // longitude transform: DFT GEMM on the tensor cores in the TF32 tier (dft_tc.cu), FFT kernels otherwise
+  const bool dft_f = p->precision == MSFNO_PREC_TF32 && dft_tc_supported(p) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(ws)) & 15) == 0;
+  int rc = dft_f ? launch_dft_fwd(p, x, ws, in_scale, in_shift, B, C, st)
+                                                                      : launch_rfft_trunc(p, x, ws, p->d_scale_rfft, 0, in_scale, in_shift, B, C, st);
   if (rc) return rc;
   // coef_pm[b][poff[m]+j][ch] = sum_k tab_lk[m][j][k] * Xt[b][m][ch][k]
   return legendre_gemm(p, GK_ANALYSIS, p->d_tab_lk, p->kpad, 1, ws, p->kpad, 1, coef_pm, 2 * C, p->h_plen4[0], 2 * C, B, C, st);
@@ -65,9 +68,14 @@ int msfno_isht_fwd(msfno_plan* p, const float* coef_cm, float* y, float* ws, int
   if (!p->d_tab_kl) return record_error(MSFNO_ERR_BAD_STATE, "isht_fwd: synthesis table (InverseRealSHT.pct) not set");
   cudaStream_t st = (cudaStream_t)stream;
   // Yt[b][m][ch][k] = sum_j coef_cm[b][ch][poff[m]+j] * tab_kl[m][k][j]
-  int rc = legendre_gemm(p, GK_SYNTHESIS, coef_cm, p->P, 1, p->d_tab_kl, p->Lj, 1, ws, p->kpad, 2 * C, p->nlat, B, C, st);
+  const bool dft = p->precision == MSFNO_PREC_TF32 && dft_tc_supported(p) &&
+                   ((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(ws) | reinterpret_cast<uintptr_t>(skip_add)) & 15) == 0;
+  // (the DFT GEMM reads Yt as a tensor-core operand: round it to TF32 where it is produced)
+  int rc = legendre_gemm(p, GK_SYNTHESIS, coef_cm, p->P, 1, p->d_tab_kl, p->Lj, 1, ws, p->kpad, 2 * C, p->nlat, B, C, st, 0, -1,
+                         dft ? 1 : 0);
   if (rc) return rc;
   if (stats) MSFNO_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)B * C, st));
+  if (dft) return launch_dft_inv(p, ws, y, skip_add, act_gelu, stats, B, C, st);
   return launch_irfft_trunc(p, ws, y, p->d_scale_irfft, skip_add, nullptr, act_gelu, stats, B, C, st);
 }
 

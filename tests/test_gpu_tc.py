@@ -198,3 +198,43 @@ def test_mlp1x1_fused_tf32(B, cin, cin2, chid, cout, H, W, with_add, per_sample)
         assert err < TOL_TF32, err
     finally:
         msfno_b200.set_precision("fp32")
+
+
+@pytest.mark.parametrize("nlat,nlon,grid,B,C", [(120, 240, "legendre-gauss", 2, 8), (721, 1440, "equiangular", 1, 3)])
+def test_sht_isht_tf32_dft_gemm(nlat, nlon, grid, B, C):
+    """TF32 tier: longitude transforms as DFT GEMMs on the tensor cores (dft_tc.cu) + Legendre GEMMs, against the
+    oracle's rfft/irfft + einsum (th_shim, torch_harmonics semantics), including the fused affine / skip / GELU / stats."""
+    from msfno_b200 import _lib
+    from msfno_b200.sht import relayout
+    L, M = 120, 121
+    o_s = th_shim.RealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid).float()
+    o_i = th_shim.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid).float()
+    s = msfno_b200.RealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid).float().cuda()
+    i = msfno_b200.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid).float().cuda()
+    g = torch.Generator().manual_seed(nlat + C)
+    x = torch.randn(B, C, nlat, nlon, generator=g)
+    sc, sh = torch.rand(B, C, generator=g) + 0.5, torch.randn(B, C, generator=g)
+    msfno_b200.set_precision("tf32")
+    try:
+        with torch.no_grad():
+            pm = s.forward_packed(x.cuda(), sc.cuda(), sh.cuda())
+            got = torch.view_as_complex(relayout(pm, s, _lib.LAYOUT_PM, _lib.LAYOUT_STD, B, C))
+            want = o_s(x.double() * sc.double()[..., None, None] + sh.double()[..., None, None])
+            assert rel_l2(torch.view_as_real(got), torch.view_as_real(want)) < TOL_TF32
+            # inverse with the fused epilogue
+            coef = o_s(x.double()).to(torch.complex64)
+            skip = torch.randn(B, C, nlat, nlon, generator=g)
+            cm = relayout(torch.view_as_real(coef).contiguous().cuda(), i, _lib.LAYOUT_STD, _lib.LAYOUT_CM, B, C)
+            stats = torch.zeros(B * C, 2, dtype=torch.float64, device="cuda")
+            y = i.inverse_packed(cm, skip_add=skip.cuda(), act_gelu=True, stats=stats)
+            ref = torch.nn.functional.gelu(o_i(coef.to(torch.complex128)) + skip.double())
+            assert torch.isfinite(y).all()
+            assert rel_l2(y, ref) < TOL_TF32
+            yd = y.double().reshape(B * C, -1)
+            assert torch.allclose(stats[:, 0], yd.sum(1), rtol=1e-6, atol=1e-3)
+            assert torch.allclose(stats[:, 1], (yd * yd).sum(1), rtol=1e-6)
+            # plain inverse (no epilogue)
+            y0 = i.inverse_packed(cm)
+            assert rel_l2(y0, o_i(coef.to(torch.complex128))) < TOL_TF32
+    finally:
+        msfno_b200.set_precision("fp32")
