@@ -185,6 +185,10 @@ int msfno_plane_stats(const float* x, double* stats, int planes, long HW, void* 
 int msfno_norm_film_coeffs(const double* stats, const float* nw, const float* nb, const float* gamma,
                            const float* beta, float scale, float eps, float* A, float* S, int B, int C,
                            long HW, void* stream);
+/* Fold the per-plane affine into the 1x1 conv that consumes it: Wb[b][o][c] = W[o][c] A[b][c] (TF32-rounded when
+ * round_tf32), bb[b][o] = sum_c W[o][c] S[b][c] + bias[o] (bias may be NULL).  W: [O][ld] zero-padded rows. */
+int msfno_fold_affine(const float* W, const float* A, const float* S, const float* bias, float* Wb, float* bb,
+                      int B, int O, int C, int ld, int round_tf32, void* stream);
 /* y[plane][:] = A[plane]*x[plane][:] + S[plane] */
 int msfno_plane_affine(const float* x, const float* A, const float* S, float* y, int planes, long HW,
                        void* stream);

@@ -51,7 +51,7 @@ def padded_weight(weight, cols=None):
 
 
 def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, cin2=0, per_sample_w=False,
-            per_sample_bias=False, final=False):
+            per_sample_bias=False, final=False, w_rounded=False):
     """y = act(conv1x1(x, w) [+ conv1x1(x2, w2)] + bias) + add   for contiguous NCHW fp32 CUDA tensors.
     w: [Cout, ld] (or [B, Cout, ld] with per_sample_w) zero-padded rows; bias [Cout] (or [B, Cout]);
     add: [B or 1, Cout, H, W]."""
@@ -62,7 +62,7 @@ def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, ci
     prec = _lib.PREC_FP32
     if _precision.get_precision() == "tf32":
         prec = _lib.PREC_TF32 | (0 if final else 2)   # bit 1: TF32-round the output (it feeds another tensor-core GEMM)
-        if per_sample_w:
+        if per_sample_w and not w_rounded:
             w = round_tf32(w)
     add_bs = 0
     if add is not None:
@@ -83,14 +83,14 @@ def mlp1x1_supported(chid, cout, HW):
 
 
 def mlp1x1(x, w1, cin, b1, w2, b2=None, add=None, x2=None, w1b=None, cin2=0, per_sample_w1=False, per_sample_b1=False,
-           final=False):
+           final=False, w1_rounded=False):
     """y = conv1x1(gelu(conv1x1(x, w1) [+ conv1x1(x2, w1b)] + b1), w2) + b2 + add in ONE kernel; the hidden activation
     never reaches HBM.  w1: [Chid, ld] (or [B, Chid, ld]), w1b: [Chid, ld2], w2: [Cout, ld3] zero-padded rows."""
     B, _, H, W = x.shape
     HW = H * W
     chid, cout = w1.shape[-2], w2.shape[-2]
     y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
-    if per_sample_w1:
+    if per_sample_w1 and not w1_rounded:
         w1 = round_tf32(w1)
     add_bs = 0
     if add is not None:

@@ -89,6 +89,18 @@ def norm_film_coeffs(stats, norm, B, C, HW, gamma=None, beta=None, scale=1.0):
     return A, S
 
 
+def fold_affine(W, A, S, bias):
+    """(Wb, bb) with conv1x1(A*y + S, W) + bias == conv1x1(y, Wb) + bb per sample: the pending per-plane affine is
+    folded into the consuming 1x1 conv's weights (msfno_fold_affine; TF32-rounded in the tensor-core tier)."""
+    B, C = A.shape
+    O, ld = W.shape
+    Wb = torch.empty((B, O, ld), dtype=torch.float32, device=W.device)
+    bb = torch.empty((B, O), dtype=torch.float32, device=W.device)
+    check(lib.msfno_fold_affine(ptr(W), ptr(A), ptr(S), ptr(bias), ptr(Wb), ptr(bb), B, O, C, ld,
+                                1 if _precision.get_precision() == "tf32" else 0, _stream()), "fold_affine")
+    return Wb, bb
+
+
 def plane_affine(x, A, S):
     y = torch.empty_like(x)
     check(lib.msfno_plane_affine(ptr(x), ptr(A), ptr(S), ptr(y), x.shape[0] * x.shape[1], x[0, 0].numel(), _stream()),
@@ -227,18 +239,14 @@ class FourierNeuralOperatorBlock(nn.Module):
         if (mlp is not None and len(mlp.fwd) == 3 and isinstance(mlp.fwd[0], nn.Conv2d) and isinstance(mlp.fwd[1], nn.GELU)
                 and getattr(mlp.fwd[1], "approximate", "none") == "none" and isinstance(mlp.fwd[2], nn.Conv2d)):
             fc1, fc2 = mlp.fwd[0], mlp.fwd[2]
-            W1 = padded_weight(fc1.weight)                                  # [hid, C]
-            Wb = (W1.unsqueeze(0) * A1.unsqueeze(1)).contiguous()           # norm1 o FiLM folded into fc1
-            bias_b = torch.matmul(S1, W1[:, :C].t())
-            if fc1.bias is not None:
-                bias_b = bias_b + fc1.bias
+            Wb, bias_b = fold_affine(padded_weight(fc1.weight), A1, S1, fc1.bias)   # norm1 o FiLM folded into fc1
             fuse_res = no_drop and not self.concat_skip and isinstance(getattr(self, "outer_skip", None), nn.Identity)
             if mlp1x1_supported(fc1.out_channels, fc2.out_channels, y.shape[2] * y.shape[3]):
                 # fc1 -> GELU -> fc2 (+ residual) in one kernel; the 512-channel hidden tile never leaves tensor memory
                 out = mlp1x1(y, Wb, C, bias_b.contiguous(), padded_weight(fc2.weight), fc2.bias,
-                             add=residual.contiguous().float() if fuse_res else None, per_sample_w1=True, per_sample_b1=True)
+                             add=residual.contiguous().float() if fuse_res else None, per_sample_w1=True, per_sample_b1=True, w1_rounded=True)
                 return out if fuse_res else self._tail(out, residual)
-            h = conv1x1(y, Wb, C, bias=bias_b.contiguous(), act_gelu=True, per_sample_w=True, per_sample_bias=True)
+            h = conv1x1(y, Wb, C, bias=bias_b.contiguous(), act_gelu=True, per_sample_w=True, per_sample_bias=True, w_rounded=True)
             out = conv1x1(h, padded_weight(fc2.weight), fc2.in_channels, bias=fc2.bias,
                           add=residual.contiguous().float() if fuse_res else None)
             return out if fuse_res else self._tail(out, residual)
@@ -464,16 +472,13 @@ class FourierNeuralOperatorNet(nn.Module):
         E = self.embed_dim_sfno
         W1 = padded_weight(dec[0].weight, cols=(0, E))
         W2 = padded_weight(dec[0].weight, cols=(E, dec[0].in_channels))
-        Wb = (W1.unsqueeze(0) * torch.nn.functional.pad(A, (0, W1.shape[1] - E)).unsqueeze(1)).contiguous()
-        bias_b = torch.matmul(S, W1[:, :E].t())
-        if dec[0].bias is not None:
-            bias_b = bias_b + dec[0].bias
+        Wb, bias_b = fold_affine(W1, A, S, dec[0].bias)
         if mlp1x1_supported(dec[0].out_channels, dec[2].out_channels, y.shape[2] * y.shape[3]):
             return mlp1x1(y, Wb, E, bias_b.contiguous(), padded_weight(dec[2].weight), dec[2].bias,
                           x2=residual.contiguous().float(), w1b=W2, cin2=self.in_chans, per_sample_w1=True,
-                          per_sample_b1=True, final=True)
+                          per_sample_b1=True, final=True, w1_rounded=True)
         h = conv1x1(y, Wb, E, bias=bias_b.contiguous(), act_gelu=True, x2=residual.contiguous().float(), w2=W2,
-                    cin2=self.in_chans, per_sample_w=True, per_sample_bias=True)
+                    cin2=self.in_chans, per_sample_w=True, per_sample_bias=True, w_rounded=True)
         return conv1x1(h, padded_weight(dec[2].weight), dec[2].in_channels, bias=dec[2].bias, final=True)
 
     def _forward_fused(self, x, film=None):
