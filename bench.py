@@ -245,6 +245,24 @@ def dominant_kernel_roofline(args, net, dev, pk):
         flops = 2.0 * NPOS * 1024 * 1024  # algorithmic: only the 7260 modes with l >= m
         ach = flops / (ms * 1e-3) / 1e12
         peak = pk["bf16_sustained"] / 2.0
+        stages["spectral_mlp_hidden_gemm"] = {
+            "kernel": "gemm_tc2_kernel (CTA pair, cta_group::2): [7440 x 1024] x [1024 x 1024], 36 launches per step", "ms": ms,
+            "bound": "tensor", "achieved_TFLOPs": ach, "peak_TFLOPs": peak, "frac_of_tf32_peak": ach / peak,
+            "peak_source": "%s bf16_tflops_sustained / 2 (TF32 = half of BF16, BASELINE.md section 2)" % pk["src"]}
+        del A, W, D
+        if args.precision == "tf32" and hasattr(net, "_encode_fused"):
+            # dominant kernel by share of the step (profiles/r01_launches_bench_tf32_v7.csv: mlp_tc_kernel 31 %): its largest
+            # launch, the fused encoder MLP  y = W2 gelu(W1 x + b1) + b2 + pos_embed  at 721x1440
+            xin = torch.randn(1, net.in_chans, *IMG, device=dev)
+            with torch.no_grad():
+                ms = timed(lambda: net._encode_fused(xin))
+            by = 4.0 * IMG[0] * IMG[1] * (net.in_chans + 2 * EMBED)   # input + pos_embed read, output written, once each
+            ach = by / (ms * 1e-3) / 1e9
+            return {"kernel": "mlp_tc_kernel (fused encoder MLP 73->256->256 + pos_embed, hidden tile in TMEM; 1 of 13 launches per step)",
+                    "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": 2.388e9,
+                    "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this launch, "
+                                      "profiles/r01_ncu_mlp_tc_v2_raw.csv",
+                    "peak_source": "%s hbm_gbs" % pk["src"], "ms_per_launch": ms, "algorithmic_bytes": by, "stages": stages}
         return {"kernel": "gemm (spectral complex-MLP hidden layer, M=7260 modes, N=K=1024 real)", "bound": "tensor",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 35.5e6,
                 "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this launch (operands are L2 resident), "
