@@ -30,7 +30,7 @@ static constexpr int ML_XBLK = ML_BM * TC_BK * 4;       // activation k-block: 3
 static constexpr int ML_WBLK = 256 * TC_BK * 4;         // weight k-block slot: up to 256 rows x 32 k = 32 KB
 static constexpr int ML_NSX = 3, ML_NSW = 5;
 static constexpr int ML_MAX_HID = 1024;
-static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + (ML_MAX_HID + 256) * 4 + 256;
+static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + (ML_MAX_HID + 256 + 512) * 4 + 256;
 
 struct MlpTcParams {
   float* D;
@@ -42,6 +42,7 @@ struct MlpTcParams {
   int HW, K1a, K1b, Chid, Cout, N2pad;
   int tiles;
   int round_tf32;
+  double* stats;   // [B][Cout][2] plane (sum, sum of squares) of y, accumulated with atomics, or null
 };
 
 // D[tmem] (+)= A[tmem] * B[smem desc]
@@ -54,6 +55,35 @@ __device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a,
       "}\n" ::"r"(tmem_d),
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+
+// Sums over the 32 lanes (pixels) of 16 per-lane values (channels) and of their squares, added to acc[ch] / acc[256 + ch]
+// in shared memory.  Halving butterfly: at each step a lane keeps half of its values and receives the partner's copy of
+// the same half, so 16 values need 16 shuffles per quantity instead of 80.  Afterwards lane pair (2k, 2k+1) holds channel
+// bitrev-free index ch = lane >> 1.
+__device__ __forceinline__ void warp_channel_sums(const float (&v)[16], float* acc, int nv, int lane) {
+  float s[16], q[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { s[j] = v[j]; q[j] = v[j] * v[j]; }
+#pragma unroll
+  for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int j = 0; j < half; ++j) {
+      const float send_s = up ? s[j] : s[j + half], send_q = up ? q[j] : q[j + half];
+      const float keep_s = up ? s[j + half] : s[j], keep_q = up ? q[j + half] : q[j];
+      s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, bit);
+      q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, bit);
+    }
+  }
+  s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+  q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+  // lane bits (4,3,2,1) selected the upper half at steps (8,4,2,1): channel = 8 b4 + 4 b3 + 2 b2 + b1 = lane >> 1
+  const int ch = lane >> 1;
+  if ((lane & 1) == 0 && ch < nv) {
+    atomicAdd(acc + ch, s[0]);
+    atomicAdd(acc + 256 + ch, q[0]);
+  }
 }
 
 #define MSFNO_TMEM_LD32(r, taddr)                                                                                        \
@@ -96,7 +126,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint8_t* wring = tiles + ML_NSX * ML_XBLK;
   float* b1_s = reinterpret_cast<float*>(wring + ML_NSW * ML_WBLK);   // [ML_MAX_HID]
   float* b2_s = b1_s + ML_MAX_HID;                                    // [256]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b2_s + 256);
+  float* stat_s = b2_s + 256;                                         // [2][256] per-CTA plane sums of the output
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 512);
   uint64_t* xfull = bars;            // [NSX]
   uint64_t* xempty = bars + 4;       // [NSX]
   uint64_t* wfull = bars + 8;        // [NSW]
@@ -120,6 +151,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int c = (int)threadIdx.x - 64;
     for (int h = c; h < ML_MAX_HID; h += 256) b1_s[h] = (p.b1 && h < p.Chid) ? p.b1[(long long)b * p.sb1 + h] : 0.0f;
     b2_s[c] = (p.b2 && c < p.Cout) ? p.b2[c] : 0.0f;
+    stat_s[c] = 0.0f;
+    stat_s[256 + c] = 0.0f;
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
@@ -250,7 +283,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       tc_fence_after();
       auto store_chunk = [&](const uint32_t (&r)[32], const int c0) {
         const int nch = min(32, p.Cout - c0);
-        if (nch <= 0 || !pix_ok) return;
+        if (nch <= 0 || (!pix_ok && !p.stats)) return;   // with statistics every lane takes part in the warp reductions
         float* dptr = p.D + (long long)b * p.sd + (long long)c0 * p.ldd + pix;
         const float* aptr = p.add ? p.add + (long long)b * p.sadd + (long long)c0 * p.ldadd + pix : nullptr;
 #pragma unroll
@@ -263,7 +296,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             if (aptr) {
               float av[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) av[j] = (j < nv) ? __ldg(aptr + (long long)(jb + j) * p.ldadd) : 0.0f;
+              for (int j = 0; j < 16; ++j) av[j] = (j < nv && pix_ok) ? __ldg(aptr + (long long)(jb + j) * p.ldadd) : 0.0f;
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] += av[j];
             }
@@ -273,7 +306,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j)
-              if (j < nv) __stcs(dptr + (long long)(jb + j) * p.ldd, v[j]);
+              if (j < nv && pix_ok) __stcs(dptr + (long long)(jb + j) * p.ldd, v[j]);
+            if (!pix_ok) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+            }
+            if (p.stats) warp_channel_sums(v, stat_s + c0 + jb, nv, lane);
           }
         }
       };
@@ -296,6 +334,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
+  if (p.stats && threadIdx.x < 512) {
+    const int ch = threadIdx.x & 255, which = threadIdx.x >> 8;
+    if (ch < p.Cout) atomicAdd(&p.stats[2 * ((size_t)b * p.Cout + ch) + which], (double)stat_s[which * 256 + ch]);
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
@@ -314,7 +356,7 @@ using namespace msfno;
 extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const float* w1, long ldw1, long w1_bstride,
                                 const float* x2, long x2_bstride, int Cin2, const float* w1b, long ldw1b, const float* b1,
                                 long b1_bstride, int Chid, const float* w2, long ldw2, const float* b2, const float* add,
-                                long add_bstride, float* y, int B, int Cout, long HW, int flags, void* stream) {
+                                long add_bstride, float* y, double* stats, int B, int Cout, long HW, int flags, void* stream) {
   if (!x || !w1 || !w2 || !y || B < 1 || Cin < 1 || Chid < 1 || Cout < 1 || HW < 1 || ldw1 < Cin || ldw2 < Chid ||
       (x2 && (!w1b || Cin2 < 1 || ldw1b < Cin2)))
     return record_error(MSFNO_ERR_BAD_SHAPE, "mlp1x1_fwd: bad argument");
@@ -353,6 +395,8 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
   p.HW = (int)HW; p.K1a = Cin; p.K1b = x2 ? Cin2 : 0; p.Chid = Chid; p.Cout = Cout; p.N2pad = N2pad;
   p.tiles = (int)((HW + ML_BM - 1) / ML_BM);
   p.round_tf32 = (flags >> 1) & 1;
+  p.stats = stats;
+  if (stats) MSFNO_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)B * Cout, st));
   int dev = 0, sms = 0;
   MSFNO_CUDA_OK(cudaGetDevice(&dev));
   MSFNO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -213,15 +213,17 @@ class FourierNeuralOperatorBlock(nn.Module):
                 x = x + self.outer_skip(residual)
         return x
 
-    def _fused(self, x, gamma=None, beta=None, scale=1.0, defer_affine=False):
+    def _fused(self, x, gamma=None, beta=None, scale=1.0, defer_affine=False, in_stats=None, want_stats=False):
         """Inference path with the normalisations / skip / activation / FiLM folded into the transforms and the
         channel MLP run as two fused 1x1-conv GEMMs (msfno_conv1x1_fwd).  With defer_affine=True (a block without
         MLP, i.e. the last one) the un-normalised output and the pending per-plane affine (A, S) are returned so the
-        caller can fold them into the next 1x1 conv instead of spending a full-tensor pass."""
+        caller can fold them into the next 1x1 conv instead of spending a full-tensor pass.
+        in_stats: plane (sum, sum of squares) of x when the producer already accumulated them (fused MLP epilogue);
+        want_stats=True returns (out, stats of out or None) so the next block can skip its statistics pass."""
         residual = x
         x = x.contiguous().float()
         B, C = x.shape[0], x.shape[1]
-        A0, S0 = norm_film_coeffs(plane_stats(x), self.norm0, B, C, x[0, 0].numel())
+        A0, S0 = norm_film_coeffs(in_stats if in_stats is not None else plane_stats(x), self.norm0, B, C, x[0, 0].numel())
         skip = None
         if hasattr(self, "inner_skip"):
             if isinstance(self.inner_skip, nn.Conv2d):
@@ -243,17 +245,23 @@ class FourierNeuralOperatorBlock(nn.Module):
             fuse_res = no_drop and not self.concat_skip and isinstance(getattr(self, "outer_skip", None), nn.Identity)
             if mlp1x1_supported(fc1.out_channels, fc2.out_channels, y.shape[2] * y.shape[3]):
                 # fc1 -> GELU -> fc2 (+ residual) in one kernel; the 512-channel hidden tile never leaves tensor memory
+                ostats = (torch.empty((B * fc2.out_channels, 2), dtype=torch.float64, device=x.device)
+                          if (want_stats and fuse_res) else None)
                 out = mlp1x1(y, Wb, C, bias_b.contiguous(), padded_weight(fc2.weight), fc2.bias,
-                             add=residual.contiguous().float() if fuse_res else None, per_sample_w1=True, per_sample_b1=True, w1_rounded=True)
-                return out if fuse_res else self._tail(out, residual)
+                             add=residual.contiguous().float() if fuse_res else None, per_sample_w1=True, per_sample_b1=True,
+                             w1_rounded=True, stats=ostats)
+                out = out if fuse_res else self._tail(out, residual)
+                return (out, ostats) if want_stats else out
             h = conv1x1(y, Wb, C, bias=bias_b.contiguous(), act_gelu=True, per_sample_w=True, per_sample_bias=True, w_rounded=True)
             out = conv1x1(h, padded_weight(fc2.weight), fc2.in_channels, bias=fc2.bias,
                           add=residual.contiguous().float() if fuse_res else None)
-            return out if fuse_res else self._tail(out, residual)
+            out = out if fuse_res else self._tail(out, residual)
+            return (out, None) if want_stats else out
         y = plane_affine(y, A1, S1)
         if mlp is not None:
             y = mlp(y)
-        return self._tail(y, residual)
+        out = self._tail(y, residual)
+        return (out, None) if want_stats else out
 
     def _unfused(self, x, gamma=None, beta=None, scale=1.0, film=None):
         """Op-by-op path (autograd-capable), same order as sfnonet.py:221-251 / :359-393."""
@@ -460,10 +468,11 @@ class FourierNeuralOperatorNet(nn.Module):
         x = x.contiguous().float()
         if enc[0].bias is not None and mlp1x1_supported(enc[0].out_channels, enc[2].out_channels, x.shape[2] * x.shape[3]):
             # both layers and the pos_embed add in one kernel: the hidden activation stays in tensor memory
+            stats = torch.empty((x.shape[0] * enc[2].out_channels, 2), dtype=torch.float64, device=x.device)
             return mlp1x1(x, padded_weight(enc[0].weight), self.in_chans, enc[0].bias, padded_weight(enc[2].weight), enc[2].bias,
-                          add=self.pos_embed)
+                          add=self.pos_embed, stats=stats), stats
         h = conv1x1(x, padded_weight(enc[0].weight), self.in_chans, bias=enc[0].bias, act_gelu=True)
-        return conv1x1(h, padded_weight(enc[2].weight), enc[2].in_channels, bias=enc[2].bias, add=self.pos_embed)
+        return conv1x1(h, padded_weight(enc[2].weight), enc[2].in_channels, bias=enc[2].bias, add=self.pos_embed), None
 
     def _decode_fused(self, y, A, S, residual):
         """decoder(cat(A*y + S, residual)): the pending affine of the last block is folded into the first conv's
@@ -484,7 +493,7 @@ class FourierNeuralOperatorNet(nn.Module):
     def _forward_fused(self, x, film=None):
         """film: None or (gamma [B, film_layers, C], beta, scale, first_filmed_block_index)."""
         residual = x
-        x = self._encode_fused(x)
+        x, stats = self._encode_fused(x)     # stats: plane sums of x accumulated by the producing kernel (or None)
         last = len(self.blocks) - 1
         for i, blk in enumerate(self.blocks):
             g = b = None
@@ -492,9 +501,9 @@ class FourierNeuralOperatorNet(nn.Module):
             if film is not None and i >= film[3]:
                 g, b, sc = film[0][:, i - film[3]], film[1][:, i - film[3]], film[2]
             if i == last:
-                y, A, S = blk._fused(x, g, b, sc, defer_affine=True)
+                y, A, S = blk._fused(x, g, b, sc, defer_affine=True, in_stats=stats)
             else:
-                x = blk._fused(x, g, b, sc)
+                x, stats = blk._fused(x, g, b, sc, in_stats=stats, want_stats=True)
         return self._decode_fused(y, A, S, residual)
 
     def forward(self, x):

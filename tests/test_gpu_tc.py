@@ -189,9 +189,14 @@ def test_mlp1x1_fused_tf32(B, cin, cin2, chid, cout, H, W, with_add, per_sample)
         b2 = torch.randn(cout, generator=g).cuda()
         add = torch.randn(B if per_sample else 1, cout, H, W, generator=g).cuda() if with_add else None
         pad = lambda w: torch.nn.functional.pad(w, (0, (-w.shape[-1]) % 4)).contiguous()
+        stats = torch.full((B * cout, 2), float("nan"), dtype=torch.float64, device="cuda")
         y = mlp1x1(x, pad(w1), cin, b1.contiguous(), pad(w2), b2, add=add, x2=x2, w1b=pad(w1b) if cin2 else None, cin2=cin2,
-                   per_sample_w1=per_sample, per_sample_b1=per_sample, final=True)
+                   per_sample_w1=per_sample, per_sample_b1=per_sample, final=True, stats=stats)
         torch.cuda.synchronize()
+        # fused plane statistics of the output (what msfno_plane_stats(y) would return)
+        yd = y.double().reshape(B * cout, -1)
+        assert torch.allclose(stats[:, 0], yd.sum(1), rtol=1e-5, atol=1e-3 * yd.abs().sum(1).max().item() / yd.shape[1] ** 0.5)
+        assert torch.allclose(stats[:, 1], (yd * yd).sum(1), rtol=1e-5)
         want = _mlp_ref(x, w1, b1, w2, b2, add, x2, w1b)
         assert torch.isfinite(y).all()
         err = rel_l2(y, want)
