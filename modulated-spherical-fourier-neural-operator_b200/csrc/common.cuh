@@ -16,6 +16,26 @@ namespace msfno {
 int record_cuda_error(cudaError_t e, const char* file, int line);
 int record_error(int code, const char* msg);
 void count_launch(int n = 1);  // kernels of this library launched so far (msfno_launch_count)
+bool pdl_enabled();            // false when MSFNO_NO_PDL is set
+
+#if defined(__CUDACC__)
+// Launch `kern` allowing it to overlap the tail of the previous kernel in the stream (the kernel must call pdl_wait()
+// before it touches anything its predecessor wrote).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
 
 #if defined(__CUDACC__)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -48,6 +68,13 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start while
+// its predecessor in the stream is still running.  pdl_trigger() lets the NEXT kernel's CTAs be scheduled as soon as
+// every CTA of this kernel has started; pdl_wait() blocks until the PREVIOUS kernel has completed and its writes are
+// visible -- everything before it (barrier init, TMEM allocation, descriptor prefetch) overlaps the predecessor's tail.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 __device__ __forceinline__ float rna_tf32_dev(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(576, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, ConvTcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * CT_BM;
   const int b = blockIdx.z;
@@ -73,10 +74,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 16); }
     fence_mbar_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + CT_BM) {
-    const int ch = m0 + (int)threadIdx.x - 64;
-    bias_s[threadIdx.x - 64] = (p.bias && ch < p.M) ? p.bias[(long long)b * p.sbias + ch] : 0.0f;
-  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(2 * CT_BN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
@@ -85,6 +82,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + CT_BM) {
+    const int ch = m0 + (int)threadIdx.x - 64;
+    bias_s[threadIdx.x - 64] = (p.bias && ch < p.M) ? p.bias[(long long)b * p.sbias + ch] : 0.0f;
+  }
+  __syncthreads();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -283,7 +286,7 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   if (gx < 1) gx = 1;
   if (gx > p.tilesN) gx = p.tilesN;
   dim3 grid(gx, tilesM, g.ngroups);
-  conv_tc_kernel<<<grid, 576, smem, st>>>(tmA, tmB, tmA2, tmB2, p);
+  MSFNO_CUDA_OK(launch_pdl(conv_tc_kernel, grid, dim3(576), smem, st, tmA, tmB, tmA2, tmB2, p));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   *handled = 1;

@@ -73,6 +73,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int lat0 = blockIdx.y * (MT * 128);
   const int n0 = blockIdx.x * DF_BN;
 
+  pdl_trigger();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + NS * STAGE);
@@ -95,6 +96,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
@@ -306,7 +308,7 @@ static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const DftP
   static_assert(!INV || NS * (MT * DF_A_BYTES + DF_B_BYTES) >= 128 * DF_TPITCH * 4, "staging tile does not fit in the pipeline stages");
   auto kern = dft_tc_kernel<INV, MT, NS>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  kern<<<grid, 256, smem, st>>>(tmA, tmB, prm);
+  MSFNO_CUDA_OK(launch_pdl(kern, grid, dim3(256), smem, st, tmA, tmB, prm));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

@@ -103,6 +103,8 @@ __global__ void plane_stats_kernel(const float* __restrict__ x, double* __restri
 __global__ void fold_affine_kernel(const float* __restrict__ W, const float* __restrict__ A, const float* __restrict__ S,
                                    const float* __restrict__ bias, float* __restrict__ Wb, float* __restrict__ bb, int O, int C,
                                    int ld, int round_tf32) {
+  pdl_trigger();
+  pdl_wait();
   const int o = blockIdx.x, b = blockIdx.y;
   const float* w = W + (size_t)o * ld;
   float* wb = Wb + ((size_t)b * O + o) * ld;
@@ -132,6 +134,8 @@ __global__ void norm_film_coeffs_kernel(const double* __restrict__ stats, const 
                                         const float* __restrict__ nb, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, float scale, float eps, float* __restrict__ A,
                                         float* __restrict__ S, int B, int C, double inv_hw) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int c = i % C;
@@ -226,8 +230,8 @@ int msfno_norm_film_coeffs(const double* stats, const float* nw, const float* nb
                            float scale, float eps, float* A, float* S, int B, int C, long HW, void* stream) {
   if (!stats || !A || !S || B < 1 || C < 1 || HW < 1 || ((gamma == nullptr) != (beta == nullptr)))
     return record_error(MSFNO_ERR_BAD_SHAPE, "norm_film_coeffs: bad argument");
-  norm_film_coeffs_kernel<<<(B * C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(stats, nw, nb, gamma, beta, scale, eps, A, S,
-                                                                                B, C, 1.0 / (double)HW);
+  MSFNO_CUDA_OK(launch_pdl(norm_film_coeffs_kernel, dim3((B * C + 127) / 128), dim3(128), 0, (cudaStream_t)stream, stats, nw, nb, gamma,
+                           beta, scale, eps, A, S, B, C, 1.0 / (double)HW));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
@@ -236,7 +240,7 @@ int msfno_norm_film_coeffs(const double* stats, const float* nw, const float* nb
 int msfno_fold_affine(const float* W, const float* A, const float* S, const float* bias, float* Wb, float* bb, int B, int O, int C,
                       int ld, int round_tf32, void* stream) {
   if (!W || !A || !S || !Wb || !bb || B < 1 || O < 1 || C < 1 || ld < C) return record_error(MSFNO_ERR_BAD_SHAPE, "fold_affine: bad argument");
-  fold_affine_kernel<<<dim3(O, B), 128, 0, (cudaStream_t)stream>>>(W, A, S, bias, Wb, bb, O, C, ld, round_tf32);
+  MSFNO_CUDA_OK(launch_pdl(fold_affine_kernel, dim3(O, B), dim3(128), 0, (cudaStream_t)stream, W, A, S, bias, Wb, bb, O, C, ld, round_tf32));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

@@ -64,6 +64,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tn = blockIdx.x / p.tilesM, tm = blockIdx.x - tn * p.tilesM;
   const int m0 = tm * TC_BM, n0 = tn * TC_BN;
   if (m0 >= grp.M || n0 >= grp.N) return;  // uniform for the CTA, before any barrier / allocation
+  pdl_trigger();
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
@@ -93,6 +94,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // the prologue above overlapped the previous kernel; its outputs are visible from here on
 
   if (nkb > 0) {
     if (warp == 0 && lane == 0) {
@@ -295,6 +297,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int m0 = tm * 256 + (int)rank * TC_BM;                 // this CTA's 128 rows
   const int n0 = tn * TC2_BN;
   if (tm * 256 >= grp.M || n0 >= grp.N) return;                // uniform for the PAIR
+  pdl_trigger();
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
@@ -323,6 +326,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();   // both CTAs' barriers are initialised and both TMEM slices allocated before any signal crosses
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (nkb > 0) {
     if (warp == 0 && lane == 0) {
@@ -460,7 +464,7 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     p.tilesM = (g.maxM + 255) / 256;
     p.tilesN = (g.maxN + TC2_BN - 1) / TC2_BN;
     dim3 grid(2 * p.tilesM * p.tilesN, g.ngroups);
-    gemm_tc2_kernel<<<grid, 256, TC2_SMEM_BYTES, st>>>(tmA, tmB, p);
+    MSFNO_CUDA_OK(launch_pdl(gemm_tc2_kernel, grid, dim3(256), TC2_SMEM_BYTES, st, tmA, tmB, p));
     count_launch();
     MSFNO_CUDA_OK(cudaGetLastError());
     return MSFNO_OK;
@@ -497,8 +501,8 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;
   p.tilesM = tilesM;
   dim3 grid(tilesM * p.tilesN, g.ngroups);
-  if (bmn) gemm_tc_kernel<true><<<grid, 256, TC_SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, p);
-  else gemm_tc_kernel<false><<<grid, 256, TC_SMEM_BYTES, st>>>(tmA, tmB, tmA2, tmB2, p);
+  if (bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<true>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+  else MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<false>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

@@ -113,6 +113,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW1b,
               const __grid_constant__ CUtensorMap tmW2, MlpTcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.z;
   const int nkb1a = (p.K1a + TC_BK - 1) / TC_BK, nkb1b = (p.K1b + TC_BK - 1) / TC_BK, nkb1 = nkb1a + nkb1b;
@@ -147,13 +148,6 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     mbar_init(acc2_empty, 16);
     fence_mbar_init();
   }
-  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
-    const int c = (int)threadIdx.x - 64;
-    for (int h = c; h < ML_MAX_HID; h += 256) b1_s[h] = (p.b1 && h < p.Chid) ? p.b1[(long long)b * p.sb1 + h] : 0.0f;
-    b2_s[c] = (p.b2 && c < p.Cout) ? p.b2[c] : 0.0f;
-    stat_s[c] = 0.0f;
-    stat_s[256 + c] = 0.0f;
-  }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
@@ -162,6 +156,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the previous kernel's tail
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
+    const int c = (int)threadIdx.x - 64;
+    for (int h = c; h < ML_MAX_HID; h += 256) b1_s[h] = (p.b1 && h < p.Chid) ? p.b1[(long long)b * p.sb1 + h] : 0.0f;
+    b2_s[c] = (p.b2 && c < p.Cout) ? p.b2[c] : 0.0f;
+    stat_s[c] = 0.0f;
+    stat_s[256 + c] = 0.0f;
+  }
+  __syncthreads();
   const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + 256;
 
   if (warp == 0) {
@@ -403,7 +406,7 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
   int gx = sms / B;
   if (gx < 1) gx = 1;
   if (gx > p.tiles) gx = p.tiles;
-  mlp_tc_kernel<<<dim3(gx, 1, B), 576, ML_SMEM, st>>>(tmX, tmX2, tmW1, tmW1b, tmW2, p);
+  MSFNO_CUDA_OK(launch_pdl(mlp_tc_kernel, dim3(gx, 1, B), dim3(576), ML_SMEM, st, tmX, tmX2, tmW1, tmW1b, tmW2, p));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

@@ -11,12 +11,19 @@
 #include <string>
 
 #include "common.cuh"
+#include <cstdlib>
+
 #include "plan.h"
 
 namespace msfno {
 
 static thread_local std::string g_last_error;
 static std::atomic<unsigned long long> g_launches{0};
+bool pdl_enabled() {
+  static const bool on = getenv("MSFNO_NO_PDL") == nullptr;
+  return on;
+}
+
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int record_error(int code, const char* msg) {
