@@ -12,7 +12,10 @@
 //                                                                  (pixels on the TMEM lanes), weights the K-major B operand
 //   EPI1   acc1 <- tf32(gelu(acc1 + b1))  IN PLACE in TMEM (tcgen05.ld -> registers -> tcgen05.st)
 //   GEMM2  acc2[128 px][Cout] = acc1 * W2^T                     -- A operand read straight from TMEM
-//   EPI2   y = acc2 + b2 (+ add), coalesced 128-byte row stores (lane = pixel)
+//   ADD    acc2 += add tile * I32  -- the residual / pos-embed operand streams through the same TMA ring as the
+//          activations and is accumulated by 32 tiny N = 32 MMAs against a resident 32 x 32 identity block
+//          (plain loads of it from the epilogue cost 13 of 18 kclk per tile and nothing made them faster)
+//   EPI2   y = acc2 + b2, coalesced 128-byte row stores (lane = pixel)
 // A hidden layer wider than the 256 TMEM columns (the 512-channel block MLPs) is processed in chunks of 256: GEMM1 /
 // EPI1 per chunk, GEMM2 accumulating the chunk's K range into acc2 (the activation blocks are re-streamed per chunk).
 // Both weight matrices stream through a shared-memory ring of 32 KB k-blocks (L2 resident: 0.3-0.4 MB in total);
@@ -20,6 +23,8 @@
 //
 // Warp roles (576 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-17 = epilogues
 // (TMEM lane quarter w % 4 = 32-pixel block; column quarter (w - 2) / 4).
+#include <cstdlib>
+
 #include "plan.h"
 #include "tc_common.cuh"
 
@@ -30,7 +35,8 @@ static constexpr int ML_XBLK = ML_BM * TC_BK * 4;       // activation k-block: 3
 static constexpr int ML_WBLK = 256 * TC_BK * 4;         // weight k-block slot: up to 256 rows x 32 k = 32 KB
 static constexpr int ML_NSX = 3, ML_NSW = 5;
 static constexpr int ML_MAX_HID = 1024;
-static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + (ML_MAX_HID + 256 + 512) * 4 + 256;
+static constexpr int ML_IDBLK = 32 * TC_BK * 4;         // resident 32 x 32 identity (K-major, 128-byte swizzle) = 4 KB
+static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + ML_IDBLK + (ML_MAX_HID + 256 + 512) * 4 + 256;
 
 struct MlpTcParams {
   float* D;
@@ -42,6 +48,8 @@ struct MlpTcParams {
   int HW, K1a, K1b, Chid, Cout, N2pad;
   int tiles;
   int round_tf32;
+  int add_tma;      // 1: `add` is accumulated on the tensor cores (tmAdd / tmId), the epilogue does not read it
+  long long add_rows_per_sample;
   double* stats;   // [B][Cout][2] plane (sum, sum of squares) of y, accumulated with atomics, or null
 };
 
@@ -111,7 +119,8 @@ __device__ __forceinline__ void warp_channel_sums(const float (&v)[16], float* a
 __global__ void __launch_bounds__(576, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmX2,
               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW1b,
-              const __grid_constant__ CUtensorMap tmW2, MlpTcParams p) {
+              const __grid_constant__ CUtensorMap tmW2, const __grid_constant__ CUtensorMap tmAdd,
+              const __grid_constant__ CUtensorMap tmId, MlpTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -125,7 +134,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* xring = tiles;
   uint8_t* wring = tiles + ML_NSX * ML_XBLK;
-  float* b1_s = reinterpret_cast<float*>(wring + ML_NSW * ML_WBLK);   // [ML_MAX_HID]
+  uint8_t* idblk = wring + ML_NSW * ML_WBLK;                           // identity block (add path)
+  float* b1_s = reinterpret_cast<float*>(idblk + ML_IDBLK);           // [ML_MAX_HID]
   float* b2_s = b1_s + ML_MAX_HID;                                    // [256]
   float* stat_s = b2_s + 256;                                         // [2][256] per-CTA plane sums of the output
   uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 512);
@@ -137,7 +147,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint64_t* h_ready = bars + 25;     // EPI1 wrote the activated hidden tile back to TMEM (16 warps)
   uint64_t* acc2_full = bars + 26;   // GEMM2 complete
   uint64_t* acc2_empty = bars + 27;  // EPI2 finished reading acc2 (16 warps)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 28);
+  uint64_t* id_full = bars + 28;     // identity block landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < ML_NSX; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
@@ -146,6 +157,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     mbar_init(h_ready, 16);
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 16);
+    mbar_init(id_full, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -173,6 +185,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const int xrow = (int)(b * p.x_rows_per_sample), x2row = (int)(b * p.x2_rows_per_sample);
       const int w1row = (int)(b * p.w1_rows_per_sample);
       uint32_t xc = 0, wc = 0;
+      if (p.add_tma) {
+        mbar_arrive_expect_tx(id_full, ML_IDBLK);
+        tma_load_2d(idblk, &tmId, id_full, 0, 0);
+      }
+      const int nadd = p.add_tma ? (p.Cout + TC_BK - 1) / TC_BK : 0;
+      const int addrow = (int)(b * p.add_rows_per_sample);
       for (int t = blockIdx.x; t < p.tiles; t += gridDim.x) {
         const int n0 = t * ML_BM;
         for (int hh = 0; hh < nh; ++hh) {
@@ -201,6 +219,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             mbar_arrive_expect_tx(&wfull[s], w2_bytes);
             tma_load_2d(wring + (size_t)s * ML_WBLK, &tmW2, &wfull[s], hh * HC + kb * TC_BK, 0);
           }
+        }
+        for (int kb = 0; kb < nadd; ++kb, ++xc) {  // `add` tile: 32 channels x 128 pixels per block, through the activation ring
+          const int s = xc % ML_NSX;
+          mbar_wait_bounded(&xempty[s], ((xc / ML_NSX) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&xfull[s], ML_XBLK);
+          uint8_t* dst = xring + (size_t)s * ML_XBLK;
+#pragma unroll
+          for (int j = 0; j < ML_BM / 32; ++j) tma_load_2d(dst + j * (TC_BK * 128), &tmAdd, &xfull[s], n0 + 32 * j, addrow + kb * TC_BK);
         }
       }
     }
@@ -246,6 +272,24 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             tc_commit(&wempty[sw]);
           }
         }
+        if (p.add_tma) {
+          // acc2[:, 32 kb .. 32 kb + 32) += add block * I32  (A = add tile, MN-major; B = identity, K-major; N = 32)
+          const uint32_t idesc3 = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(ML_BM >> 4) << 24);
+          const uint32_t id_addr = w_addr + ML_NSW * ML_WBLK;
+          if (it == 0) { mbar_wait_bounded(id_full, 0); tc_fence_after(); }
+          const int nadd = (p.Cout + TC_BK - 1) / TC_BK;
+          for (int kb = 0; kb < nadd; ++kb, ++xc) {
+            const int sx = xc % ML_NSX;
+            mbar_wait_bounded(&xfull[sx], (xc / ML_NSX) & 1u);
+            tc_fence_after();
+            const uint32_t sa = x_addr + (uint32_t)sx * ML_XBLK;
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k)
+              tc_mma_tf32(tmem_acc2 + (uint32_t)(kb * TC_BK), make_smem_desc(sa + 1024 * k, TC_BK * 128, 512, 1),
+                          make_smem_desc(id_addr + 32 * k, 16, 1024), idesc3, 1u);
+            tc_commit(&xempty[sx]);
+          }
+        }
         tc_commit(acc2_full);
       }
     }
@@ -288,7 +332,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         const int nch = min(32, p.Cout - c0);
         if (nch <= 0 || (!pix_ok && !p.stats)) return;   // with statistics every lane takes part in the warp reductions
         float* dptr = p.D + (long long)b * p.sd + (long long)c0 * p.ldd + pix;
-        const float* aptr = p.add ? p.add + (long long)b * p.sadd + (long long)c0 * p.ldadd + pix : nullptr;
+        const float* aptr = (p.add && !p.add_tma) ? p.add + (long long)b * p.sadd + (long long)c0 * p.ldadd + pix : nullptr;
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           const int jb = g * 16, nv = nch - jb;
@@ -386,6 +430,25 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
   }
   rc = make_wmap(&tmW2, w2, Cout, Chid, ldw2, N2pad);
   if (rc) return rc;
+  // `add` on the tensor cores: needs a TMA-able operand (16-byte aligned, plane stride HW) and the identity block
+  CUtensorMap tmAdd = tmX, tmId = tmW2;
+  static float* d_ident = nullptr;   // [32][32] identity, shared by all calls on this device context
+  static std::once_flag id_once;
+  static cudaError_t id_err = cudaSuccess;
+  std::call_once(id_once, [] {
+    float h[32 * 32] = {0};
+    for (int i = 0; i < 32; ++i) h[i * 32 + i] = 1.0f;
+    id_err = cudaMalloc(&d_ident, sizeof(h));
+    if (id_err == cudaSuccess) id_err = cudaMemcpy(d_ident, h, sizeof(h), cudaMemcpyHostToDevice);
+  });
+  static const bool add_tma_off = getenv("MSFNO_MLP_ADD_LSU") != nullptr;
+  const bool add_tma = add && !add_tma_off && al16(add) && add_bstride % HW == 0 && id_err == cudaSuccess && d_ident;
+  if (add_tma) {
+    rc = make_map(&tmAdd, add, (add_bstride ? (long long)(B - 1) * (add_bstride / HW) : 0) + Cout, HW, HW, TC_BK, true);
+    if (rc) return rc;
+    rc = make_wmap(&tmId, d_ident, 32, 32, 32, 32);
+    if (rc) return rc;
+  }
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] { attr_err = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM); });
@@ -398,6 +461,8 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
   p.HW = (int)HW; p.K1a = Cin; p.K1b = x2 ? Cin2 : 0; p.Chid = Chid; p.Cout = Cout; p.N2pad = N2pad;
   p.tiles = (int)((HW + ML_BM - 1) / ML_BM);
   p.round_tf32 = (flags >> 1) & 1;
+  p.add_tma = add_tma ? 1 : 0;
+  p.add_rows_per_sample = add_bstride / HW;
   p.stats = stats;
   if (stats) MSFNO_CUDA_OK(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)B * Cout, st));
   int dev = 0, sms = 0;
@@ -406,7 +471,7 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
   int gx = sms / B;
   if (gx < 1) gx = 1;
   if (gx > p.tiles) gx = p.tiles;
-  MSFNO_CUDA_OK(launch_pdl(mlp_tc_kernel, dim3(gx, 1, B), dim3(576), ML_SMEM, st, tmX, tmX2, tmW1, tmW1b, tmW2, p));
+  MSFNO_CUDA_OK(launch_pdl(mlp_tc_kernel, dim3(gx, 1, B), dim3(576), ML_SMEM, st, tmX, tmX2, tmW1, tmW1b, tmW2, tmAdd, tmId, p));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
