@@ -33,10 +33,15 @@ namespace msfno {
 static constexpr int ML_BM = 128;                       // pixels per tile
 static constexpr int ML_XBLK = ML_BM * TC_BK * 4;       // activation k-block: 32 channels x 128 pixels = 16 KB
 static constexpr int ML_WBLK = 256 * TC_BK * 4;         // weight k-block slot: up to 256 rows x 32 k = 32 KB
-static constexpr int ML_NSX = 3, ML_NSW = 5;
+#ifndef MSFNO_ML_NSX
+#define MSFNO_ML_NSX 5
+#define MSFNO_ML_NSW 4
+#endif
+// activation blocks come from HBM (2 us under load), weight blocks from L2: the deep ring belongs to the activations
+static constexpr int ML_NSX = MSFNO_ML_NSX, ML_NSW = MSFNO_ML_NSW;
 static constexpr int ML_MAX_HID = 1024;
 static constexpr int ML_IDBLK = 32 * TC_BK * 4;         // resident 32 x 32 identity (K-major, 128-byte swizzle) = 4 KB
-static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + ML_IDBLK + (ML_MAX_HID + 256 + 512) * 4 + 256;
+static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + ML_IDBLK + (ML_MAX_HID + 256 + 512) * 4 + 512;
 
 struct MlpTcParams {
   float* D;
@@ -140,15 +145,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   float* stat_s = b2_s + 256;                                         // [2][256] per-CTA plane sums of the output
   uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 512);
   uint64_t* xfull = bars;            // [NSX]
-  uint64_t* xempty = bars + 4;       // [NSX]
-  uint64_t* wfull = bars + 8;        // [NSW]
-  uint64_t* wempty = bars + 16;      // [NSW]
-  uint64_t* acc1_full = bars + 24;   // GEMM1 of a tile complete
-  uint64_t* h_ready = bars + 25;     // EPI1 wrote the activated hidden tile back to TMEM (16 warps)
-  uint64_t* acc2_full = bars + 26;   // GEMM2 complete
-  uint64_t* acc2_empty = bars + 27;  // EPI2 finished reading acc2 (16 warps)
-  uint64_t* id_full = bars + 28;     // identity block landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  uint64_t* xempty = bars + 8;       // [NSX]
+  uint64_t* wfull = bars + 16;       // [NSW]
+  uint64_t* wempty = bars + 24;      // [NSW]
+  uint64_t* acc1_full = bars + 32;   // GEMM1 of a tile complete
+  uint64_t* h_ready = bars + 33;     // EPI1 wrote the activated hidden tile back to TMEM (16 warps)
+  uint64_t* acc2_full = bars + 34;   // GEMM2 complete
+  uint64_t* acc2_empty = bars + 35;  // EPI2 finished reading acc2 (16 warps)
+  uint64_t* id_full = bars + 36;     // identity block landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 37);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < ML_NSX; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
