@@ -16,6 +16,7 @@
 // Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator; afterwards all
 // 8 warps drain the accumulator (TMEM lane quarter q = warp % 4, column half = warp / 4).  BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32 fp32
 // (= one 128-byte swizzle span = 4 UMMA K-steps of 8).
+#include <cstdio>
 #include <cstdlib>
 
 #include "plan.h"
@@ -31,6 +32,7 @@ static constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align s
 
 struct TcParams {
   float* D;
+  long long* trace;   // debug (MSFNO_GEMM_TRACE): clock stamps of every CTA of the pair kernel, or null
   long long lda, ldb, ldd;
   const GemmGroup* groups;
   GemmGroup single;
@@ -185,8 +187,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
       const int gn = n0 + c0;
-      if (row < grp.M && gn < grp.N) {
-        const bool full_vec = vec && gn + 31 < grp.N;
+      if (gn < grp.N) {                                     // warp-uniform
+        const bool full_vec = vec && gn + 31 < grp.N;       // warp-uniform
+        const bool row_ok = row < grp.M;
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -194,7 +197,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.act_gelu) t = gelu_tanh3(t);
           v[j] = t;
         }
-        if (arow) {
+        if (arow && row_ok) {
           if (full_vec && ((p.ldadd | p.sadd) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.add) & 15) == 0) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -212,10 +215,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.relu_even && !(j & 1)) v[j] = fmaxf(v[j], 0.f);
           if (p.round_tf32) v[j] = round_to_tf32(v[j]);
         }
-        if (full_vec) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(drow + gn + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
+        if (full_vec) {   // all lanes take part: rows beyond M are masked inside
+          store_block_transposed(v, reinterpret_cast<float*>(tiles) + warp * (32 * 36),
+                                 p.D + grp.d_off + (long long)(m0 + q * 32) * p.ldd + gn, p.ldd, grp.M - (m0 + q * 32), lane);
+        } else if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (gn + j < grp.N) drow[gn + j] = v[j];
@@ -232,182 +235,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Persistent variant for launches made of MANY SHORT tiles (the Legendre contractions: 480 - 2880 tiles of 128 x 128
-// with only 4 k-blocks each).  In the one-tile-per-CTA kernel such a tile is all prologue (barrier init, TMEM
-// allocation, first-load latency) and epilogue; here a CTA keeps its TMA ring and its two TMEM accumulators across
-// tiles, so loads of tile i+1 and the drain of tile i-1 overlap the MMAs of tile i.
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-// (TMEM lane quarter w % 4).  Two CTAs fit per SM (96 KB ring, 2 x 128 TMEM columns each).
-static constexpr int TCP_STAGES = 3;
-static constexpr int TCP_SMEM_BYTES = TCP_STAGES * TC_STAGE_BYTES + 1024 + 256;
-
-template <bool B_MN>
-__global__ void __launch_bounds__(192, 2)
-gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p, int ngroups) {
-  extern __shared__ uint8_t smem_raw[];
-  pdl_trigger();
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TCP_STAGES * TC_STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + TCP_STAGES;
-  uint64_t* tmem_full = bars + 2 * TCP_STAGES;        // [2]
-  uint64_t* tmem_empty = bars + 2 * TCP_STAGES + 2;   // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TCP_STAGES + 4);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < TCP_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(2 * TC_BN));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();
-
-  const int per_group = p.tilesM * p.tilesN;
-  const int total = ngroups * per_group;
-  // every role walks the same tile sequence; tiles outside a group's extents are skipped by all of them alike
-  auto tile_of = [&](int t, GemmGroup& grp, int& m0, int& n0, int& g) -> bool {
-    g = t / per_group;
-    const int r = t - g * per_group;
-    const int tn = r / p.tilesM, tm = r - tn * p.tilesM;
-    if (p.use_single) {
-      grp = p.single;
-      grp.a_off += g * p.sa; grp.b_off += g * p.sb; grp.d_off += g * p.sd;
-    } else {
-      grp = p.groups[g];
-    }
-    m0 = tm * TC_BM; n0 = tn * TC_BN;
-    return m0 < grp.M && n0 < grp.N && grp.K > 0;
-  };
-
-  if (warp == 0) {
-    if (lane == 0) {
-      uint32_t kc = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        GemmGroup grp; int m0, n0, g;
-        if (!tile_of(t, grp, m0, n0, g)) continue;
-        const int nkb = (grp.K + TC_BK - 1) / TC_BK;
-        const int acol = (int)(grp.a_off % p.lda), arow = (int)(grp.a_off / p.lda) + m0;
-        const int bcol = (int)(grp.b_off % p.ldb), brow = (int)(grp.b_off / p.ldb);
-        for (int kb = 0; kb < nkb; ++kb, ++kc) {
-          const int s = kc % TCP_STAGES;
-          mbar_wait_bounded(&empty[s], ((kc / TCP_STAGES) & 1u) ^ 1u);
-          mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
-          uint8_t* sa = tiles + s * TC_STAGE_BYTES;
-          tma_load_2d(sa, &tmA, &full[s], acol + kb * TC_BK, arow);
-          if (!B_MN) {
-            tma_load_2d(sa + TC_A_BYTES, &tmB, &full[s], bcol + kb * TC_BK, brow + n0);
-          } else {
-#pragma unroll
-            for (int j = 0; j < TC_BN / 32; ++j)
-              tma_load_2d(sa + TC_A_BYTES + j * (TC_BK * 128), &tmB, &full[s], bcol + n0 + 32 * j, brow + kb * TC_BK);
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      uint32_t kc = 0, it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        GemmGroup grp; int m0, n0, g;
-        if (!tile_of(t, grp, m0, n0, g)) continue;
-        const int nkb = (grp.K + TC_BK - 1) / TC_BK;
-        const uint32_t acc = it & 1u, use = it >> 1;
-        mbar_wait_bounded(&tmem_empty[acc], (use & 1u) ^ 1u);
-        tc_fence_after();
-        for (int kb = 0; kb < nkb; ++kb, ++kc) {
-          const int s = kc % TCP_STAGES;
-          mbar_wait_bounded(&full[s], (kc / TCP_STAGES) & 1u);
-          tc_fence_after();
-          const uint32_t sa = base + s * TC_STAGE_BYTES, sb = sa + TC_A_BYTES;
-#pragma unroll
-          for (int k = 0; k < TC_BK / 8; ++k) {
-            const uint64_t adesc = make_smem_desc(sa + 32 * k, 16, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(sb + 1024 * k, TC_BK * 128, 512, 1) : make_smem_desc(sb + 32 * k, 16, 1024);
-            tc_mma_tf32(tmem_base + acc * TC_BN, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
-          }
-          tc_commit(&empty[s]);
-        }
-        tc_commit(&tmem_full[acc]);
-        ++it;
-      }
-    }
-  } else {
-    const int q = warp & 3;
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      GemmGroup grp; int m0, n0, g;
-      if (!tile_of(t, grp, m0, n0, g)) continue;
-      const uint32_t acc = it & 1u, use = it >> 1;
-      ++it;
-      const int row = m0 + q * 32 + lane;
-      float* drow = p.D + grp.d_off + (long long)row * p.ldd;
-      const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
-      const float bv = (p.bias && row < grp.M) ? p.bias[g * p.sbias + row] : 0.0f;
-      mbar_wait_bounded(&tmem_full[acc], use & 1u);
-      tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (c0 + 32 >= TC_BN) {   // last chunk read: hand the accumulator back before the stores
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        const int gn = n0 + c0;
-        if (row < grp.M && gn < grp.N) {
-          const bool full_vec = vec && gn + 31 < grp.N;
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float tv = __uint_as_float(r[j]) + bv;
-            if (p.act_gelu) tv = gelu_tanh3(tv);
-            if (p.relu_even && !(j & 1)) tv = fmaxf(tv, 0.f);
-            if (p.round_tf32) tv = round_to_tf32(tv);
-            v[j] = tv;
-          }
-          if (full_vec) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(drow + gn + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (gn + j < grp.N) drow[gn + j] = v[j];
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(2 * TC_BN));
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 // CTA-pair variant (cta_group::2): two CTAs of a cluster (the two SMs of a TPC) compute one 256 x 256 tile.
 // Each CTA stages ITS 128 rows of A and ITS 128 rows of B (= 128 of the 256 output columns); the leader's single
 // thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256), which reads both CTAs' shared memory and writes each
@@ -420,6 +247,11 @@ static constexpr int TC2_BN = 256;
 static constexpr int TC2_STAGE_BYTES = TC_A_BYTES + TC_A_BYTES;   // 128 rows of A + 128 rows of B per CTA
 static constexpr int TC2_SMEM_BYTES = TC_STAGES * TC2_STAGE_BYTES + 1024 + 256;
 
+__device__ __forceinline__ uint32_t __smid() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%smid;\n" : "=r"(r));
+  return r;
+}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
@@ -474,6 +306,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int n0 = tn * TC2_BN;
   if (tm * 256 >= grp.M || n0 >= grp.N) return;                // uniform for the PAIR
   pdl_trigger();
+  long long t_start = 0;
+  if (p.trace && threadIdx.x == 0) { t_start = clock64(); p.trace[blockIdx.x * 8 + 0] = (long long)(__smid()); }
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
@@ -503,6 +337,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
+  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 1] = clock64() - t_start;
 
   if (nkb > 0) {
     if (warp == 0 && lane == 0) {
@@ -547,6 +382,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (nkb > 0) {
       mbar_wait_bounded(tmem_full, 0);
       tc_fence_after();
+      if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 2] = clock64() - t_start;
     }
     float* drow = p.D + grp.d_off + (long long)row * p.ldd;
     const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
@@ -571,8 +407,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
       const int gn = n0 + c0;
-      if (row < grp.M && gn < grp.N) {
-        const bool full_vec = vec && gn + 31 < grp.N;
+      if (gn < grp.N) {                                     // warp-uniform
+        const bool full_vec = vec && gn + 31 < grp.N;       // warp-uniform
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -582,10 +418,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (p.round_tf32) t = round_to_tf32(t);
           v[j] = t;
         }
-        if (full_vec) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(drow + gn + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
+        if (full_vec) {   // all lanes take part: rows beyond M are masked inside
+          store_block_transposed(v, reinterpret_cast<float*>(tiles) + warp * (32 * 36),
+                                 p.D + grp.d_off + (long long)(m0 + q * 32) * p.ldd + gn, p.ldd, grp.M - (m0 + q * 32), lane);
+        } else if (row < grp.M) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (gn + j < grp.N) drow[gn + j] = v[j];
@@ -594,6 +430,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     tc_fence_before();
   }
+  if (p.trace && threadIdx.x == 0) { p.trace[blockIdx.x * 8 + 3] = clock64() - t_start; p.trace[blockIdx.x * 8 + 4] = t_start; }
   cluster_sync_all();   // neither CTA may retire (or free TMEM) while its peer can still touch it
   if (warp == 2) {
     tc_fence_after();
@@ -640,7 +477,24 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     p.tilesM = (g.maxM + 255) / 256;
     p.tilesN = (g.maxN + TC2_BN - 1) / TC2_BN;
     dim3 grid(2 * p.tilesM * p.tilesN, g.ngroups);
+    static const bool trace_on = getenv("MSFNO_GEMM_TRACE") != nullptr;
+    static long long* d_trace = nullptr;
+    if (trace_on) {
+      if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 1024 * 8 * sizeof(long long)));
+      MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 1024 * 8 * sizeof(long long), st));
+      if (grid.x <= 1024 && grid.y == 1) p.trace = d_trace;
+    }
     MSFNO_CUDA_OK(launch_pdl(gemm_tc2_kernel, grid, dim3(256), TC2_SMEM_BYTES, st, tmA, tmB, p));
+    if (trace_on && p.trace) {
+      static long long h[1024 * 8];
+      MSFNO_CUDA_OK(cudaStreamSynchronize(st));
+      MSFNO_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+      long long t0 = h[4];
+      for (unsigned i = 0; i < grid.x; ++i) if (h[i * 8 + 4] && h[i * 8 + 4] < t0) t0 = h[i * 8 + 4];
+      fprintf(stderr, "gemm_tc2 trace: cta sm | start(rel) prologue_done mainloop_done epilogue_done (clk since CTA start)\n");
+      for (unsigned i = 0; i < grid.x; i += (grid.x > 64 ? 7 : 1))
+        fprintf(stderr, "%4u %3lld | %8lld %8lld %8lld %8lld\n", i, h[i * 8], h[i * 8 + 4] - t0, h[i * 8 + 1], h[i * 8 + 2], h[i * 8 + 3]);
+    }
     count_launch();
     MSFNO_CUDA_OK(cudaGetLastError());
     return MSFNO_OK;
@@ -650,38 +504,6 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   if (rc) return rc;
   rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, bmn ? TC_BK : TC_BN, bmn);
   if (rc) return rc;
-  // many short tiles (K <= 256, e.g. the Legendre contractions): persistent kernel
-  static const bool persist_off = getenv("MSFNO_GEMM_NO_PERSIST") != nullptr;
-  {
-    int maxK = g.use_single ? g.single.K : g.maxK;
-    const long long ntiles = (long long)g.ngroups * ((g.maxM + TC_BM - 1) / TC_BM) * ((g.maxN + TC_BN - 1) / TC_BN);
-    if (!persist_off && !g.A2 && !g.add && maxK > 0 && maxK <= 256 && ntiles >= 296) {
-      static std::once_flag oncep;
-      static cudaError_t attr_errp = cudaSuccess;
-      std::call_once(oncep, [] {
-        attr_errp = cudaFuncSetAttribute(gemm_tcp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
-        if (attr_errp == cudaSuccess)
-          attr_errp = cudaFuncSetAttribute(gemm_tcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_BYTES);
-      });
-      MSFNO_CUDA_OK(attr_errp);
-      TcParams p{};
-      p.D = g.D; p.lda = g.lda; p.ldb = g.ldb; p.ldd = g.ldd;
-      p.groups = g.groups; p.single = g.single; p.sa = g.sa; p.sb = g.sb; p.sd = g.sd; p.use_single = g.use_single;
-      p.relu_even = g.relu_even; p.round_tf32 = round_tf32;
-      p.bias = g.bias; p.sbias = g.sbias; p.act_gelu = g.act_gelu;
-      p.tilesM = (g.maxM + TC_BM - 1) / TC_BM;
-      p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;
-      int dev = 0, sms = 0;
-      MSFNO_CUDA_OK(cudaGetDevice(&dev));
-      MSFNO_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      const int gx = (int)(ntiles < 2LL * sms ? ntiles : 2LL * sms);
-      if (bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tcp_kernel<true>, dim3(gx), dim3(192), TCP_SMEM_BYTES, st, tmA, tmB, p, g.ngroups));
-      else MSFNO_CUDA_OK(launch_pdl(gemm_tcp_kernel<false>, dim3(gx), dim3(192), TCP_SMEM_BYTES, st, tmA, tmB, p, g.ngroups));
-      count_launch();
-      MSFNO_CUDA_OK(cudaGetLastError());
-      return MSFNO_OK;
-    }
-  }
   if (g.A2) {
     rc = make_map(&tmA2, g.A2, a2_rows, a2_cols, g.lda2, TC_BM);
     if (rc) return rc;

@@ -86,7 +86,6 @@ struct GemmLaunch {
   const GemmGroup* groups;  // device array
   int ngroups;
   int maxM, maxN;           // over groups (grid sizing)
-  int maxK;                 // over groups, 0 = unknown (selects the persistent short-tile kernel in the tensor-core tier)
   int use_single;           // 1: ignore `groups`; group y = `single` shifted by y * (sa, sb, sd) (strided batch)
   GemmGroup single;
   long long sa, sb, sd;

@@ -21,7 +21,6 @@ static int legendre_gemm(msfno_plan* p, int kind, const float* A, long long lda,
   g.lda = lda; g.ldb = ldb; g.ldd = ldd;
   g.a_kmajor = a_k; g.b_kmajor = b_k;
   g.groups = groups; g.ngroups = ng; g.maxM = maxM; g.maxN = maxN;
-  g.maxK = (kind == GK_ANALYSIS || kind == GK_SYNTHESIS_ADJ) ? p->nlat : p->Lj;
   if (p->precision == MSFNO_PREC_TF32 && (kind == GK_ANALYSIS || kind == GK_SYNTHESIS) && gemm_tc_supported(g)) {
     // tensor-core tier: the 2-D buffers behind A and B as TMA sees them (zero-fill outside)
     const int mloc = (m_hi < 0 ? p->mlim : m_hi) - m_lo;

@@ -78,6 +78,27 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Epilogue store of a 32 x 32 block held one ROW per lane (v[32] = 32 consecutive columns) to a row-major matrix.
+// Stored straight from the registers a warp instruction touches 32 different rows (32 L1 wavefronts per STG.128: the
+// per-CTA clock trace of the pair GEMM showed 10-14 kclk of epilogue for 16 kclk of MMAs).  Transposed through a private
+// 32 x 36 shared-memory tile (conflict-free 16-byte writes and reads), every instruction writes four full 128-byte lines.
+//   wt: this warp's 32 x 36 floats, 16-byte aligned;  dst: address of (first row, first column);  rows: valid rows (<= 32)
+__device__ __forceinline__ void store_block_transposed(const float (&v)[32], float* wt, float* dst, long long ldd, int rows,
+                                                       int lane) {
+  float4* wrow = reinterpret_cast<float4*>(wt + lane * 36);
+#pragma unroll
+  for (int jj = 0; jj < 8; ++jj) wrow[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+  __syncwarp();
+  const int rr = lane >> 3, c4 = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = rr + 4 * i;
+    const float4 t = *reinterpret_cast<const float4*>(wt + row * 36 + 4 * c4);
+    if (row < rows) *reinterpret_cast<float4*>(dst + (long long)row * ldd + 4 * c4) = t;
+  }
+  __syncwarp();
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
