@@ -18,6 +18,7 @@
 // CTA tile: MT x 128 rows (lat of one (b, c) plane) by 256 columns, K blocks of 32; MT = 2 halves the re-reads of the
 // DFT matrix at 721x1440 (two accumulators = all 512 TMEM columns).  Warp roles as in gemm_tc.cu.
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -29,7 +30,6 @@ namespace msfno {
 static constexpr int DF_BN = 256;
 static constexpr int DF_A_BYTES = 128 * TC_BK * 4;      // 16 KB: 128 rows x 32 k
 static constexpr int DF_B_BYTES = DF_BN * TC_BK * 4;    // 32 KB: 256 rows x 32 k
-static constexpr int DF_TPITCH = DF_BN + 1;             // staging pitch (floats) of the inverse epilogue
 
 struct DftParams {
   float* out;
@@ -40,6 +40,7 @@ struct DftParams {
   int nkb;                              // k blocks
   int flags;                            // forward: bit0 round to TF32; inverse: bit0 GELU, bit1 round to TF32
   float dc;                             // forward: factor of the shift on the (m = 0, re) bin = 2 pi
+  long long* trace;                     // debug (MSFNO_DFT_TRACE): per-CTA clock stamps, or null
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
@@ -74,6 +75,8 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int n0 = blockIdx.x * DF_BN;
 
   pdl_trigger();
+  const long long t_start = clock64();
+  const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
   uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + NS * STAGE);
@@ -97,6 +100,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
+  if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 4 + 0] = clock64() - t_start;
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
@@ -147,6 +151,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int q = warp & 3, chalf = warp >> 2;
   mbar_wait_bounded(tmem_full, 0);
   tc_fence_after();
+  if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 4 + 1] = clock64() - t_start;
   if (!INV) {
     const float sc = p.sc ? p.sc[bc] : 1.0f;
     const float dcv = p.sh ? p.dc * p.sh[bc] : 0.0f;
@@ -161,60 +166,96 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint32_t r[32];
         MSFNO_DFT_LD32(r, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * DF_BN + c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (in_pad) {
-          float* o = p.out + (((size_t)b * p.mlim + (c0 >> 1)) * twoC + 2 * c) * p.kpad + lat;
+        // values of this lane's latitude for 32 spectral columns -> private [col][lat] tile (pitch 36) -> four latitudes
+        // (16 bytes) per lane: a store instruction then writes 128 contiguous bytes of FOUR columns instead of one
+        // (the epilogue cost 25 of 95 kclk per CTA with one 4-byte store per lane and column)
+        float* wt = reinterpret_cast<float*>(tiles) + warp * (32 * 36);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (c0 + j < 2 * p.mlim) {
-              float v = __uint_as_float(r[j]) * sc;
-              if (c0 + j == 0) v += dcv;
-              if (p.flags & 1) v = round_to_tf32(v);
-              if (!in_rows) v = 0.0f;
-              // column n = 2m + ri of plane c -> row (m * 2C + 2c + ri) of the [mlim * 2C][kpad] matrix
-              o[((size_t)(j >> 1) * twoC + (j & 1)) * p.kpad] = v;
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(r[j]) * sc;
+          if (c0 + j == 0) v += dcv;
+          if (p.flags & 1) v = round_to_tf32(v);
+          if (!in_rows) v = 0.0f;
+          wt[j * 36 + lane] = v;
+        }
+        __syncwarp();
+        {
+          const int cc = lane >> 3, l4 = lane & 7;
+          const int latq = lat0 + mt * 128 + q * 32 + 4 * l4;          // first of this lane's four latitudes
+          if (latq < p.kpad) {                                         // kpad % 4 == 0: all four or none
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int j = cc + 4 * i, n = c0 + j;                    // column n = 2m + ri -> row (m * 2C + 2c + ri)
+              if (n < 2 * p.mlim) {
+                const float4 t4 = *reinterpret_cast<const float4*>(wt + j * 36 + 4 * l4);
+                *reinterpret_cast<float4*>(p.out + (((size_t)b * p.mlim + (n >> 1)) * twoC + 2 * c + (n & 1)) * p.kpad + latq) = t4;
+              }
             }
           }
         }
+        __syncwarp();
       }
     }
     tc_fence_before();
   } else {
-    float* stage_t = reinterpret_cast<float*>(tiles);   // [128][DF_TPITCH]: the pipeline stages are idle now
+    // Staging tile in the (now idle) pipeline stages: all 256 columns when they fit, otherwise two passes of 128
+    // (small grids run with a 2-stage ring so that two CTAs share an SM and overlap each other's phases).
+    constexpr int SW = (NS * STAGE >= 128 * (DF_BN + 1) * 4) ? DF_BN : DF_BN / 2;
+    constexpr int SP = SW + 1;                            // pitch: lane = row keeps a warp's 32 rows on distinct banks
+    static_assert(NS * STAGE >= 128 * SP * 4, "staging tile does not fit in the pipeline stages");
+    float* stage_t = reinterpret_cast<float*>(tiles);     // [128][SP]
     float lsum = 0.0f, lsq = 0.0f;
     const size_t plane = (size_t)bc * p.nlat;
+    const int ncol = min(DF_BN, p.nlon - n0);             // multiple of 4 (nlon % 4 == 0)
+    const bool has_skip = p.skip != nullptr;
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      if (mt) __syncthreads();
-      // TMEM -> staging tile (lane = row: pitch 257 words keeps the 32 rows of a warp on distinct banks)
+    for (int pass = 0; pass < MT * (DF_BN / SW); ++pass) {
+      const int mt = pass / (DF_BN / SW), hc = pass % (DF_BN / SW);
+      const int cbase = hc * SW;                          // first column of this pass
+      if (pass) __syncthreads();
+      // TMEM -> staging tile
 #pragma unroll 1
       for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+        if (c0 < cbase || c0 >= cbase + SW) continue;
         uint32_t r[32];
         MSFNO_DFT_LD32(r, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * DF_BN + c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        float* trow = stage_t + (size_t)(q * 32 + lane) * DF_TPITCH + c0;
+        float* trow = stage_t + (size_t)(q * 32 + lane) * SP + (c0 - cbase);
 #pragma unroll
         for (int j = 0; j < 32; ++j) trow[j] = __uint_as_float(r[j]);
       }
       __syncthreads();
       // staging tile -> global: a warp walks rows; a lane owns float4 groups (512 contiguous bytes per warp access).
-      // All global loads of a row (skip) are issued before any arithmetic: their latency overlaps instead of adding up.
-      const int ncol = min(DF_BN, p.nlon - n0);           // multiple of 4 (nlon % 4 == 0)
-      const bool has_skip = p.skip != nullptr;
-      for (int row = warp; row < 128; row += 8) {
+      // The skip values are requested three rows ahead (register ring; the loop is unrolled by 3 so its indices are
+      // compile-time): a dependent DRAM / L2 round trip per row was most of this phase.
+      auto load_skip = [&](int row, float4 (&dst)[SW / 128]) {
+        const int lat = lat0 + mt * 128 + row;
+        const size_t goff = (plane + lat) * p.nlon + n0 + cbase;
+#pragma unroll
+        for (int i = 0; i < SW / 128; ++i) {
+          const int col = 4 * (lane + 32 * i);
+          dst[i] = (has_skip && row < 128 && lat < p.nlat && cbase + col < ncol) ? __ldg(reinterpret_cast<const float4*>(p.skip + goff + col))
+                                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      float4 skr[3][SW / 128];
+      load_skip(warp, skr[0]);
+      load_skip(warp + 8, skr[1]);
+      load_skip(warp + 16, skr[2]);
+#pragma unroll 3
+      for (int row = warp, u = 0; row < 128; row += 8, ++u) {
         const int lat = lat0 + mt * 128 + row;
         if (lat >= p.nlat) break;
-        const size_t goff = (plane + lat) * p.nlon + n0;
-        const float* trow = stage_t + (size_t)row * DF_TPITCH;
-        float4 sk[2];
+        const size_t goff = (plane + lat) * p.nlon + n0 + cbase;
+        const float* trow = stage_t + (size_t)row * SP;
+        float4 sk[SW / 128];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const int col = 4 * (lane + 32 * i);
-          sk[i] = (has_skip && col < ncol) ? __ldg(reinterpret_cast<const float4*>(p.skip + goff + col)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+        for (int i = 0; i < SW / 128; ++i) sk[i] = skr[u % 3][i];
+        load_skip(row + 24, skr[u % 3]);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < SW / 128; ++i) {
           const int col = 4 * (lane + 32 * i);
-          if (col < ncol) {
+          if (cbase + col < ncol) {
             float v[4] = {trow[col] + sk[i].x, trow[col + 1] + sk[i].y, trow[col + 2] + sk[i].z, trow[col + 3] + sk[i].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -246,6 +287,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   }
   __syncthreads();
+  if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 4 + 2] = clock64() - t_start;
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(MT * DF_BN));
@@ -305,10 +347,26 @@ static int make_map_5d(CUtensorMap* tm, const float* base, const cuuint64_t dims
 template <bool INV, int MT, int NS>
 static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const DftParams& prm, dim3 grid, cudaStream_t st) {
   constexpr int smem = NS * (MT * DF_A_BYTES + DF_B_BYTES) + 1024 + 512;
-  static_assert(!INV || NS * (MT * DF_A_BYTES + DF_B_BYTES) >= 128 * DF_TPITCH * 4, "staging tile does not fit in the pipeline stages");
   auto kern = dft_tc_kernel<INV, MT, NS>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  MSFNO_CUDA_OK(launch_pdl(kern, grid, dim3(256), smem, st, tmA, tmB, prm));
+  static const bool trace_on = getenv("MSFNO_DFT_TRACE") != nullptr;
+  static long long* d_trace = nullptr;
+  DftParams prm2 = prm;
+  if (trace_on) {
+    if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 512 * 4 * sizeof(long long)));
+    MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 512 * 4 * sizeof(long long), st));
+    prm2.trace = d_trace;
+  }
+  MSFNO_CUDA_OK(launch_pdl(kern, grid, dim3(256), smem, st, tmA, tmB, prm2));
+  if (trace_on) {
+    static long long h[512 * 4];
+    MSFNO_CUDA_OK(cudaStreamSynchronize(st));
+    MSFNO_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+    double a0 = 0, a1 = 0, a2 = 0; int n = 0;
+    for (int i = 0; i < 512; ++i) if (h[i * 4 + 2]) { a0 += h[i * 4]; a1 += h[i * 4 + 1]; a2 += h[i * 4 + 2]; ++n; }
+    if (n) fprintf(stderr, "dft_tc trace INV=%d MT=%d grid=(%u,%u,%u): mean clk since CTA start: prologue %.0f  mainloop_done %.0f  cta_done %.0f  (n=%d)\n",
+                   (int)INV, MT, grid.x, grid.y, grid.z, a0 / n, a1 / n, a2 / n, n);
+  }
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
@@ -353,7 +411,7 @@ int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, 
   prm.flags = act_flags;
   const int tilesN = (p->nlon + DF_BN - 1) / DF_BN;
   if (p->nlat > 128) return launch_dft<true, 2, 3>(tmA, tmB, prm, dim3(tilesN, (p->nlat + 255) / 256, B * C), st);
-  return launch_dft<true, 1, 3>(tmA, tmB, prm, dim3(tilesN, 1, B * C), st);
+  return launch_dft<true, 1, 2>(tmA, tmB, prm, dim3(tilesN, 1, B * C), st);
 }
 
 }  // namespace msfno
