@@ -100,7 +100,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
-  if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 4 + 0] = clock64() - t_start;
+  if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 8 + 0] = clock64() - t_start;
 
   if (warp == 0 && lane == 0) {
     // ---------------- TMA producer ----------------
@@ -151,7 +151,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int q = warp & 3, chalf = warp >> 2;
   mbar_wait_bounded(tmem_full, 0);
   tc_fence_after();
-  if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 4 + 1] = clock64() - t_start;
+  if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 8 + 1] = clock64() - t_start;
   if (!INV) {
     const float sc = p.sc ? p.sc[bc] : 1.0f;
     const float dcv = p.sh ? p.dc * p.sh[bc] : 0.0f;
@@ -200,8 +200,8 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   } else {
     // Staging tile in the (now idle) pipeline stages: all 256 columns when they fit, otherwise two passes of 128
     // (small grids run with a 2-stage ring so that two CTAs share an SM and overlap each other's phases).
-    constexpr int SW = (NS * STAGE >= 128 * (DF_BN + 1) * 4) ? DF_BN : DF_BN / 2;
-    constexpr int SP = SW + 1;                            // pitch: lane = row keeps a warp's 32 rows on distinct banks
+    constexpr int SW = (NS * STAGE >= 128 * (DF_BN + 4) * 4) ? DF_BN : DF_BN / 2;
+    constexpr int SP = SW + 4;   // pitch = 4 (mod 32) words: 16-byte writes by row (lane = row) and 16-byte reads along a row are both conflict-free
     static_assert(NS * STAGE >= 128 * SP * 4, "staging tile does not fit in the pipeline stages");
     float* stage_t = reinterpret_cast<float*>(tiles);     // [128][SP]
     float lsum = 0.0f, lsq = 0.0f;
@@ -220,11 +220,13 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         uint32_t r[32];
         MSFNO_DFT_LD32(r, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * DF_BN + c0));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        float* trow = stage_t + (size_t)(q * 32 + lane) * SP + (c0 - cbase);
+        float4* trow = reinterpret_cast<float4*>(stage_t + (size_t)(q * 32 + lane) * SP + (c0 - cbase));
 #pragma unroll
-        for (int j = 0; j < 32; ++j) trow[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 8; ++j)
+          trow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
       }
       __syncthreads();
+      if (p.trace && threadIdx.x == 0 && cta_lin < 512 && pass == 0) p.trace[cta_lin * 8 + 3] = clock64() - t_start;
       // staging tile -> global: a warp walks rows; a lane owns float4 groups (512 contiguous bytes per warp access).
       // The skip values are requested three rows ahead (register ring; the loop is unrolled by 3 so its indices are
       // compile-time): a dependent DRAM / L2 round trip per row was most of this phase.
@@ -256,7 +258,8 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         for (int i = 0; i < SW / 128; ++i) {
           const int col = 4 * (lane + 32 * i);
           if (cbase + col < ncol) {
-            float v[4] = {trow[col] + sk[i].x, trow[col + 1] + sk[i].y, trow[col + 2] + sk[i].z, trow[col + 3] + sk[i].w};
+            const float4 t4 = *reinterpret_cast<const float4*>(trow + col);
+            float v[4] = {t4.x + sk[i].x, t4.y + sk[i].y, t4.z + sk[i].z, t4.w + sk[i].w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               if (p.flags & 1) v[e] = gelu_tanh3(v[e]);
@@ -268,6 +271,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
         }
       }
+      if (p.trace && threadIdx.x == 0 && cta_lin < 512 && pass == 0) p.trace[cta_lin * 8 + 4] = clock64() - t_start;
     }
     tc_fence_before();
     if (p.stats) {
@@ -287,7 +291,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     }
   }
   __syncthreads();
-  if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 4 + 2] = clock64() - t_start;
+  if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 8 + 2] = clock64() - t_start;
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(MT * DF_BN));
@@ -353,19 +357,19 @@ static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const DftP
   static long long* d_trace = nullptr;
   DftParams prm2 = prm;
   if (trace_on) {
-    if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 512 * 4 * sizeof(long long)));
-    MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 512 * 4 * sizeof(long long), st));
+    if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 512 * 8 * sizeof(long long)));
+    MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 512 * 8 * sizeof(long long), st));
     prm2.trace = d_trace;
   }
   MSFNO_CUDA_OK(launch_pdl(kern, grid, dim3(256), smem, st, tmA, tmB, prm2));
   if (trace_on) {
-    static long long h[512 * 4];
+    static long long h[512 * 8];
     MSFNO_CUDA_OK(cudaStreamSynchronize(st));
     MSFNO_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
-    double a0 = 0, a1 = 0, a2 = 0; int n = 0;
-    for (int i = 0; i < 512; ++i) if (h[i * 4 + 2]) { a0 += h[i * 4]; a1 += h[i * 4 + 1]; a2 += h[i * 4 + 2]; ++n; }
-    if (n) fprintf(stderr, "dft_tc trace INV=%d MT=%d grid=(%u,%u,%u): mean clk since CTA start: prologue %.0f  mainloop_done %.0f  cta_done %.0f  (n=%d)\n",
-                   (int)INV, MT, grid.x, grid.y, grid.z, a0 / n, a1 / n, a2 / n, n);
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0; int n = 0;
+    for (int i = 0; i < 512; ++i) if (h[i * 8 + 2]) { a0 += h[i * 8]; a1 += h[i * 8 + 1]; a2 += h[i * 8 + 2]; a3 += h[i * 8 + 3]; a4 += h[i * 8 + 4]; ++n; }
+    if (n) fprintf(stderr, "dft_tc trace INV=%d MT=%d grid=(%u,%u,%u): mean clk since CTA start: prologue %.0f  mainloop_done %.0f  [staged %.0f  pass0_done %.0f]  cta_done %.0f  (n=%d)\n",
+                   (int)INV, MT, grid.x, grid.y, grid.z, a0 / n, a1 / n, a3 / n, a4 / n, a2 / n, n);
   }
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
