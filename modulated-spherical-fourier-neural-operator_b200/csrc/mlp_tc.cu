@@ -133,6 +133,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int nkb1a = (p.K1a + TC_BK - 1) / TC_BK, nkb1b = (p.K1b + TC_BK - 1) / TC_BK, nkb1 = nkb1a + nkb1b;
   const int HC = min(p.Chid, 256), nh = p.Chid / HC;      // hidden chunk (TMEM columns of acc1) and chunk count
   const int nkb2 = HC / TC_BK;                            // GEMM2 k-blocks per chunk
+  // EPI1 activates the hidden chunk in two column halves; GEMM2's first k-blocks start after the first half, so the
+  // tensor pipe runs while the second half is still being activated
+  const int nhalf = (HC % 64 == 0) ? 2 : 1, hwid = HC / nhalf;
   const uint32_t w2_bytes = (uint32_t)p.N2pad * TC_BK * 4, w1_bytes = (uint32_t)HC * TC_BK * 4;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -149,17 +152,18 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint64_t* wfull = bars + 16;       // [NSW]
   uint64_t* wempty = bars + 24;      // [NSW]
   uint64_t* acc1_full = bars + 32;   // GEMM1 of a tile complete
-  uint64_t* h_ready = bars + 33;     // EPI1 wrote the activated hidden tile back to TMEM (16 warps)
-  uint64_t* acc2_full = bars + 34;   // GEMM2 complete
-  uint64_t* acc2_empty = bars + 35;  // EPI2 finished reading acc2 (16 warps)
-  uint64_t* id_full = bars + 36;     // identity block landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 37);
+  uint64_t* h_ready = bars + 33;     // [2] EPI1 wrote the activated hidden columns of half 0 / half 1 back to TMEM (16 warps each)
+  uint64_t* acc2_full = bars + 35;   // GEMM2 complete
+  uint64_t* acc2_empty = bars + 36;  // EPI2 finished reading acc2 (16 warps)
+  uint64_t* id_full = bars + 37;     // identity block landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 38);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < ML_NSX; ++s) { mbar_init(&xfull[s], 1); mbar_init(&xempty[s], 1); }
     for (int s = 0; s < ML_NSW; ++s) { mbar_init(&wfull[s], 1); mbar_init(&wempty[s], 1); }
     mbar_init(acc1_full, 1);
-    mbar_init(h_ready, 16);
+    mbar_init(&h_ready[0], 16);
+    mbar_init(&h_ready[1], 16);
     mbar_init(acc2_full, 1);
     mbar_init(acc2_empty, 16);
     mbar_init(id_full, 1);
@@ -262,10 +266,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             tc_commit(&wempty[sw]);
           }
           tc_commit(acc1_full);
-          mbar_wait_bounded(h_ready, seq & 1u);                     // hidden chunk activated in place
+          mbar_wait_bounded(&h_ready[0], seq & 1u);                 // first half of the hidden chunk activated in place
           if (hh == 0) mbar_wait_bounded(acc2_empty, (it & 1u) ^ 1u);   // previous tile's EPI2 has drained acc2
           tc_fence_after();
           for (int kb = 0; kb < nkb2; ++kb, ++wc) {
+            if (kb * TC_BK == hwid || (nhalf == 1 && kb == 0)) mbar_wait_bounded(&h_ready[1], seq & 1u);   // second half
             const int sw = wc % ML_NSW;
             mbar_wait_bounded(&wfull[sw], (wc / ML_NSW) & 1u);
             tc_fence_after();
@@ -310,22 +315,24 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         tc_fence_after();
 #pragma unroll 1
         for (int h = 0; h < 2; ++h) {
-          const int c0 = cq * 64 + h * 32;
-          if (c0 < HC) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_acc1 + lane_off + (uint32_t)c0;
-            MSFNO_TMEM_LD32(r, taddr);
-            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-            const float* bb = b1_s + hh * HC + c0;
+          if (h < nhalf) {
+#pragma unroll 1
+            for (int c0 = h * hwid + cq * 32; c0 < (h + 1) * hwid; c0 += 128) {
+              uint32_t r[32];
+              const uint32_t taddr = tmem_acc1 + lane_off + (uint32_t)c0;
+              MSFNO_TMEM_LD32(r, taddr);
+              asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+              const float* bb = b1_s + hh * HC + c0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_to_tf32_pretrunc(gelu_tanh3(__uint_as_float(r[j]) + bb[j])));
-            MSFNO_TMEM_ST32(taddr, r);
+              for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(round_to_tf32_pretrunc(gelu_tanh3(__uint_as_float(r[j]) + bb[j])));
+              MSFNO_TMEM_ST32(taddr, r);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
           }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&h_ready[h]);
         }
-        asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(h_ready);
       }
 
       // ---- EPI2: output channels [cq*64, cq*64+64) of acc2
