@@ -414,7 +414,9 @@ int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, 
   prm.nkb = (2 * p->mlim + TC_BK - 1) / TC_BK;
   prm.flags = act_flags;
   const int tilesN = (p->nlon + DF_BN - 1) / DF_BN;
-  if (p->nlat > 128) return launch_dft<true, 2, 3>(tmA, tmB, prm, dim3(tilesN, (p->nlat + 255) / 256, B * C), st);
+  static const int inv_mt = getenv("MSFNO_DFT_INV_MT") ? atoi(getenv("MSFNO_DFT_INV_MT")) : 1;   // 1: 128-row tiles, two CTAs per SM overlap each other's load / MMA / store phases (faster than one 256-row tile per SM)
+  if (p->nlat > 128 && inv_mt == 2) return launch_dft<true, 2, 3>(tmA, tmB, prm, dim3(tilesN, (p->nlat + 255) / 256, B * C), st);
+  if (p->nlat > 128) return launch_dft<true, 1, 2>(tmA, tmB, prm, dim3(tilesN, (p->nlat + 127) / 128, B * C), st);
   return launch_dft<true, 1, 2>(tmA, tmB, prm, dim3(tilesN, 1, B * C), st);
 }
 
