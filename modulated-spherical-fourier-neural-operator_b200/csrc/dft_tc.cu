@@ -391,7 +391,9 @@ int launch_dft_fwd(msfno_plan* p, const float* x, float* Xt, const float* in_sca
   prm.nkb = (p->nlon + TC_BK - 1) / TC_BK;
   prm.flags = 1;
   prm.dc = (float)(2.0 * M_PI);
-  if (p->kpad > 128) return launch_dft<false, 2, 3>(tmA, tmB, prm, dim3(1, (p->kpad + 255) / 256, B * C), st);
+  static const int fwd_mt = getenv("MSFNO_DFT_FWD_MT") ? atoi(getenv("MSFNO_DFT_FWD_MT")) : 2;
+  if (p->kpad > 128 && fwd_mt == 2) return launch_dft<false, 2, 3>(tmA, tmB, prm, dim3(1, (p->kpad + 255) / 256, B * C), st);
+  if (p->kpad > 128) return launch_dft<false, 1, 2>(tmA, tmB, prm, dim3(1, (p->kpad + 127) / 128, B * C), st);
   return launch_dft<false, 1, 2>(tmA, tmB, prm, dim3(1, 1, B * C), st);
 }
 
