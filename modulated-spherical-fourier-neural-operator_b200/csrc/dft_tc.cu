@@ -41,6 +41,7 @@ struct DftParams {
   int flags;                            // forward: bit0 round to TF32; inverse: bit0 GELU, bit1 round to TF32
   float dc;                             // forward: factor of the shift on the (m = 0, re) bin = 2 pi
   long long* trace;                     // debug (MSFNO_DFT_TRACE): per-CTA clock stamps, or null
+  int skip_tma;                         // inverse: skip is accumulated on the tensor cores (tmS / tmI), the epilogue does not load it
 };
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
@@ -66,7 +67,8 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* t
 // grid: (N tiles of 256 [inverse only], row tiles of MT*128, B*C planes)
 template <bool INV, int MT, int NS>
 __global__ void __launch_bounds__(256, 1)
-dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DftParams p) {
+dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmS,
+              const __grid_constant__ CUtensorMap tmI, DftParams p) {
   constexpr int STAGE = MT * DF_A_BYTES + DF_B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -79,16 +81,19 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int cta_lin = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + NS * STAGE);
+  uint8_t* idblk = tiles + NS * STAGE;                               // 32 x 32 identity, K-major swizzled (skip path)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(idblk + 4096);
   uint64_t* full = bars;
   uint64_t* empty = bars + NS;
   uint64_t* tmem_full = bars + 2 * NS;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 1);
-  double* red = reinterpret_cast<double*>(bars + 2 * NS + 2);   // [16]
+  uint64_t* id_full = bars + 2 * NS + 2;
+  double* red = reinterpret_cast<double*>(bars + 2 * NS + 4);   // [16]
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NS; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(tmem_full, 1);
+    mbar_init(id_full, 1);
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -123,6 +128,26 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       tma_load_2d(sa + MT * DF_A_BYTES, &tmB, &full[s], kb * TC_BK, n0);
     }
+    if (INV && p.skip_tma) {
+      // skip tile: [MT x 128 rows (lat)] x 32 longitudes per block, K-major, through the A slots of the same ring; it is
+      // accumulated by N = 32 MMAs against the identity (plain loads of it were the inverse kernel's top stall)
+      mbar_arrive_expect_tx(id_full, 4096);
+      tma_load_2d(idblk, &tmI, id_full, 0, 0);
+      // a stage holds SPS skip blocks here (the B part of the stage is free in this phase): more bytes in flight
+      constexpr int SPS = STAGE / (MT * DF_A_BYTES);
+      const int nsk = (min(DF_BN, p.nlon - n0) + TC_BK - 1) / TC_BK;
+      for (int j0 = 0, u = 0; j0 < nsk; j0 += SPS, ++u) {
+        const int kc = p.nkb + u, s = kc % NS;
+        const int nb = min(SPS, nsk - j0);
+        mbar_wait_bounded(&empty[s], (uint32_t)(((kc / NS) & 1) ^ 1));
+        mbar_arrive_expect_tx(&full[s], (uint32_t)(nb * MT * DF_A_BYTES));
+        uint8_t* sa = tiles + (size_t)s * STAGE;
+        for (int i = 0; i < nb; ++i)
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_2d(sa + (i * MT + mt) * DF_A_BYTES, &tmS, &full[s], n0 + (j0 + i) * TC_BK, bc * p.nlat + lat0 + mt * 128);
+      }
+    }
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((INV ? 1u : 0u) << 15) | ((uint32_t)(DF_BN >> 3) << 17) |
@@ -142,6 +167,28 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           tc_mma_tf32(tmem_base + mt * DF_BN, adesc, make_smem_desc(sb + 32 * k, 16, 1024), idesc, (kb | k) ? 1u : 0u);
         }
       tc_commit(&empty[s]);
+    }
+    if (INV && p.skip_tma) {
+      const uint32_t idesc_s = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(32 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t id_addr = base + NS * STAGE;
+      mbar_wait_bounded(id_full, 0);
+      constexpr int SPS = STAGE / (MT * DF_A_BYTES);
+      const int nsk = (min(DF_BN, p.nlon - n0) + TC_BK - 1) / TC_BK;
+      for (int j0 = 0, u = 0; j0 < nsk; j0 += SPS, ++u) {
+        const int kc = p.nkb + u, s = kc % NS;
+        const int nb = min(SPS, nsk - j0);
+        mbar_wait_bounded(&full[s], (uint32_t)((kc / NS) & 1));
+        tc_fence_after();
+        const uint32_t sa = base + (uint32_t)s * STAGE;
+        for (int i = 0; i < nb; ++i)
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int k = 0; k < TC_BK / 8; ++k)
+              tc_mma_tf32(tmem_base + mt * DF_BN + (j0 + i) * TC_BK, make_smem_desc(sa + (i * MT + mt) * DF_A_BYTES + 32 * k, 16, 1024),
+                          make_smem_desc(id_addr + 32 * k, 16, 1024), idesc_s, 1u);
+        tc_commit(&empty[s]);
+      }
     }
     tc_commit(tmem_full);
   }
@@ -207,7 +254,7 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     float lsum = 0.0f, lsq = 0.0f;
     const size_t plane = (size_t)bc * p.nlat;
     const int ncol = min(DF_BN, p.nlon - n0);             // multiple of 4 (nlon % 4 == 0)
-    const bool has_skip = p.skip != nullptr;
+    const bool has_skip = p.skip != nullptr && !p.skip_tma;
 #pragma unroll 1
     for (int pass = 0; pass < MT * (DF_BN / SW); ++pass) {
       const int mt = pass / (DF_BN / SW), hc = pass % (DF_BN / SW);
@@ -349,8 +396,9 @@ static int make_map_5d(CUtensorMap* tm, const float* base, const cuuint64_t dims
 }
 
 template <bool INV, int MT, int NS>
-static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const DftParams& prm, dim3 grid, cudaStream_t st) {
-  constexpr int smem = NS * (MT * DF_A_BYTES + DF_B_BYTES) + 1024 + 512;
+static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmS, const CUtensorMap& tmI, const DftParams& prm,
+                      dim3 grid, cudaStream_t st) {
+  constexpr int smem = NS * (MT * DF_A_BYTES + DF_B_BYTES) + 4096 + 1024 + 512;
   auto kern = dft_tc_kernel<INV, MT, NS>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   static const bool trace_on = getenv("MSFNO_DFT_TRACE") != nullptr;
@@ -361,7 +409,7 @@ static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const DftP
     MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 512 * 8 * sizeof(long long), st));
     prm2.trace = d_trace;
   }
-  MSFNO_CUDA_OK(launch_pdl(kern, grid, dim3(256), smem, st, tmA, tmB, prm2));
+  MSFNO_CUDA_OK(launch_pdl(kern, grid, dim3(256), smem, st, tmA, tmB, tmS, tmI, prm2));
   if (trace_on) {
     static long long h[512 * 8];
     MSFNO_CUDA_OK(cudaStreamSynchronize(st));
@@ -392,9 +440,9 @@ int launch_dft_fwd(msfno_plan* p, const float* x, float* Xt, const float* in_sca
   prm.flags = 1;
   prm.dc = (float)(2.0 * M_PI);
   static const int fwd_mt = getenv("MSFNO_DFT_FWD_MT") ? atoi(getenv("MSFNO_DFT_FWD_MT")) : 2;
-  if (p->kpad > 128 && fwd_mt == 2) return launch_dft<false, 2, 3>(tmA, tmB, prm, dim3(1, (p->kpad + 255) / 256, B * C), st);
-  if (p->kpad > 128) return launch_dft<false, 1, 2>(tmA, tmB, prm, dim3(1, (p->kpad + 127) / 128, B * C), st);
-  return launch_dft<false, 1, 2>(tmA, tmB, prm, dim3(1, 1, B * C), st);
+  if (p->kpad > 128 && fwd_mt == 2) return launch_dft<false, 2, 3>(tmA, tmB, tmA, tmB, prm, dim3(1, (p->kpad + 255) / 256, B * C), st);
+  if (p->kpad > 128) return launch_dft<false, 1, 2>(tmA, tmB, tmA, tmB, prm, dim3(1, (p->kpad + 127) / 128, B * C), st);
+  return launch_dft<false, 1, 2>(tmA, tmB, tmA, tmB, prm, dim3(1, 1, B * C), st);
 }
 
 int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, int act_flags, double* stats, int B, int C,
@@ -417,9 +465,28 @@ int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, 
   prm.flags = act_flags;
   const int tilesN = (p->nlon + DF_BN - 1) / DF_BN;
   static const int inv_mt = getenv("MSFNO_DFT_INV_MT") ? atoi(getenv("MSFNO_DFT_INV_MT")) : 1;   // 1: 128-row tiles, two CTAs per SM overlap each other's load / MMA / store phases (faster than one 256-row tile per SM)
-  if (p->nlat > 128 && inv_mt == 2) return launch_dft<true, 2, 3>(tmA, tmB, prm, dim3(tilesN, (p->nlat + 255) / 256, B * C), st);
-  if (p->nlat > 128) return launch_dft<true, 1, 2>(tmA, tmB, prm, dim3(tilesN, (p->nlat + 127) / 128, B * C), st);
-  return launch_dft<true, 1, 2>(tmA, tmB, prm, dim3(tilesN, 1, B * C), st);
+  // skip operand on the tensor cores: TMA-able tensor (16-byte aligned rows) and the shared identity block
+  CUtensorMap tmS = tmB, tmI = tmB;
+  static float* d_ident = nullptr;
+  static std::once_flag id_once;
+  static cudaError_t id_err = cudaSuccess;
+  std::call_once(id_once, [] {
+    float h[32 * 32] = {0};
+    for (int i = 0; i < 32; ++i) h[i * 32 + i] = 1.0f;
+    id_err = cudaMalloc(&d_ident, sizeof(h));
+    if (id_err == cudaSuccess) id_err = cudaMemcpy(d_ident, h, sizeof(h), cudaMemcpyHostToDevice);
+  });
+  static const bool skip_lsu = getenv("MSFNO_DFT_SKIP_LSU") != nullptr;
+  if (skip && !skip_lsu && id_err == cudaSuccess && d_ident && (reinterpret_cast<uintptr_t>(skip) & 15) == 0) {
+    rc = make_map(&tmS, skip, (long long)B * C * p->nlat, p->nlon, p->nlon, 128);
+    if (rc) return rc;
+    rc = make_map(&tmI, d_ident, 32, 32, 32, 32);
+    if (rc) return rc;
+    prm.skip_tma = 1;
+  }
+  if (p->nlat > 128 && inv_mt == 2) return launch_dft<true, 2, 3>(tmA, tmB, tmS, tmI, prm, dim3(tilesN, (p->nlat + 255) / 256, B * C), st);
+  if (p->nlat > 128) return launch_dft<true, 1, 2>(tmA, tmB, tmS, tmI, prm, dim3(tilesN, (p->nlat + 127) / 128, B * C), st);
+  return launch_dft<true, 1, 2>(tmA, tmB, tmS, tmI, prm, dim3(tilesN, 1, B * C), st);
 }
 
 }  // namespace msfno
