@@ -67,6 +67,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m0 = tm * TC_BM, n0 = tn * TC_BN;
   if (m0 >= grp.M || n0 >= grp.N) return;  // uniform for the CTA, before any barrier / allocation
   pdl_trigger();
+  const long long t_start = clock64();
+  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
@@ -97,6 +99,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // the prologue above overlapped the previous kernel; its outputs are visible from here on
+  if (p.trace && threadIdx.x == 0 && cta_lin < 1024) p.trace[cta_lin * 8 + 1] = clock64() - t_start;
 
   if (nkb > 0) {
     if (warp == 0 && lane == 0) {
@@ -162,6 +165,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (nkb > 0) {
       mbar_wait_bounded(tmem_full, 0);
       tc_fence_after();
+      if (p.trace && threadIdx.x == 0 && cta_lin < 1024) p.trace[cta_lin * 8 + 2] = clock64() - t_start;
     }
     float* drow = p.D + grp.d_off + (long long)row * p.ldd;
     const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
@@ -215,9 +219,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (p.relu_even && !(j & 1)) v[j] = fmaxf(v[j], 0.f);
           if (p.round_tf32) v[j] = round_to_tf32(v[j]);
         }
-        if (full_vec) {   // all lanes take part: rows beyond M are masked inside
+        if (vec) {   // all lanes take part: rows beyond M and columns beyond N are masked inside
           store_block_transposed(v, reinterpret_cast<float*>(tiles) + warp * (32 * 36),
-                                 p.D + grp.d_off + (long long)(m0 + q * 32) * p.ldd + gn, p.ldd, grp.M - (m0 + q * 32), lane);
+                                 p.D + grp.d_off + (long long)(m0 + q * 32) * p.ldd + gn, p.ldd, grp.M - (m0 + q * 32), lane, grp.N - gn);
         } else if (row_ok) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -228,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tc_fence_before();
   }
   __syncthreads();
+  if (p.trace && threadIdx.x == 0 && cta_lin < 1024) p.trace[cta_lin * 8 + 3] = clock64() - t_start;
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TC_BN));
@@ -418,9 +423,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (p.round_tf32) t = round_to_tf32(t);
           v[j] = t;
         }
-        if (full_vec) {   // all lanes take part: rows beyond M are masked inside
+        if (vec) {   // all lanes take part: rows beyond M and columns beyond N are masked inside
           store_block_transposed(v, reinterpret_cast<float*>(tiles) + warp * (32 * 36),
-                                 p.D + grp.d_off + (long long)(m0 + q * 32) * p.ldd + gn, p.ldd, grp.M - (m0 + q * 32), lane);
+                                 p.D + grp.d_off + (long long)(m0 + q * 32) * p.ldd + gn, p.ldd, grp.M - (m0 + q * 32), lane, grp.N - gn);
         } else if (row < grp.M) {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
@@ -531,8 +536,24 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;
   p.tilesM = tilesM;
   dim3 grid(tilesM * p.tilesN, g.ngroups);
+  static const bool trace1_on = getenv("MSFNO_GEMM_TRACE") != nullptr;
+  static long long* d_trace1 = nullptr;
+  if (trace1_on && (long long)grid.x * grid.y <= 1024) {
+    if (!d_trace1) MSFNO_CUDA_OK(cudaMalloc(&d_trace1, 1024 * 8 * sizeof(long long)));
+    MSFNO_CUDA_OK(cudaMemsetAsync(d_trace1, 0, 1024 * 8 * sizeof(long long), st));
+    p.trace = d_trace1;
+  }
   if (bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<true>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
   else MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<false>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+  if (p.trace) {
+    static long long h[1024 * 8];
+    MSFNO_CUDA_OK(cudaStreamSynchronize(st));
+    MSFNO_CUDA_OK(cudaMemcpy(h, d_trace1, sizeof(h), cudaMemcpyDeviceToHost));
+    double a1 = 0, a2 = 0, a3 = 0; int n = 0;
+    for (int i = 0; i < 1024; ++i) if (h[i * 8 + 3]) { a1 += h[i * 8 + 1]; a2 += h[i * 8 + 2]; a3 += h[i * 8 + 3]; ++n; }
+    if (n) fprintf(stderr, "gemm_tc trace grid=(%u,%u) maxM=%d maxN=%d: mean clk since CTA start: prologue %.0f  mainloop_done %.0f  cta_done %.0f  (n=%d)\n",
+                   grid.x, grid.y, g.maxM, g.maxN, a1 / n, a2 / n, a3 / n, n);
+  }
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
