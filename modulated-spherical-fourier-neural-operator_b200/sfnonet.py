@@ -213,7 +213,7 @@ class FourierNeuralOperatorBlock(nn.Module):
                 x = x + self.outer_skip(residual)
         return x
 
-    def _fused(self, x, gamma=None, beta=None, scale=1.0, defer_affine=False, in_stats=None, want_stats=False):
+    def _fused(self, x, gamma=None, beta=None, scale=1.0, defer_affine=False, in_stats=None, want_stats=False, prefilm=False):
         """Inference path with the normalisations / skip / activation / FiLM folded into the transforms and the
         channel MLP run as two fused 1x1-conv GEMMs (msfno_conv1x1_fwd).  With defer_affine=True (a block without
         MLP, i.e. the last one) the un-normalised output and the pending per-plane affine (A, S) are returned so the
@@ -234,6 +234,8 @@ class FourierNeuralOperatorBlock(nn.Module):
         y = self.filter_layer(x, in_scale=A0, in_shift=S0, skip_add=skip, act_gelu=hasattr(self, "act_layer"),
                               stats=stats1)
         A1, S1 = norm_film_coeffs(stats1, self.norm1, B, C, y[0, 0].numel(), gamma, beta, scale)
+        if prefilm:   # training: the caller applies norm1's affine, then FiLM / MLP / skip under autograd
+            return y, A1, S1
         mlp = getattr(self, "mlp", None)
         no_drop = isinstance(self.drop_path, nn.Identity) or not self.training
         if mlp is None and defer_affine and not hasattr(self, "outer_skip"):
@@ -314,6 +316,21 @@ class FourierNeuralOperatorBlock_Filmed(FourierNeuralOperatorBlock):
             scale = float(scale)
         if self._can_fuse(x) and not (gamma.requires_grad and torch.is_grad_enabled()):
             return self._fused(x, gamma, beta, scale)
+        if torch.is_grad_enabled() and x.is_cuda and not x.requires_grad and not any(
+                p.requires_grad for n, p in self.named_parameters() if not n.startswith(("mlp.", "outer_skip"))):
+            # Training with a frozen backbone (reference: train.py freezes everything but the FiLM generator): nothing
+            # before the FiLM op needs a gradient, so norm0 -> filter -> skip -> act -> norm1 statistics run on the fused
+            # inference kernels; only FiLM and what follows it is recorded by autograd.
+            with torch.no_grad():
+                fusable = self._can_fuse(x)
+                if fusable:
+                    y, A1, S1 = self._fused(x, prefilm=True)
+                    xn = plane_affine(y, A1, S1)
+            if fusable:
+                xf = self.film(xn, gamma, beta, scale)
+                if hasattr(self, "mlp"):
+                    xf = self.mlp(xf)
+                return self._tail(xf, x)
         return self._unfused(x, gamma, beta, scale, film=self.film)
 
 
@@ -605,12 +622,15 @@ class FourierNeuralOperatorNet_Filmed(FourierNeuralOperatorNet):
         if self.big_skip:
             residual = x
         with torch.no_grad():
-            if self.checkpointing_encoder:
-                x = checkpoint(self.encoder, x, use_reentrant=False)
+            if self._can_fuse_net(x):
+                x, _ = self._encode_fused(x)        # encoder MLP + pos_embed in one kernel (no gradient flows through it)
             else:
-                x = self.encoder(x)
-            x = x + self.pos_embed
-            x = self.pos_drop(x)
+                if self.checkpointing_encoder:
+                    x = checkpoint(self.encoder, x, use_reentrant=False)
+                else:
+                    x = self.encoder(x)
+                x = x + self.pos_embed
+                x = self.pos_drop(x)
         for i, blk in enumerate(self.blocks):
             if self.cfg.repeat_film or i >= self.num_layers - self.film_layers:
                 film_idx = i - (self.num_layers - self.film_layers)

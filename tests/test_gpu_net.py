@@ -90,6 +90,40 @@ def test_filmed_net_matches_reference(fl):
     assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
 
 
+def test_filmed_net_frozen_backbone_training_shortcut():
+    """Reference training freezes everything but the FiLM generator (train.py): the FiLMed block then runs its pre-FiLM
+    part on the fused no-grad kernels and only FiLM -> decoder is recorded by autograd.  The film-head gradients must
+    match the oracle's (which differentiates the whole graph)."""
+    fl = 1
+    d = torch.load(os.path.join(GOLD, "filmed_fl%d_small.pt" % fl))
+    cfg = dict(d["cfg"])
+    c = _Cfg()
+    c.film_layers, c.batch_size = fl, d["x"].shape[0]
+    mlp_ratio = cfg.pop("mlp_ratio")
+    net = msfno_b200.FourierNeuralOperatorNet_Filmed("cuda", c, mlp_ratio=mlp_ratio, advanced_logging=True,
+                                                     film_layers=fl, model_depth=6, **cfg)
+    cfg["mlp_ratio"] = mlp_ratio
+    sd = _oracle_sd(cfg, "non-linear", d["seed"], film_layers=fl)
+    net = _load(net, sd).cuda().eval()
+    for n, p in net.named_parameters():
+        p.requires_grad_(n.startswith("film_gen"))
+    x, cond = d["x"].cuda(), d["cond"].cuda()
+    y = net(x, cond, d["scale"])
+    assert rel_l2(y, d["y"]) < TOL_FP32
+    gy = torch.randn(d["y"].shape, generator=torch.Generator().manual_seed(1))
+    with msfno_b200.precision.library_scope():
+        y.backward(gy.cuda())
+    sdo = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+    tr = sfno_oracle.Transforms(cfg["img_size"], cfg["scale_factor"])
+    fm = sfno_oracle.film_head(d["cond"], sdo).reshape(x.shape[0], 2, fl, 256)
+    yo = sfno_oracle.sfno_forward(d["x"], sdo, tr, "non-linear", cfg["num_layers"], film_mod=fm, film_layers=fl, scale=d["scale"])
+    yo.backward(gy)
+    got = dict(net.named_parameters())
+    for k in ("film_gen.film_head.net.4.weight", "film_gen.film_head.net.1.weight", "film_gen.film_head.net.4.bias"):
+        assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
+    assert got["decoder.fwd.0.weight"].grad is None
+
+
 def test_weight_caches_survive_address_reuse():
     """Regression: caches of derived weights must be keyed on tensor identity, not on addresses -- a second model built
     after the first one is freed reuses the same device addresses (in a different order) with different values."""
