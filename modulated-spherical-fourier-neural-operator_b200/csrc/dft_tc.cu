@@ -467,17 +467,9 @@ int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, 
   static const int inv_mt = getenv("MSFNO_DFT_INV_MT") ? atoi(getenv("MSFNO_DFT_INV_MT")) : 1;   // 1: 128-row tiles, two CTAs per SM overlap each other's load / MMA / store phases (faster than one 256-row tile per SM)
   // skip operand on the tensor cores: TMA-able tensor (16-byte aligned rows) and the shared identity block
   CUtensorMap tmS = tmB, tmI = tmB;
-  static float* d_ident = nullptr;
-  static std::once_flag id_once;
-  static cudaError_t id_err = cudaSuccess;
-  std::call_once(id_once, [] {
-    float h[32 * 32] = {0};
-    for (int i = 0; i < 32; ++i) h[i * 32 + i] = 1.0f;
-    id_err = cudaMalloc(&d_ident, sizeof(h));
-    if (id_err == cudaSuccess) id_err = cudaMemcpy(d_ident, h, sizeof(h), cudaMemcpyHostToDevice);
-  });
+  const float* d_ident = identity32_device();
   static const bool skip_lsu = getenv("MSFNO_DFT_SKIP_LSU") != nullptr;
-  if (skip && !skip_lsu && id_err == cudaSuccess && d_ident && (reinterpret_cast<uintptr_t>(skip) & 15) == 0) {
+  if (skip && !skip_lsu && d_ident != nullptr && (reinterpret_cast<uintptr_t>(skip) & 15) == 0) {
     rc = make_map(&tmS, skip, (long long)B * C * p->nlat, p->nlon, p->nlon, 128);
     if (rc) return rc;
     rc = make_map(&tmI, d_ident, 32, 32, 32, 32);

@@ -444,17 +444,9 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
   if (rc) return rc;
   // `add` on the tensor cores: needs a TMA-able operand (16-byte aligned, plane stride HW) and the identity block
   CUtensorMap tmAdd = tmX, tmId = tmW2;
-  static float* d_ident = nullptr;   // [32][32] identity, shared by all calls on this device context
-  static std::once_flag id_once;
-  static cudaError_t id_err = cudaSuccess;
-  std::call_once(id_once, [] {
-    float h[32 * 32] = {0};
-    for (int i = 0; i < 32; ++i) h[i * 32 + i] = 1.0f;
-    id_err = cudaMalloc(&d_ident, sizeof(h));
-    if (id_err == cudaSuccess) id_err = cudaMemcpy(d_ident, h, sizeof(h), cudaMemcpyHostToDevice);
-  });
+  const float* d_ident = identity32_device();
   static const bool add_tma_off = getenv("MSFNO_MLP_ADD_LSU") != nullptr;
-  const bool add_tma = add && !add_tma_off && al16(add) && add_bstride % HW == 0 && id_err == cudaSuccess && d_ident;
+  const bool add_tma = add && !add_tma_off && al16(add) && add_bstride % HW == 0 && d_ident != nullptr;
   if (add_tma) {
     rc = make_map(&tmAdd, add, (add_bstride ? (long long)(B - 1) * (add_bstride / HW) : 0) + Cout, HW, HW, TC_BK, true);
     if (rc) return rc;

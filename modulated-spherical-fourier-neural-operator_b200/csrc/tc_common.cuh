@@ -108,6 +108,25 @@ __device__ __forceinline__ void store_block_transposed(const float (&v)[32], flo
   __syncwarp();
 }
 
+// [32][32] fp32 identity in device memory, one per device of this process (operand of the "add by identity MMA" paths
+// of mlp_tc.cu and dft_tc.cu).  Returns nullptr if it cannot be allocated.
+inline const float* identity32_device() {
+  static std::mutex mu;
+  static float* per_dev[64] = {nullptr};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!per_dev[dev]) {
+    float h[32 * 32] = {0};
+    for (int i = 0; i < 32; ++i) h[i * 32 + i] = 1.0f;
+    float* d = nullptr;
+    if (cudaMalloc(&d, sizeof(h)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(d, h, sizeof(h), cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(d); return nullptr; }
+    per_dev[dev] = d;
+  }
+  return per_dev[dev];
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
