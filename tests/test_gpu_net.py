@@ -142,3 +142,19 @@ def test_weight_caches_survive_address_reuse():
         del net
         gc.collect()
         torch.cuda.empty_cache()
+
+
+def test_fold_affine_matches_algebra():
+    """msfno_fold_affine: conv1x1(A*y + S, W) + bias == conv1x1(y, Wb) + bb (norm / FiLM affine folded into the conv)."""
+    from msfno_b200.sfnonet import fold_affine
+    g = torch.Generator().manual_seed(3)
+    B, C, O = 3, 73, 40
+    W = torch.zeros(O, 76)
+    W[:, :C] = torch.randn(O, C, generator=g)
+    A, S, bias = torch.rand(B, C, generator=g) + 0.5, torch.randn(B, C, generator=g), torch.randn(O, generator=g)
+    Wb, bb = fold_affine(W.cuda(), A.cuda(), S.cuda(), bias.cuda())
+    assert rel_l2(Wb[:, :, :C], W[None, :, :C].double() * A[:, None, :].double()) < 1e-6
+    assert float(Wb[:, :, C:].abs().max()) == 0.0
+    assert rel_l2(bb, S.double() @ W[:, :C].double().T + bias.double()) < 1e-6
+    Wb2, bb2 = fold_affine(W.cuda(), A.cuda(), S.cuda(), None)
+    assert rel_l2(bb2, S.double() @ W[:, :C].double().T) < 1e-6

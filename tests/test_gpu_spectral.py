@@ -143,3 +143,44 @@ def test_gemm_nt(M, N, K):
     check(lib.msfno_gemm_nt(ptr(A), K, ptr(Bm), K, ptr(D), N, M, N, K, 0, 0, torch.cuda.current_stream().cuda_stream))
     want = A.double() @ Bm.double().T
     assert rel_l2(D, want) < 1e-6
+
+
+def test_specconv_c_abi_paths_agree():
+    """msfno_specconv_fwd / bwd_x / bwd_w through the C ABI: the TMA-ring kernels (workspace given) and the
+    register-load fallback (ws = NULL) against the complex einsum of contractions.py:37-41 and its adjoints."""
+    from msfno_b200._lib import check, lib, ptr
+    from msfno_b200.sht import relayout
+    from msfno_b200 import _lib
+    B, C = 3, 8
+    sht = msfno_b200.RealSHT(120, 240, lmax=120, mmax=121, grid="legendre-gauss").float().cuda()
+    plan = sht._get_plan(torch.device("cuda:0"))
+    g = torch.Generator().manual_seed(11)
+    a = torch.randn(B, C, 120, 121, dtype=torch.complex64, generator=g)
+    gy = torch.randn(B, C, 120, 121, dtype=torch.complex64, generator=g)
+    ii, jj = torch.tril_indices(120, 121)
+    a, gy = a * 0, gy * 0 + 0 * a  # keep shapes; fill only the tril modes (the packed layouts store l >= m only)
+    a[..., ii, jj] = torch.randn(B, C, len(ii), dtype=torch.complex64, generator=g)
+    gy[..., ii, jj] = torch.randn(B, C, len(ii), dtype=torch.complex64, generator=g)
+    w = torch.randn(C, C, len(ii), 2, generator=g)
+    wc = torch.view_as_complex(w)
+    want = torch.einsum("bin,kin->bkn", a[..., ii, jj].to(torch.complex128), wc.to(torch.complex128))
+    want_ga = torch.einsum("bkn,kin->bin", gy[..., ii, jj].to(torch.complex128), wc.conj().to(torch.complex128))
+    want_gw = torch.einsum("bkn,bin->kin", gy[..., ii, jj].to(torch.complex128), a[..., ii, jj].conj().to(torch.complex128))
+    st = torch.cuda.current_stream().cuda_stream
+    a_pm = relayout(torch.view_as_real(a).contiguous().cuda(), sht, _lib.LAYOUT_STD, _lib.LAYOUT_PM, B, C)
+    g_pm = relayout(torch.view_as_real(gy).contiguous().cuda(), sht, _lib.LAYOUT_STD, _lib.LAYOUT_PM, B, C)
+    wd = w.cuda()
+    for use_ws in (True, False):
+        ws = torch.empty(lib.msfno_specconv_ws_floats(plan.h, B, C, C), device="cuda") if use_ws else None
+        out = torch.full((B, plan.P, 2 * C), float("nan"), device="cuda")
+        ga = torch.full((B, plan.P, 2 * C), float("nan"), device="cuda")
+        gw = torch.full_like(wd, float("nan"))
+        check(lib.msfno_specconv_fwd(plan.h, ptr(a_pm), ptr(wd), ptr(out), ptr(ws), B, C, C, st))
+        check(lib.msfno_specconv_bwd_x(plan.h, ptr(g_pm), ptr(wd), ptr(ga), ptr(ws), B, C, C, st))
+        check(lib.msfno_specconv_bwd_w(plan.h, ptr(a_pm), ptr(g_pm), ptr(gw), ptr(ws), B, C, C, st))
+        got = torch.view_as_complex(relayout(out, sht, _lib.LAYOUT_PM, _lib.LAYOUT_STD, B, C))[..., ii, jj]
+        got_ga = torch.view_as_complex(relayout(ga, sht, _lib.LAYOUT_PM, _lib.LAYOUT_STD, B, C))[..., ii, jj]
+        assert torch.isfinite(out).all() and torch.isfinite(ga).all() and torch.isfinite(gw).all()
+        assert rel_l2(torch.view_as_real(got), torch.view_as_real(want)) < TOL_FP32
+        assert rel_l2(torch.view_as_real(got_ga), torch.view_as_real(want_ga)) < TOL_FP32
+        assert rel_l2(gw, torch.view_as_real(want_gw)) < TOL_FP32
