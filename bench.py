@@ -259,9 +259,9 @@ def dominant_kernel_roofline(args, net, dev, pk):
             by = 4.0 * IMG[0] * IMG[1] * (net.in_chans + 2 * EMBED)   # input + pos_embed read, output written, once each
             ach = by / (ms * 1e-3) / 1e9
             return {"kernel": "mlp_tc_kernel (fused encoder MLP 73->256->256 + pos_embed, hidden tile in TMEM; 1 of 13 launches per step)",
-                    "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": 2.388e9,
+                    "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": 2.386e9,
                     "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this launch, "
-                                      "profiles/r01_ncu_mlp_tc_v2_raw.csv",
+                                      "profiles/r01_ncu_final_raw.csv",
                     "peak_source": "%s hbm_gbs" % pk["src"], "ms_per_launch": ms, "algorithmic_bytes": by, "stages": stages}
         return {"kernel": "gemm (spectral complex-MLP hidden layer, M=7260 modes, N=K=1024 real)", "bound": "tensor",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 35.5e6,
