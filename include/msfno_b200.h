@@ -162,7 +162,8 @@ size_t msfno_specattn_ws_floats(const msfno_plan* plan, int B, int C, int hidden
 int msfno_specattn_fwd(const msfno_plan* plan, const float* a_pm, const float* const* w, int nlayers,
                        const float* wout, float* out_cm, float* ws, int B, int C, int hidden,
                        int precision, void* stream);
-/* g_cm (CM) -> ga_pm (PM); gw[l] / gwout receive the weight gradients in the parameter layout.
+/* g_cm (CM) -> ga_pm (PM); gw[l] / gwout receive the weight gradients in the parameter layout; a NULL entry
+ * (or gwout == NULL) skips that weight gradient -- frozen-backbone training needs only ga_pm.
  * scratch: msfno_specattn_bwd_scratch_floats() floats. */
 size_t msfno_specattn_bwd_scratch_floats(const msfno_plan* plan, int B, int C, int hidden, int nlayers);
 int msfno_specattn_bwd(const msfno_plan* plan, const float* a_pm, const float* g_cm, const float* ws,

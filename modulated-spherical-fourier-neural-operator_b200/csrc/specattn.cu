@@ -151,7 +151,8 @@ int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* cons
 
 int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm, const float* ws, float* ga_pm,
                        float* const* gw, float* gwout, float* scratch, int nl, int B, int C, int hid, void* stream) {
-  if (!p || !a_pm || !g_cm || !ws || !ga_pm || !gw || !gwout || !scratch || nl < 1 || nl > 16)
+  // gwout and the entries of gw may be NULL: that weight gradient is not wanted (frozen backbone) and its GEMM is skipped
+  if (!p || !a_pm || !g_cm || !ws || !ga_pm || !gw || !scratch || nl < 1 || nl > 16)
     return record_error(MSFNO_ERR_BAD_SHAPE, "specattn_bwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const AttnWs L = attn_layout(p->P, B, C, hid, nl);
@@ -163,13 +164,15 @@ int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm
 
   // ---- output layer: out[b][ch][p] = sum_k Wout_big[ch][k] h[b*P+p][k]
   // gWout_big[ch][k] = sum_{b,p} g_cm[b][ch][p] * h[b*P+p][k]
-  for (int b = 0; b < B; ++b) {
-    int rc = launch_gemm_single(g_cm + (size_t)b * 2 * C * P, P, 1, hlast + (size_t)b * P * 2 * hid, 2 * hid, 0, gwbig,
-                                2 * hid, 2 * C, 2 * hid, P, 0, nullptr, 0, /*accumulate=*/b > 0, st);
-    if (rc) return rc;
+  if (gwout) {
+    for (int b = 0; b < B; ++b) {
+      int rc = launch_gemm_single(g_cm + (size_t)b * 2 * C * P, P, 1, hlast + (size_t)b * P * 2 * hid, 2 * hid, 0, gwbig,
+                                  2 * hid, 2 * C, 2 * hid, P, 0, nullptr, 0, /*accumulate=*/b > 0, st);
+      if (rc) return rc;
+    }
+    unpack_cweight_grad_kernel<<<(hid * C + 255) / 256, 256, 0, st>>>(gwbig, gwout, hid, C);
+    count_launch();
   }
-  unpack_cweight_grad_kernel<<<(hid * C + 255) / 256, 256, 0, st>>>(gwbig, gwout, hid, C);
-  count_launch();
   // gz_last[b*P+p][k] = relu'(h) * sum_ch g_cm[b][ch][p] * Wout_big[ch][k]
   {
     GemmLaunch g{};
@@ -189,11 +192,13 @@ int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm
     const int cin = (l == 0) ? C : hid;
     const float* in = (l == 0) ? a_pm : ws + L.h[l - 1];
     // gWbig_l[hidcol][cincol] = sum_rows gz[row][hidcol] * in[row][cincol]
-    int rc = launch_gemm_single(gz[cur], 2 * hid, 0, in, 2 * cin, 0, gwbig, 2 * cin, 2 * hid, 2 * cin, rows, 0, nullptr, 0,
-                                0, st);
-    if (rc) return rc;
-    unpack_cweight_grad_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(gwbig, gw[l], cin, hid);
-    count_launch();
+    int rc = MSFNO_OK;
+    if (gw[l]) {
+      rc = launch_gemm_single(gz[cur], 2 * hid, 0, in, 2 * cin, 0, gwbig, 2 * cin, 2 * hid, 2 * cin, rows, 0, nullptr, 0, 0, st);
+      if (rc) return rc;
+      unpack_cweight_grad_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(gwbig, gw[l], cin, hid);
+      count_launch();
+    }
     // g_in[row][cincol] = sum_hidcol gz[row][hidcol] * Wbig_l[hidcol][cincol]  (masked by ReLU of the layer below)
     float* dst = (l == 0) ? ga_pm : gz[cur ^ 1];
     rc = launch_gemm_single(gz[cur], 2 * hid, 1, ws + L.wbig[l], 2 * cin, 0, dst, 2 * cin, rows, 2 * cin, 2 * hid, 0,

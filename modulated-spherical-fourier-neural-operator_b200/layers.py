@@ -144,11 +144,14 @@ class _SpecAttn(torch.autograd.Function):
         plan = ctx.sht._get_plan(g.device)
         g = g.contiguous()
         ga = torch.empty_like(a_pm)
-        gws = [torch.empty_like(w) for w in ws_layers]
-        gwout = torch.empty_like(wout)
+        # weight gradients only where autograd wants them (inputs: a_pm, sht, precision, wout, *ws_layers): with a
+        # frozen backbone the weight-gradient GEMMs, the largest of this backward, are skipped altogether
+        need = ctx.needs_input_grad
+        gwout = torch.empty_like(wout) if need[3] else None
+        gws = [torch.empty_like(w) if need[4 + i] else None for i, w in enumerate(ws_layers)]
         scratch = torch.empty(lib.msfno_specattn_bwd_scratch_floats(plan.h, B, C, hid, nl), dtype=torch.float32,
                               device=g.device)
-        garr = (ctypes.c_void_p * nl)(*[t.data_ptr() for t in gws])
+        garr = (ctypes.c_void_p * nl)(*[t.data_ptr() if t is not None else None for t in gws])
         check(lib.msfno_specattn_bwd(plan.h, ptr(a_pm), ptr(g), ptr(ws), ptr(ga), garr, ptr(gwout), ptr(scratch), nl, B, C,
                                      hid, _stream()), "specattn_bwd")
         return (ga, None, None, gwout, *gws)
