@@ -190,6 +190,8 @@ int msfno_norm_film_coeffs(const double* stats, const float* nw, const float* nb
  * round_tf32), bb[b][o] = sum_c W[o][c] S[b][c] + bias[o] (bias may be NULL).  W: [O][ld] zero-padded rows. */
 int msfno_fold_affine(const float* W, const float* A, const float* S, const float* bias, float* Wb, float* bb,
                       int B, int O, int C, int ld, int round_tf32, void* stream);
+/* out = g * gelu'(h), exact (erf) GELU: activation adjoint of the frozen-weight channel-MLP backward (a14) */
+int msfno_gelu_bwd_mul(const float* g, const float* h, float* out, long long n, void* stream);
 /* y[plane][:] = A[plane]*x[plane][:] + S[plane] */
 int msfno_plane_affine(const float* x, const float* A, const float* S, float* y, int planes, long HW,
                        void* stream);

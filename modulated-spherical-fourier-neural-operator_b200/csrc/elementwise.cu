@@ -130,6 +130,24 @@ __global__ void fold_affine_kernel(const float* __restrict__ W, const float* __r
   }
 }
 
+// out[i] = g[i] * gelu'(h[i])  (exact erf GELU): the activation's adjoint in the frozen-weight MLP backward
+__global__ void gelu_bwd_mul_kernel(const float* __restrict__ g, const float* __restrict__ h, float* __restrict__ out, long long n) {
+  const long long n4 = n >> 2;
+  const bool vec = (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
+  if (vec) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+      const float4 a = __ldcs(reinterpret_cast<const float4*>(g) + i), b = __ldcs(reinterpret_cast<const float4*>(h) + i);
+      __stcs(reinterpret_cast<float4*>(out) + i,
+             make_float4(a.x * gelu_erf_grad(b.x), a.y * gelu_erf_grad(b.y), a.z * gelu_erf_grad(b.z), a.w * gelu_erf_grad(b.w)));
+    }
+    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      out[i] = g[i] * gelu_erf_grad(h[i]);
+  } else {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+      out[i] = g[i] * gelu_erf_grad(h[i]);
+  }
+}
+
 __global__ void norm_film_coeffs_kernel(const double* __restrict__ stats, const float* __restrict__ nw,
                                         const float* __restrict__ nb, const float* __restrict__ gamma,
                                         const float* __restrict__ beta, float scale, float eps, float* __restrict__ A,
@@ -241,6 +259,17 @@ int msfno_fold_affine(const float* W, const float* A, const float* S, const floa
                       int ld, int round_tf32, void* stream) {
   if (!W || !A || !S || !Wb || !bb || B < 1 || O < 1 || C < 1 || ld < C) return record_error(MSFNO_ERR_BAD_SHAPE, "fold_affine: bad argument");
   MSFNO_CUDA_OK(launch_pdl(fold_affine_kernel, dim3(O, B), dim3(128), 0, (cudaStream_t)stream, W, A, S, bias, Wb, bb, O, C, ld, round_tf32));
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+int msfno_gelu_bwd_mul(const float* g, const float* h, float* out, long long n, void* stream) {
+  if (!g || !h || !out || n < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "gelu_bwd_mul: bad argument");
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks < 1) blocks = 1;
+  gelu_bwd_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, h, out, n);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

@@ -28,7 +28,7 @@ from torch.utils.checkpoint import checkpoint
 from . import _lib
 from . import precision as _precision
 from ._lib import check, lib, ptr
-from .conv import mlp1x1, mlp1x1_supported, conv1x1, padded_weight
+from .conv import mlp1x1, mlp1x1_supported, conv1x1, padded_weight, round_tf32
 from .layers import MLP, DropPath, SpectralAttentionS2, SpectralConvS2, trunc_normal_
 from .sht import InverseRealSHT, RealSHT, _stream
 
@@ -99,6 +99,63 @@ def fold_affine(W, A, S, bias):
     check(lib.msfno_fold_affine(ptr(W), ptr(A), ptr(S), ptr(bias), ptr(Wb), ptr(bb), B, O, C, ld,
                                 1 if _precision.get_precision() == "tf32" else 0, _stream()), "fold_affine")
     return Wb, bb
+
+
+class _FrozenMLPFn(torch.autograd.Function):
+    """y = conv1x1(gelu(conv1x1(x, W1a) + conv1x1(x2, W1b) + b1), W2) + b2 for FROZEN weights: the forward is the fused
+    tensor-memory kernel (msfno_mlp1x1_fwd, or two msfno_conv1x1_fwd in the fp32 tier), the backward returns the
+    gradient with respect to x only:  g_x = W1a^T (gelu'(h) * (W2^T g_y)),  h recomputed (not stored: 1 GB per sample
+    at 721x1440).  Replaces, in frozen-backbone training, torch.cat + two cuDNN convolutions with their NCHW<->NHWC
+    layout passes and the autograd graph behind them (sfnonet.py:682-684)."""
+
+    @staticmethod
+    def forward(ctx, x, x2, w1, b1, w2, b2, cin, cin2):
+        E = cin
+        W1a = padded_weight(w1, cols=(0, E))
+        W1b = padded_weight(w1, cols=(E, E + cin2)) if x2 is not None else None
+        W2 = padded_weight(w2)
+        x = x.contiguous().float()
+        x2c = x2.contiguous().float() if x2 is not None else None
+        if mlp1x1_supported(W1a.shape[0], W2.shape[0], x.shape[2] * x.shape[3]) and b1 is not None:
+            y = mlp1x1(x, W1a, cin, b1, W2, b2, x2=x2c, w1b=W1b, cin2=cin2, final=True)
+        else:
+            h = conv1x1(x, W1a, cin, bias=b1, act_gelu=True, x2=x2c, w2=W1b, cin2=cin2)
+            y = conv1x1(h, W2, w2.shape[1], bias=b2, final=True)
+        ctx.save_for_backward(x, x2c if x2c is not None else x.new_empty(0), w1, b1 if b1 is not None else x.new_empty(0), w2)
+        ctx.dims = (cin, cin2, x2 is not None, b1 is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, x2c, w1, b1, w2 = ctx.saved_tensors
+        cin, cin2, has_x2, has_b1 = ctx.dims
+        with torch.no_grad():
+            gy = gy.contiguous().float()
+            W1a = padded_weight(w1, cols=(0, cin))
+            W1b = padded_weight(w1, cols=(cin, cin + cin2)) if has_x2 else None
+            # pre-activation hidden tile, recomputed
+            h = conv1x1(x, W1a, cin, bias=b1 if has_b1 else None, act_gelu=False, x2=x2c if has_x2 else None, w2=W1b, cin2=cin2,
+                        final=True)
+            w2m = w2.detach().reshape(w2.shape[0], -1).float()           # [Cout, Chid]
+            w1m = w1.detach().reshape(w1.shape[0], -1).float()[:, :cin]  # [Chid, cin]
+            W2T = _padded_matrix(w2m.t())                                # [Chid, Cout]
+            W1aT = _padded_matrix(w1m.t())                               # [cin, Chid]
+            gh = conv1x1(gy, W2T, w2m.shape[0], final=True)              # W2^T g_y
+            check(lib.msfno_gelu_bwd_mul(ptr(gh), ptr(h), ptr(gh), gh.numel(), _stream()), "gelu_bwd_mul")
+            if _precision.get_precision() == "tf32":
+                gh = round_tf32(gh)
+            gx = conv1x1(gh, W1aT, w1m.shape[0], final=True)
+        return gx, None, None, None, None, None, None, None
+
+
+def _padded_matrix(m):
+    """[rows, cols] -> contiguous [rows, ceil4(cols)], zero padded, TF32-rounded in the tensor-core tier."""
+    m = m.contiguous()
+    ld = (m.shape[1] + 3) // 4 * 4
+    if ld != m.shape[1]:
+        m = torch.nn.functional.pad(m, (0, ld - m.shape[1]))
+    m = m.contiguous()
+    return round_tf32(m) if _precision.get_precision() == "tf32" else m
 
 
 def plane_affine(x, A, S):
@@ -641,6 +698,14 @@ class FourierNeuralOperatorNet_Filmed(FourierNeuralOperatorNet):
             else:
                 with torch.no_grad():
                     x = blk(x)
+        dec = self.decoder.fwd
+        if (self.big_skip and x.is_cuda and torch.is_grad_enabled() and not self.checkpointing_decoder and len(dec) == 3
+                and isinstance(dec[0], nn.Conv2d) and isinstance(dec[1], nn.GELU)
+                and getattr(dec[1], "approximate", "none") == "none" and isinstance(dec[2], nn.Conv2d)
+                and not any(p.requires_grad for p in self.decoder.parameters()) and not residual.requires_grad):
+            # frozen decoder: fused forward, hand-written input-gradient backward, no concat, no cuDNN layout passes
+            return _FrozenMLPFn.apply(x, residual, dec[0].weight, dec[0].bias, dec[2].weight, dec[2].bias,
+                                      self.embed_dim_sfno, self.in_chans)
         if self.big_skip:
             x = torch.cat((x, residual), dim=1)
         if self.checkpointing_decoder:
