@@ -42,7 +42,19 @@ struct DftParams {
   float dc;                             // forward: factor of the shift on the (m = 0, re) bin = 2 pi
   long long* trace;                     // debug (MSFNO_DFT_TRACE): per-CTA clock stamps, or null
   int skip_tma;                         // inverse: skip is accumulated on the tensor cores (tmS / tmI), the epilogue does not load it
+  int out_tma;                          // inverse: output leaves through per-warp TMA tensor stores (tmO)
 };
+
+// TMA tensor store shared -> global of one 3-D box (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];\n" ::"l"(
+                   reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2, int c3,
                                             int c4) {
@@ -68,7 +80,7 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* t
 template <bool INV, int MT, int NS>
 __global__ void __launch_bounds__(256, 1)
 dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmS,
-              const __grid_constant__ CUtensorMap tmI, DftParams p) {
+              const __grid_constant__ CUtensorMap tmI, const __grid_constant__ CUtensorMap tmO, DftParams p) {
   constexpr int STAGE = MT * DF_A_BYTES + DF_B_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -244,6 +256,74 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
     }
     tc_fence_before();
+  } else if (p.out_tma) {
+    // Output through per-warp TMA tensor stores.  A warp owns 32 latitudes (its TMEM lane quarter) and four 32-column
+    // blocks of each accumulator: TMEM -> registers (activation, rounding, plane statistics: sums do not care which lane
+    // holds which element) -> a private 4 KB tile in the 128-byte-swizzle layout (conflict-free 16-byte writes, row =
+    // lane) -> one 32 x 32 box store by lane 0.  Two tiles per warp alternate, so the next block is read and processed
+    // while the TMA engine drains the previous one; no CTA-wide barrier and no second pass over shared memory (the
+    // staged row-walk epilogue below spent 15 kclk per 128 x 128 block, most of this kernel's time).  The tensor map
+    // [B C][nlat][nlon] clips the ragged last latitude tile and the ragged last column block.
+    float lsum = 0.0f, lsq = 0.0f;
+    uint8_t* wbuf = tiles + warp * 8192;                  // pipeline stages are idle: every MMA has completed
+    int it = 0;
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row0 = lat0 + mt * 128 + q * 32;
+      if (row0 >= p.nlat) break;
+      const bool row_ok = row0 + lane < p.nlat;
+#pragma unroll 1
+      for (int c0 = chalf * 128; c0 < chalf * 128 + 128; c0 += 32) {
+        if (n0 + c0 >= p.nlon) break;
+        uint32_t r[32];
+        MSFNO_DFT_LD32(r, tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * DF_BN + c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (it >= 2) {                                    // the store issued two blocks ago has read this tile
+          if (lane == 0) bulk_wait_read<1>();
+          __syncwarp();
+        }
+        uint8_t* buf = wbuf + (it & 1) * 4096;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = __uint_as_float(r[j]);
+          if (p.flags & 1) t = gelu_tanh3(t);
+          if (p.flags & 2) t = round_to_tf32(t);
+          v[j] = t;
+          const float ts = row_ok ? t : 0.0f;             // columns beyond nlon are exact zeros (zero-filled G rows)
+          lsum += ts;
+          lsq = fmaf(ts, ts, lsq);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          *reinterpret_cast<float4*>(buf + lane * 128 + ((jj ^ (lane & 7)) << 4)) = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tmO, buf, n0 + c0, row0, bc);
+          bulk_commit();
+        }
+        ++it;
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();                   // shared memory must outlive the engine's reads
+    if (p.trace && threadIdx.x == 0 && cta_lin < 512) p.trace[cta_lin * 8 + 4] = clock64() - t_start;
+    tc_fence_before();
+    if (p.stats) {
+      double ds = (double)lsum, dq = (double)lsq;
+      for (int o = 16; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+      }
+      if (lane == 0) { red[2 * warp] = ds; red[2 * warp + 1] = dq; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0.0, sq = 0.0;
+        for (int w = 0; w < 8; ++w) { s += red[2 * w]; sq += red[2 * w + 1]; }
+        atomicAdd(&p.stats[2 * bc], s);
+        atomicAdd(&p.stats[2 * bc + 1], sq);
+      }
+    }
   } else {
     // Staging tile in the (now idle) pipeline stages: all 256 columns when they fit, otherwise two passes of 128
     // (small grids run with a 2-stage ring so that two CTAs share an SM and overlap each other's phases).
@@ -345,6 +425,214 @@ dft_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ full-grid inverse, m-parity split
+// y[lat, j]            = E[lat, j] + O[lat, j]
+// y[lat, j + nlon / 2] = E[lat, j] - O[lat, j],   0 <= j < nlon / 2,
+// E / O = the contributions of the even / odd orders m (cos and sin of 2 pi m (j + nlon/2) / nlon pick up (-1)^m).  Half
+// the MMAs and half the DFT-matrix bytes of the plain product.  The plain kernel at 721 x 1440 moved 384 KB of operands
+// through L2 per 128 KB of output and ran at the L2 throughput (3.5 GB + 1.06 GB at ~12 TB/s); here a CTA keeps the
+// A operand (128 latitudes x all orders of one plane, 128 KB) resident in shared memory for ALL column tiles and streams
+// only the two half matrices: 1.2 bytes of operand per byte of output.
+//
+// Persistent CTAs (one per SM) walk (plane, latitude tile) items.  Warp 0: TMA producer (A blocks once per item, B ring),
+// warp 1: MMA issuer, warps 2-5: epilogue.  Two accumulator pairs (E, O: 2 x 128 columns each, all 512 TMEM columns)
+// alternate between column tiles, so the epilogue of tile t (TMEM -> registers -> E+O / E-O -> swizzled 4 KB tile -> TMA
+// tensor store) runs under the MMAs of tile t+1.
+static constexpr int EO_BN = 128;                 // j columns per tile (two output blocks of 128 columns)
+static constexpr int EO_KB = 4;                   // k blocks of 32 per parity (K padded to 128)
+static constexpr int EO_BLK = 128 * TC_BK * 4;    // 16 KB: operand block, 128 rows x 32 k
+static constexpr int EO_NSB = 4;                  // B ring slots
+static constexpr int EO_EPI_WARPS = 4;
+static constexpr int EO_THREADS = 64 + 32 * EO_EPI_WARPS;
+static constexpr int EO_SMEM = 2 * EO_KB * EO_BLK + EO_NSB * EO_BLK + EO_EPI_WARPS * 8192 + 1024 + 512;
+
+struct EoParams {
+  double* stats;
+  int nlat, half, C;          // half = nlon / 2
+  int ntr, ntn, nitems;       // latitude tiles per plane, column tiles, planes * ntr
+  int flags;                  // bit0 GELU, bit1 round to TF32
+};
+
+__global__ void __launch_bounds__(EO_THREADS, 1)
+idft_eo_kernel(const __grid_constant__ CUtensorMap tmAe, const __grid_constant__ CUtensorMap tmAo, const __grid_constant__ CUtensorMap tmBe,
+               const __grid_constant__ CUtensorMap tmBo, const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
+               EoParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+  uint8_t* a_blk = tiles;                                         // [2 EO_KB] blocks: even k blocks, then odd
+  uint8_t* b_ring = tiles + 2 * EO_KB * EO_BLK;
+  uint8_t* stage = b_ring + EO_NSB * EO_BLK;                      // per epilogue warp: two 4 KB swizzled tiles
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + EO_EPI_WARPS * 8192);
+  uint64_t* a_full = bars;                  // [8]
+  uint64_t* a_empty = bars + 8;             // [8]
+  uint64_t* b_full = bars + 16;             // [EO_NSB]
+  uint64_t* b_empty = bars + 16 + EO_NSB;   // [EO_NSB]
+  uint64_t* t_full = bars + 16 + 2 * EO_NSB;       // [2]
+  uint64_t* t_empty = bars + 18 + 2 * EO_NSB;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20 + 2 * EO_NSB);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 2 * EO_KB; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < EO_NSB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], EO_EPI_WARPS); }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0 && lane == 0) {
+    // ---------------- TMA producer ----------------
+    uint32_t cb = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
+      const int bc = item / p.ntr, lat0 = (item - bc * p.ntr) * 128;
+      const int b = bc / p.C, c = bc - b * p.C;
+      for (int nt = 0; nt < p.ntn; ++nt)
+        for (int kb = 0; kb < 2 * EO_KB; ++kb) {
+          const bool odd = kb >= EO_KB;
+          const int kl = odd ? kb - EO_KB : kb;
+          if (nt == 0) {
+            // A block kb of this item: 128 latitudes x 16 orders of one parity x (re, im); free once the previous item's
+            // last column tile has consumed it
+            mbar_wait_bounded(&a_empty[kb], (uint32_t)((it & 1) ^ 1));
+            mbar_arrive_expect_tx(&a_full[kb], EO_BLK);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              tma_load_5d(a_blk + kb * EO_BLK + j * (TC_BK * 128), odd ? &tmAo : &tmAe, &a_full[kb], lat0 + 32 * j, 0, c, kl * (TC_BK / 2), b);
+          }
+          const uint32_t s = cb % EO_NSB;
+          mbar_wait_bounded(&b_empty[s], ((cb / EO_NSB) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&b_full[s], EO_BLK);
+          tma_load_2d(b_ring + s * EO_BLK, odd ? &tmBo : &tmBe, &b_full[s], kl * TC_BK, nt * EO_BN);
+          ++cb;
+        }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(EO_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    uint32_t cb = 0, t = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
+      for (int nt = 0; nt < p.ntn; ++nt, ++t) {
+        const uint32_t acc = t & 1u;
+        mbar_wait_bounded(&t_empty[acc], ((t >> 1) & 1u) ^ 1u);          // the epilogue has drained this accumulator pair
+        tc_fence_after();
+        for (int kb = 0; kb < 2 * EO_KB; ++kb) {
+          const bool odd = kb >= EO_KB;
+          if (nt == 0) mbar_wait_bounded(&a_full[kb], (uint32_t)(it & 1));
+          const uint32_t s = cb % EO_NSB;
+          mbar_wait_bounded(&b_full[s], (cb / EO_NSB) & 1u);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)kb * EO_BLK;
+          const uint32_t sb = base + (uint32_t)(2 * EO_KB + s) * EO_BLK;
+          const uint32_t d = tmem_base + acc * 256u + (odd ? 128u : 0u);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 8; ++k)
+            tc_mma_tf32(d, make_smem_desc(sa + 1024 * k, TC_BK * 128, 512, 1), make_smem_desc(sb + 32 * k, 16, 1024), idesc,
+                        ((kb & (EO_KB - 1)) | k) ? 1u : 0u);
+          tc_commit(&b_empty[s]);
+          if (nt == p.ntn - 1) tc_commit(&a_empty[kb]);
+          ++cb;
+        }
+        tc_commit(&t_full[acc]);
+      }
+    }
+  } else if (warp >= 2) {
+    // ---------------- epilogue warps: TMEM lane quarter q ----------------
+    const int q = warp & 3;
+    uint8_t* wbuf = stage + (warp - 2) * 8192;
+    uint32_t t = 0;
+    int nst = 0;                                                   // stores issued by this warp
+    for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
+      const int bc = item / p.ntr, lat0 = (item - bc * p.ntr) * 128;
+      const int row0 = lat0 + q * 32;
+      const bool warp_rows = row0 < p.nlat, row_ok = row0 + lane < p.nlat;
+      float lsum = 0.0f, lsq = 0.0f;
+      for (int nt = 0; nt < p.ntn; ++nt, ++t) {
+        const uint32_t acc = t & 1u;
+        mbar_wait_bounded(&t_full[acc], (t >> 1) & 1u);
+        tc_fence_after();
+        const int j0 = nt * EO_BN;
+        if (warp_rows) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < EO_BN; c0 += 32) {
+            if (j0 + c0 >= p.half) break;
+            uint32_t e[32], o[32];
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)c0;
+            MSFNO_DFT_LD32(e, ta);
+            MSFNO_DFT_LD32(o, ta + 128u);
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              if (nst >= 2) {                                      // the store issued two boxes ago has read this tile
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+              }
+              uint8_t* buf = wbuf + (nst & 1) * 4096;
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj) {
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const float ev = __uint_as_float(e[4 * jj + u]), ov = __uint_as_float(o[4 * jj + u]);
+                  float tv = hf ? ev - ov : ev + ov;
+                  if (p.flags & 1) tv = gelu_tanh3(tv);
+                  if (p.flags & 2) tv = round_to_tf32(tv);
+                  v[u] = tv;
+                  const float ts = row_ok ? tv : 0.0f;             // columns beyond nlon / 2 are exact zeros (zero-filled matrix rows)
+                  lsum += ts;
+                  lsq = fmaf(ts, ts, lsq);
+                }
+                *reinterpret_cast<float4*>(buf + lane * 128 + ((jj ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+              }
+              fence_proxy_async();
+              __syncwarp();
+              if (lane == 0) {
+                tma_store_3d(hf ? &tmO2 : &tmO1, buf, j0 + c0, row0, bc);
+                bulk_commit();
+              }
+              ++nst;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&t_empty[acc]);
+      }
+      if (p.stats && warp_rows) {
+        double ds = (double)lsum, dq = (double)lsq;
+        for (int of = 16; of > 0; of >>= 1) {
+          ds += __shfl_xor_sync(0xffffffffu, ds, of);
+          dq += __shfl_xor_sync(0xffffffffu, dq, of);
+        }
+        if (lane == 0) {
+          atomicAdd(&p.stats[2 * bc], ds);
+          atomicAdd(&p.stats[2 * bc + 1], dq);
+        }
+      }
+    }
+    if (lane == 0) bulk_wait_read<0>();                            // shared memory must outlive the engine's reads
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 static float host_round_tf32(float x) {
   uint32_t u;
@@ -396,8 +684,8 @@ static int make_map_5d(CUtensorMap* tm, const float* base, const cuuint64_t dims
 }
 
 template <bool INV, int MT, int NS>
-static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmS, const CUtensorMap& tmI, const DftParams& prm,
-                      dim3 grid, cudaStream_t st) {
+static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmS, const CUtensorMap& tmI, const CUtensorMap& tmO,
+                      const DftParams& prm, dim3 grid, cudaStream_t st) {
   constexpr int smem = NS * (MT * DF_A_BYTES + DF_B_BYTES) + 4096 + 1024 + 512;
   auto kern = dft_tc_kernel<INV, MT, NS>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -409,7 +697,7 @@ static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
     MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 512 * 8 * sizeof(long long), st));
     prm2.trace = d_trace;
   }
-  MSFNO_CUDA_OK(launch_pdl(kern, grid, dim3(256), smem, st, tmA, tmB, tmS, tmI, prm2));
+  MSFNO_CUDA_OK(launch_pdl(kern, grid, dim3(256), smem, st, tmA, tmB, tmS, tmI, tmO, prm2));
   if (trace_on) {
     static long long h[512 * 8];
     MSFNO_CUDA_OK(cudaStreamSynchronize(st));
@@ -440,13 +728,91 @@ int launch_dft_fwd(msfno_plan* p, const float* x, float* Xt, const float* in_sca
   prm.flags = 1;
   prm.dc = (float)(2.0 * M_PI);
   static const int fwd_mt = getenv("MSFNO_DFT_FWD_MT") ? atoi(getenv("MSFNO_DFT_FWD_MT")) : 2;
-  if (p->kpad > 128 && fwd_mt == 2) return launch_dft<false, 2, 3>(tmA, tmB, tmA, tmB, prm, dim3(1, (p->kpad + 255) / 256, B * C), st);
-  if (p->kpad > 128) return launch_dft<false, 1, 2>(tmA, tmB, tmA, tmB, prm, dim3(1, (p->kpad + 127) / 128, B * C), st);
-  return launch_dft<false, 1, 2>(tmA, tmB, tmA, tmB, prm, dim3(1, 1, B * C), st);
+  if (p->kpad > 128 && fwd_mt == 2) return launch_dft<false, 2, 3>(tmA, tmB, tmA, tmB, tmA, prm, dim3(1, (p->kpad + 255) / 256, B * C), st);
+  if (p->kpad > 128) return launch_dft<false, 1, 2>(tmA, tmB, tmA, tmB, tmA, prm, dim3(1, (p->kpad + 127) / 128, B * C), st);
+  return launch_dft<false, 1, 2>(tmA, tmB, tmA, tmB, tmA, prm, dim3(1, 1, B * C), st);
+}
+
+
+// Even / odd halves of the inverse DFT matrix: Geo[par][j][2 mh + ri] = c_m (cos, -sin)(2 pi m j / nlon), m = 2 mh + par,
+// 0 <= j < nlon / 2, K padded to 128 with zeros
+static int dft_eo_build(msfno_plan* p) {
+  if (p->d_dft_inv_eo) return MSFNO_OK;
+  const int nlon = p->nlon, half = nlon / 2;
+  std::vector<float> G((size_t)2 * half * 128, 0.0f);
+  for (int m = 0; m < p->mlim; ++m) {
+    const double cm = (m == 0 || 2 * m == nlon) ? 1.0 : 2.0;
+    const bool real_only = (m == 0 || 2 * m == nlon);
+    const int par = m & 1, mh = m >> 1;
+    for (int j = 0; j < half; ++j) {
+      const double a = 2.0 * M_PI * (double)(((long long)m * j) % nlon) / nlon;
+      float* row = G.data() + ((size_t)par * half + j) * 128;
+      row[2 * mh] = host_round_tf32((float)(cm * cos(a)));
+      row[2 * mh + 1] = real_only ? 0.0f : host_round_tf32((float)(-cm * sin(a)));
+    }
+  }
+  MSFNO_CUDA_OK(cudaMalloc(&p->d_dft_inv_eo, G.size() * sizeof(float)));
+  MSFNO_CUDA_OK(cudaMemcpy(p->d_dft_inv_eo, G.data(), G.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return MSFNO_OK;
+}
+
+static bool dft_eo_supported(const msfno_plan* p, const float* y) {
+  static const bool off = getenv("MSFNO_DFT_NO_EO") != nullptr;
+  return !off && p->nlat > 128 && p->nlon % 8 == 0 && p->mlim + 1 <= 128 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
+}
+
+static int launch_idft_eo(msfno_plan* p, const float* Yt, float* y, int act_flags, double* stats, int B, int C, cudaStream_t st) {
+  int rc = dft_eo_build(p);
+  if (rc) return rc;
+  EncodeTiledFn enc = get_encode();
+  const int half = p->nlon / 2;
+  const int me = (p->mlim + 1) / 2, mo = p->mlim / 2;             // even / odd orders
+  CUtensorMap tmAe, tmAo, tmBe, tmBo, tmO1, tmO2;
+  const cuuint64_t kp = (cuuint64_t)p->kpad;
+  const cuuint64_t strides[4] = {kp * 4, 2 * kp * 4, (cuuint64_t)2 * (2 * C) * kp * 4, (cuuint64_t)p->mlim * 2 * C * kp * 4};
+  const cuuint32_t box[5] = {32, 2, 1, TC_BK / 2, 1};
+  const cuuint64_t dims_e[5] = {kp, 2, (cuuint64_t)C, (cuuint64_t)me, (cuuint64_t)B};
+  const cuuint64_t dims_o[5] = {kp, 2, (cuuint64_t)C, (cuuint64_t)(mo > 0 ? mo : 1), (cuuint64_t)B};
+  rc = make_map_5d(&tmAe, Yt, dims_e, strides, box);
+  if (rc) return rc;
+  rc = make_map_5d(&tmAo, Yt + (size_t)2 * C * p->kpad, dims_o, strides, box);
+  if (rc) return rc;
+  rc = make_map(&tmBe, p->d_dft_inv_eo, half, 128, 128, EO_BN);
+  if (rc) return rc;
+  rc = make_map(&tmBo, p->d_dft_inv_eo + (size_t)half * 128, half, 128, 128, EO_BN);
+  if (rc) return rc;
+  const cuuint64_t odims[3] = {(cuuint64_t)half, (cuuint64_t)p->nlat, (cuuint64_t)B * C};
+  const cuuint64_t ostr[2] = {(cuuint64_t)p->nlon * 4, (cuuint64_t)p->nlat * p->nlon * 4};
+  const cuuint32_t obox[3] = {32, 32, 1};
+  const cuuint32_t oes[3] = {1, 1, 1};
+  for (int h = 0; h < 2; ++h)
+    if (enc(h ? &tmO2 : &tmO1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, y + (size_t)h * half, odims, ostr, obox, oes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled failed (idft_eo output map)");
+  EoParams prm{};
+  prm.stats = stats;
+  prm.nlat = p->nlat; prm.half = half; prm.C = C;
+  prm.ntr = (p->nlat + 127) / 128;
+  prm.ntn = (half + EO_BN - 1) / EO_BN;
+  prm.nitems = B * C * prm.ntr;
+  prm.flags = act_flags;
+  static int n_sm = 0;
+  if (!n_sm) {
+    int dev = 0;
+    MSFNO_CUDA_OK(cudaGetDevice(&dev));
+    MSFNO_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  MSFNO_CUDA_OK(cudaFuncSetAttribute(idft_eo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EO_SMEM));
+  const int grid = prm.nitems < n_sm ? prm.nitems : n_sm;
+  MSFNO_CUDA_OK(launch_pdl(idft_eo_kernel, dim3(grid), dim3(EO_THREADS), EO_SMEM, st, tmAe, tmAo, tmBe, tmBo, tmO1, tmO2, prm));
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
 }
 
 int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, int act_flags, double* stats, int B, int C,
                    cudaStream_t st) {
+  if (skip == nullptr && dft_eo_supported(p, y)) return launch_idft_eo(p, Yt, y, act_flags, stats, B, C, st);
   int rc = dft_tc_build(p);
   if (rc) return rc;
   CUtensorMap tmA, tmB;
@@ -476,9 +842,23 @@ int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, 
     if (rc) return rc;
     prm.skip_tma = 1;
   }
-  if (p->nlat > 128 && inv_mt == 2) return launch_dft<true, 2, 3>(tmA, tmB, tmS, tmI, prm, dim3(tilesN, (p->nlat + 255) / 256, B * C), st);
-  if (p->nlat > 128) return launch_dft<true, 1, 2>(tmA, tmB, tmS, tmI, prm, dim3(tilesN, (p->nlat + 127) / 128, B * C), st);
-  return launch_dft<true, 1, 2>(tmA, tmB, tmS, tmI, prm, dim3(tilesN, 1, B * C), st);
+  // output through TMA tensor stores: [B C][nlat][nlon] map, 32 x 32 boxes in the 128-byte-swizzle layout
+  CUtensorMap tmO = tmB;
+  static const bool out_lsu = getenv("MSFNO_DFT_OUT_LSU") != nullptr;
+  if (!out_lsu && (skip == nullptr || prm.skip_tma) && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+    EncodeTiledFn enc = get_encode();
+    const cuuint64_t odims[3] = {(cuuint64_t)p->nlon, (cuuint64_t)p->nlat, (cuuint64_t)B * C};
+    const cuuint64_t ostr[2] = {(cuuint64_t)p->nlon * 4, (cuuint64_t)p->nlat * p->nlon * 4};
+    const cuuint32_t obox[3] = {32, 32, 1};
+    const cuuint32_t oes[3] = {1, 1, 1};
+    if (enc(&tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, y, odims, ostr, obox, oes, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled failed (dft output map)");
+    prm.out_tma = 1;
+  }
+  if (p->nlat > 128 && inv_mt == 2) return launch_dft<true, 2, 3>(tmA, tmB, tmS, tmI, tmO, prm, dim3(tilesN, (p->nlat + 255) / 256, B * C), st);
+  if (p->nlat > 128) return launch_dft<true, 1, 2>(tmA, tmB, tmS, tmI, tmO, prm, dim3(tilesN, (p->nlat + 127) / 128, B * C), st);
+  return launch_dft<true, 1, 2>(tmA, tmB, tmS, tmI, tmO, prm, dim3(tilesN, 1, B * C), st);
 }
 
 }  // namespace msfno

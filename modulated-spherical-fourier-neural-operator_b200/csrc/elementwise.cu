@@ -185,12 +185,24 @@ __global__ void film_bwd_kernel(const float* __restrict__ gy, const float* __res
   double dg = 0.0, db = 0.0;
   float sg = 0.f, sb = 0.f;
   int cnt = 0;
-  for (long long i = threadIdx.x; i < HW; i += blockDim.x) {
-    const float g = gp[i];
-    sg = fmaf(g, xp[i], sg);
-    sb += g;
-    if (op) op[i] = a * g;
-    if (++cnt == 128) { dg += sg; db += sb; sg = sb = 0.f; cnt = 0; }
+  const bool vec = ((HW & 3) == 0) && (((reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(xp) | reinterpret_cast<uintptr_t>(op)) & 15) == 0);
+  if (vec) {   // 16-byte streaming loads: this pass reads 2 x 8.5 GB at B = 8 (it ran at 1.9 TB/s with 4-byte loads)
+    const long long n4 = HW >> 2;
+    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 g = __ldcs(reinterpret_cast<const float4*>(gp) + i), xv = __ldcs(reinterpret_cast<const float4*>(xp) + i);
+      sg = fmaf(g.x, xv.x, sg); sg = fmaf(g.y, xv.y, sg); sg = fmaf(g.z, xv.z, sg); sg = fmaf(g.w, xv.w, sg);
+      sb += (g.x + g.y) + (g.z + g.w);
+      if (op) __stcs(reinterpret_cast<float4*>(op) + i, make_float4(a * g.x, a * g.y, a * g.z, a * g.w));
+      if (++cnt == 32) { dg += sg; db += sb; sg = sb = 0.f; cnt = 0; }
+    }
+  } else {
+    for (long long i = threadIdx.x; i < HW; i += blockDim.x) {
+      const float g = gp[i];
+      sg = fmaf(g, xp[i], sg);
+      sb += g;
+      if (op) op[i] = a * g;
+      if (++cnt == 128) { dg += sg; db += sb; sg = sb = 0.f; cnt = 0; }
+    }
   }
   dg += sg; db += sb;
   const double tg = block_sum(dg, sh);

@@ -257,7 +257,7 @@ int msfno_plan_destroy(msfno_plan* p) {
   if (!p) return MSFNO_OK;
   cudaFree(p->d_tw); cudaFree(p->d_tw2);
   cudaFree(p->d_scale_rfft); cudaFree(p->d_scale_irfft_adj); cudaFree(p->d_scale_irfft); cudaFree(p->d_scale_rfft_adj);
-  cudaFree(p->d_dft_fwd); cudaFree(p->d_dft_inv);
+  cudaFree(p->d_dft_fwd); cudaFree(p->d_dft_inv); cudaFree(p->d_dft_inv_eo);
   cudaFree(p->d_poff); cudaFree(p->d_n2p); cudaFree(p->d_p2lm);
   cudaFree(p->d_tab_lk); cudaFree(p->d_tab_kl); cudaFree(p->d_flag);
   for (auto& kv : p->groups) cudaFree(kv.second);

@@ -47,6 +47,7 @@ struct msfno_plan {
   int32_t* d_flag = nullptr;          // table validation flag
   float* d_dft_fwd = nullptr;         // tensor-core tier: DFT matrix  [2 mlim][nlon]  (dft_tc.cu, built on first use)
   float* d_dft_inv = nullptr;         //                   inverse DFT [nlon][2 mlim]
+  float* d_dft_inv_eo = nullptr;      //                   inverse DFT split by the parity of m: [2][nlon / 2][128] (idft_eo_kernel)
   // grouped-GEMM descriptors cached per (kind, B, C)
   std::mutex mu;
   std::map<std::vector<int>, msfno::GemmGroup*> groups;  // key: kind, B, C, m_lo, m_hi

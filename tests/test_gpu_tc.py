@@ -243,3 +243,40 @@ def test_sht_isht_tf32_dft_gemm(nlat, nlon, grid, B, C):
             assert rel_l2(y0, o_i(coef.to(torch.complex128))) < TOL_TF32
     finally:
         msfno_b200.set_precision("fp32")
+
+
+@pytest.mark.parametrize("nlat,nlon,B,C,gelu", [(721, 1440, 1, 3, False), (200, 288, 2, 2, True), (130, 320, 1, 5, True),
+                                                 (257, 512, 3, 1, False)])
+def test_isht_tf32_parity_split_kernel(nlat, nlon, B, C, gelu):
+    """Full-grid inverse longitude transform of the TF32 tier (idft_eo_kernel: even / odd orders accumulated separately,
+    y[j] = E + O, y[j + nlon/2] = E - O, persistent CTAs, TMA tensor stores) against the oracle's einsum + irfft,
+    with the GELU / plane-statistics epilogue, ragged last latitude and column tiles, and several items per CTA;
+    MSFNO_DFT_NO_EO's plain product must agree with it to rounding."""
+    from msfno_b200 import _lib
+    from msfno_b200.sht import relayout
+    L, M = 120, 121
+    o_s = th_shim.RealSHT(nlat, nlon, lmax=L, mmax=M, grid="equiangular").float()
+    o_i = th_shim.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid="equiangular").float()
+    i = msfno_b200.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid="equiangular").float().cuda()
+    g = torch.Generator().manual_seed(nlat + nlon)
+    x = torch.randn(B, C, nlat, nlon, generator=g)
+    msfno_b200.set_precision("tf32")
+    try:
+        with torch.no_grad():
+            coef = o_s(x.double()).to(torch.complex64)
+            cm = relayout(torch.view_as_real(coef).contiguous().cuda(), i, _lib.LAYOUT_STD, _lib.LAYOUT_CM, B, C)
+            stats = torch.zeros(B * C, 2, dtype=torch.float64, device="cuda")
+            y = i.inverse_packed(cm, act_gelu=gelu, stats=stats)
+            ref = o_i(coef.to(torch.complex128))
+            if gelu:
+                ref = torch.nn.functional.gelu(ref)
+            assert torch.isfinite(y).all()
+            assert rel_l2(y, ref) < TOL_TF32
+            # both halves of the longitude circle separately (a wrong sign of the odd part shows up in one of them only)
+            assert rel_l2(y[..., : nlon // 2], ref[..., : nlon // 2]) < TOL_TF32
+            assert rel_l2(y[..., nlon // 2:], ref[..., nlon // 2:]) < TOL_TF32
+            yd = y.double().reshape(B * C, -1)
+            assert torch.allclose(stats[:, 0], yd.sum(1), rtol=1e-6, atol=1e-3)
+            assert torch.allclose(stats[:, 1], (yd * yd).sum(1), rtol=1e-6)
+    finally:
+        msfno_b200.set_precision("fp32")
