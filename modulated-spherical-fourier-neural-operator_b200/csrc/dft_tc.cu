@@ -443,17 +443,31 @@ static constexpr int EO_BN = 128;                 // j columns per tile (two out
 static constexpr int EO_KB = 4;                   // k blocks of 32 per parity (K padded to 128)
 static constexpr int EO_BLK = 128 * TC_BK * 4;    // 16 KB: operand block, 128 rows x 32 k
 static constexpr int EO_NSB = 4;                  // B ring slots
-static constexpr int EO_EPI_WARPS = 4;
+static constexpr int EO_EPI_WARPS = 8;
 static constexpr int EO_THREADS = 64 + 32 * EO_EPI_WARPS;
-static constexpr int EO_SMEM = 2 * EO_KB * EO_BLK + EO_NSB * EO_BLK + EO_EPI_WARPS * 8192 + 1024 + 512;
+static constexpr int EO_SMEM = 2 * EO_KB * EO_BLK + EO_NSB * EO_BLK + EO_EPI_WARPS * 4096 + 1024 + 512;
 
 struct EoParams {
   double* stats;
   int nlat, half, C;          // half = nlon / 2
   int ntr, ntn, nitems;       // latitude tiles per plane, column tiles, planes * ntr
   int flags;                  // bit0 GELU, bit1 round to TF32
+  long long* trace;           // debug (MSFNO_DFT_TRACE): per-CTA wait-time totals of each role, or null
 };
 
+// clock64-bracketed wait: adds the cycles spent to `acc` when tracing
+#define EO_TIMED(acc, stmt)                          \
+  do {                                               \
+    if (p.trace) {                                   \
+      const long long _t0 = clock64();               \
+      stmt;                                          \
+      acc += clock64() - _t0;                        \
+    } else {                                         \
+      stmt;                                          \
+    }                                                \
+  } while (0)
+
+template <int FLAGS>
 __global__ void __launch_bounds__(EO_THREADS, 1)
 idft_eo_kernel(const __grid_constant__ CUtensorMap tmAe, const __grid_constant__ CUtensorMap tmAo, const __grid_constant__ CUtensorMap tmBe,
                const __grid_constant__ CUtensorMap tmBo, const __grid_constant__ CUtensorMap tmO1, const __grid_constant__ CUtensorMap tmO2,
@@ -465,8 +479,8 @@ idft_eo_kernel(const __grid_constant__ CUtensorMap tmAe, const __grid_constant__
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* a_blk = tiles;                                         // [2 EO_KB] blocks: even k blocks, then odd
   uint8_t* b_ring = tiles + 2 * EO_KB * EO_BLK;
-  uint8_t* stage = b_ring + EO_NSB * EO_BLK;                      // per epilogue warp: two 4 KB swizzled tiles
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + EO_EPI_WARPS * 8192);
+  uint8_t* stage = b_ring + EO_NSB * EO_BLK;                      // per epilogue warp: one 4 KB swizzled tile
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage + EO_EPI_WARPS * 4096);
   uint64_t* a_full = bars;                  // [8]
   uint64_t* a_empty = bars + 8;             // [8]
   uint64_t* b_full = bars + 16;             // [EO_NSB]
@@ -495,6 +509,7 @@ idft_eo_kernel(const __grid_constant__ CUtensorMap tmAe, const __grid_constant__
     // ---------------- TMA producer ----------------
     uint32_t cb = 0;
     int it = 0;
+    long long w_be = 0, w_ae = 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
       const int bc = item / p.ntr, lat0 = (item - bc * p.ntr) * 128;
       const int b = bc / p.C, c = bc - b * p.C;
@@ -505,34 +520,37 @@ idft_eo_kernel(const __grid_constant__ CUtensorMap tmAe, const __grid_constant__
           if (nt == 0) {
             // A block kb of this item: 128 latitudes x 16 orders of one parity x (re, im); free once the previous item's
             // last column tile has consumed it
-            mbar_wait_bounded(&a_empty[kb], (uint32_t)((it & 1) ^ 1));
+            EO_TIMED(w_ae, mbar_wait_bounded(&a_empty[kb], (uint32_t)((it & 1) ^ 1)));
             mbar_arrive_expect_tx(&a_full[kb], EO_BLK);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
               tma_load_5d(a_blk + kb * EO_BLK + j * (TC_BK * 128), odd ? &tmAo : &tmAe, &a_full[kb], lat0 + 32 * j, 0, c, kl * (TC_BK / 2), b);
           }
           const uint32_t s = cb % EO_NSB;
-          mbar_wait_bounded(&b_empty[s], ((cb / EO_NSB) & 1u) ^ 1u);
+          EO_TIMED(w_be, mbar_wait_bounded(&b_empty[s], ((cb / EO_NSB) & 1u) ^ 1u));
           mbar_arrive_expect_tx(&b_full[s], EO_BLK);
           tma_load_2d(b_ring + s * EO_BLK, odd ? &tmBo : &tmBe, &b_full[s], kl * TC_BK, nt * EO_BN);
           ++cb;
         }
     }
+    if (p.trace) { p.trace[blockIdx.x * 8 + 6] = w_be; p.trace[blockIdx.x * 8 + 7] = w_ae; }
   } else if (warp == 1 && lane == 0) {
     // ---------------- MMA issuer ----------------
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | ((uint32_t)(EO_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     uint32_t cb = 0, t = 0;
     int it = 0;
+    long long w_te = 0, w_bf = 0, w_af = 0;
+    const long long t_begin = clock64();
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x, ++it) {
       for (int nt = 0; nt < p.ntn; ++nt, ++t) {
         const uint32_t acc = t & 1u;
-        mbar_wait_bounded(&t_empty[acc], ((t >> 1) & 1u) ^ 1u);          // the epilogue has drained this accumulator pair
+        EO_TIMED(w_te, mbar_wait_bounded(&t_empty[acc], ((t >> 1) & 1u) ^ 1u));   // the epilogue has drained this accumulator pair
         tc_fence_after();
         for (int kb = 0; kb < 2 * EO_KB; ++kb) {
           const bool odd = kb >= EO_KB;
-          if (nt == 0) mbar_wait_bounded(&a_full[kb], (uint32_t)(it & 1));
+          if (nt == 0) EO_TIMED(w_af, mbar_wait_bounded(&a_full[kb], (uint32_t)(it & 1)));
           const uint32_t s = cb % EO_NSB;
-          mbar_wait_bounded(&b_full[s], (cb / EO_NSB) & 1u);
+          EO_TIMED(w_bf, mbar_wait_bounded(&b_full[s], (cb / EO_NSB) & 1u));
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)kb * EO_BLK;
           const uint32_t sb = base + (uint32_t)(2 * EO_KB + s) * EO_BLK;
@@ -548,70 +566,88 @@ idft_eo_kernel(const __grid_constant__ CUtensorMap tmAe, const __grid_constant__
         tc_commit(&t_full[acc]);
       }
     }
+    if (p.trace) {
+      p.trace[blockIdx.x * 8 + 0] = clock64() - t_begin;
+      p.trace[blockIdx.x * 8 + 1] = w_te; p.trace[blockIdx.x * 8 + 2] = w_bf; p.trace[blockIdx.x * 8 + 3] = w_af;
+    }
   } else if (warp >= 2) {
-    // ---------------- epilogue warps: TMEM lane quarter q ----------------
-    const int q = warp & 3;
-    uint8_t* wbuf = stage + (warp - 2) * 8192;
+    // ---------------- epilogue warps: TMEM lane quarter q, column half ch of every tile ----------------
+    const int q = warp & 3, ch = (warp - 2) >> 2;
+    uint8_t* buf = stage + (warp - 2) * 4096;
     uint32_t t = 0;
-    int nst = 0;                                                   // stores issued by this warp
+    bool pending = false;                                          // a store of this warp may still be reading buf
+    long long w_tf = 0, w_rd = 0;
     for (int item = blockIdx.x; item < p.nitems; item += gridDim.x) {
       const int bc = item / p.ntr, lat0 = (item - bc * p.ntr) * 128;
       const int row0 = lat0 + q * 32;
-      const bool warp_rows = row0 < p.nlat, row_ok = row0 + lane < p.nlat;
-      float lsum = 0.0f, lsq = 0.0f;
+      const bool warp_rows = row0 < p.nlat, row_ok = row0 + lane < p.nlat, all_rows = row0 + 32 <= p.nlat;
+      float ls[4] = {0.f, 0.f, 0.f, 0.f}, lq[4] = {0.f, 0.f, 0.f, 0.f};
       for (int nt = 0; nt < p.ntn; ++nt, ++t) {
         const uint32_t acc = t & 1u;
-        mbar_wait_bounded(&t_full[acc], (t >> 1) & 1u);
+        EO_TIMED(w_tf, mbar_wait_bounded(&t_full[acc], (t >> 1) & 1u));
         tc_fence_after();
         const int j0 = nt * EO_BN;
+        bool released = false;
         if (warp_rows) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < EO_BN; c0 += 32) {
+          for (int cc = 0; cc < 2; ++cc) {
+            const int c0 = ch * (EO_BN / 2) + cc * 32;
             if (j0 + c0 >= p.half) break;
             uint32_t e[32], o[32];
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256u + (uint32_t)c0;
             MSFNO_DFT_LD32(e, ta);
             MSFNO_DFT_LD32(o, ta + 128u);
             asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+            if (cc == 1 || j0 + c0 + 32 >= p.half) {               // last read of this accumulator pair: hand it back to the MMA warp now
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&t_empty[acc]);
+              released = true;
+            }
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-              if (nst >= 2) {                                      // the store issued two boxes ago has read this tile
-                if (lane == 0) bulk_wait_read<1>();
-                __syncwarp();
-              }
-              uint8_t* buf = wbuf + (nst & 1) * 4096;
+              float v[32];
 #pragma unroll
-              for (int jj = 0; jj < 8; ++jj) {
-                float v[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  const float ev = __uint_as_float(e[4 * jj + u]), ov = __uint_as_float(o[4 * jj + u]);
-                  float tv = hf ? ev - ov : ev + ov;
-                  if (p.flags & 1) tv = gelu_tanh3(tv);
-                  if (p.flags & 2) tv = round_to_tf32(tv);
-                  v[u] = tv;
-                  const float ts = row_ok ? tv : 0.0f;             // columns beyond nlon / 2 are exact zeros (zero-filled matrix rows)
-                  lsum += ts;
-                  lsq = fmaf(ts, ts, lsq);
-                }
-                *reinterpret_cast<float4*>(buf + lane * 128 + ((jj ^ (lane & 7)) << 4)) = make_float4(v[0], v[1], v[2], v[3]);
+              for (int j = 0; j < 32; ++j) {
+                const float ev = __uint_as_float(e[j]), ov = __uint_as_float(o[j]);
+                float tv = hf ? ev - ov : ev + ov;
+                if (FLAGS & 1) tv = gelu_tanh3(tv);
+                if (FLAGS & 2) tv = round_to_tf32(tv);
+                v[j] = tv;
               }
+              // plane statistics (four independent chains); columns beyond nlon / 2 are exact zeros (zero-filled matrix
+              // rows), latitudes beyond nlat hold whatever the workspace held: masked unless the whole warp is inside
+              if (all_rows) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { ls[j & 3] += v[j]; lq[j & 3] = fmaf(v[j], v[j], lq[j & 3]); }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { const float ts = row_ok ? v[j] : 0.0f; ls[j & 3] += ts; lq[j & 3] = fmaf(ts, ts, lq[j & 3]); }
+              }
+              if (pending) {                                       // the previous store of this warp has read the tile
+                EO_TIMED(w_rd, if (lane == 0) bulk_wait_read<0>(); __syncwarp());
+              }
+#pragma unroll
+              for (int jj = 0; jj < 8; ++jj)
+                *reinterpret_cast<float4*>(buf + lane * 128 + ((jj ^ (lane & 7)) << 4)) = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
               fence_proxy_async();
               __syncwarp();
               if (lane == 0) {
                 tma_store_3d(hf ? &tmO2 : &tmO1, buf, j0 + c0, row0, bc);
                 bulk_commit();
               }
-              ++nst;
+              pending = true;
             }
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[acc]);
+        if (!released) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&t_empty[acc]);
+        }
       }
       if (p.stats && warp_rows) {
-        double ds = (double)lsum, dq = (double)lsq;
+        double ds = (double)((ls[0] + ls[1]) + (ls[2] + ls[3])), dq = (double)((lq[0] + lq[1]) + (lq[2] + lq[3]));
         for (int of = 16; of > 0; of >>= 1) {
           ds += __shfl_xor_sync(0xffffffffu, ds, of);
           dq += __shfl_xor_sync(0xffffffffu, dq, of);
@@ -623,6 +659,7 @@ idft_eo_kernel(const __grid_constant__ CUtensorMap tmAe, const __grid_constant__
       }
     }
     if (lane == 0) bulk_wait_read<0>();                            // shared memory must outlive the engine's reads
+    if (p.trace && warp == 2 && lane == 0) { p.trace[blockIdx.x * 8 + 4] = w_tf; p.trace[blockIdx.x * 8 + 5] = w_rd; }
   }
   __syncwarp();
   tc_fence_before();
@@ -802,9 +839,28 @@ static int launch_idft_eo(msfno_plan* p, const float* Yt, float* y, int act_flag
     MSFNO_CUDA_OK(cudaGetDevice(&dev));
     MSFNO_CUDA_OK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
-  MSFNO_CUDA_OK(cudaFuncSetAttribute(idft_eo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EO_SMEM));
+  auto kern = (act_flags & 3) == 0 ? idft_eo_kernel<0> : (act_flags & 3) == 1 ? idft_eo_kernel<1> : (act_flags & 3) == 2 ? idft_eo_kernel<2> : idft_eo_kernel<3>;
+  MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, EO_SMEM));
   const int grid = prm.nitems < n_sm ? prm.nitems : n_sm;
-  MSFNO_CUDA_OK(launch_pdl(idft_eo_kernel, dim3(grid), dim3(EO_THREADS), EO_SMEM, st, tmAe, tmAo, tmBe, tmBo, tmO1, tmO2, prm));
+  static const bool trace_on = getenv("MSFNO_DFT_TRACE") != nullptr;
+  static long long* d_trace = nullptr;
+  if (trace_on) {
+    if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 512 * 8 * sizeof(long long)));
+    MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 512 * 8 * sizeof(long long), st));
+    prm.trace = d_trace;
+  }
+  MSFNO_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(EO_THREADS), EO_SMEM, st, tmAe, tmAo, tmBe, tmBo, tmO1, tmO2, prm));
+  if (trace_on) {
+    static long long h[512 * 8];
+    MSFNO_CUDA_OK(cudaStreamSynchronize(st));
+    MSFNO_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+    double a[8] = {0};
+    const int n = grid < 512 ? grid : 512;
+    for (int i = 0; i < n; ++i) for (int k = 0; k < 8; ++k) a[k] += (double)h[i * 8 + k];
+    fprintf(stderr, "idft_eo trace grid=%d items=%d tiles/item=%d: mean clk per CTA: mma_total %.0f | mma waits: t_empty %.0f b_full %.0f a_full %.0f | "
+                    "epilogue(warp 2) waits: t_full %.0f store_read %.0f | producer waits: b_empty %.0f a_empty %.0f\n",
+            grid, prm.nitems, prm.ntn, a[0] / n, a[1] / n, a[2] / n, a[3] / n, a[4] / n, a[5] / n, a[6] / n, a[7] / n);
+  }
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
