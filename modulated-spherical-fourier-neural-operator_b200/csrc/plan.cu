@@ -183,7 +183,7 @@ unsigned long long msfno_launch_count(void) { return g_launches.load(); }
 
 const char* msfno_build_info(void) {
   return "{\"arch\": \"sm_100a\", \"abi\": 2, \"tiers\": [\"fp32\", \"tf32\"], \"fft\": \"four-step in-register (fp32 tier)\", "
-         "\"tensor_core\": [\"tcgen05 tf32 gemm (cta_group::1 and ::2)\", \"dft gemm\", \"fused mlp (A operand in TMEM)\", \"1x1 conv\"], "
+         "\"tensor_core\": [\"tcgen05 tf32 gemm (cta_group::1 and ::2)\", \"dft gemm\", \"parity-split persistent inverse dft (tma stores)\", \"fused mlp (A operand in TMEM)\", \"1x1 conv\"], "
          "\"streams\": [\"specconv tma ring\"]}";
 }
 
