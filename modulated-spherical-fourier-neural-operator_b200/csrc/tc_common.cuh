@@ -21,6 +21,7 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
 // try_wait in a bounded loop: a faulty descriptor traps (error surfaced to the host) instead of hanging the SM
 __device__ __forceinline__ void mbar_wait_bounded(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
+#pragma unroll 1   // (nvcc otherwise unrolls this poll 64 times at every call site: 4 200 of dft_tc.o's 23 600 SASS lines)
   for (uint32_t it = 0; it < (1u << 24); ++it) {
     uint32_t ok;
     asm volatile(
