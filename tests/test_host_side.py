@@ -147,3 +147,29 @@ def test_fft2d_core_host_emulation(tmp_path):
         goti = run(1, N, M, np.stack([X.real, X.imag], 1))
         refi = np.fft.irfft(X.astype(np.complex128), n=N, norm="forward")
         assert np.linalg.norm(goti - refi) / np.linalg.norm(refi) < 1e-6
+
+
+@pytest.mark.parametrize("nlon,mlim", [(1440, 121), (240, 121), (48, 13), (16, 9)])
+def test_parity_split_inverse_dft_matches_irfft(nlon, mlim):
+    """The algebra idft_eo_kernel (csrc/dft_tc.cu) runs on the tensor cores, restated in numpy: with the orders split by
+    parity, y[j] = E[j] + O[j] and y[j + nlon/2] = E[j] - O[j] for 0 <= j < nlon/2, where E / O are products with the even /
+    odd halves of the inverse DFT matrix c_m (cos, -sin)(2 pi m j / nlon) (c_0 = c_Nyquist = 1, else 2; the imaginary parts
+    of the DC and Nyquist bins do not contribute).  Must equal irfft(X, n=nlon, norm="forward") of the oracle
+    (torch_harmonics.InverseRealSHT) including the ignored Im(DC) / Im(Nyquist)."""
+    rng = np.random.default_rng(nlon + mlim)
+    rows, half = 5, nlon // 2
+    X = rng.standard_normal((rows, mlim)) + 1j * rng.standard_normal((rows, mlim))
+    want = torch.fft.irfft(torch.from_numpy(X), n=nlon, dim=-1, norm="forward").numpy()
+    j = np.arange(half)
+    E, O = np.zeros((rows, half)), np.zeros((rows, half))
+    for m in range(mlim):
+        cm = 1.0 if (m == 0 or 2 * m == nlon) else 2.0
+        ang = 2.0 * np.pi * ((m * j) % nlon) / nlon
+        im = 0.0 if (m == 0 or 2 * m == nlon) else 1.0
+        term = cm * (np.outer(X[:, m].real, np.cos(ang)) - im * np.outer(X[:, m].imag, np.sin(ang)))
+        if m % 2 == 0:
+            E += term
+        else:
+            O += term
+    got = np.concatenate([E + O, E - O], axis=1)
+    assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
