@@ -1,0 +1,70 @@
+"""BASELINE config 4: autoregressive rollout x <- net(x) of an ensemble, members sharded across GPUs with no data-path
+collective (SURVEY.md section 8(d) "Config 4", 8(e) "Ensemble / batch").  Reference loop: MSFNO/Models/sfno/model.py:327-331
+(one forward per 6 h step, output fed back as the next input).
+    python tools/bench_rollout.py [--members 8] [--steps 112] [--batch 1|2|4|8] [--precision tf32|fp32]
+    torchrun --nproc-per-node N ... tools/bench_rollout.py      (each rank rolls out its own --members members)
+The members of a rank are forecast in groups of --batch (one CUDA graph of the batched forward, replayed 112 times per
+group).  Device time is taken with CUDA events around every group's rollout; rank 0 prints one JSON line with the
+member-steps/s of the whole job (max time over ranks) and the per-member rate."""
+import argparse, json, os, sys
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import msfno_b200
+from msfno_b200.graph import GraphedForward
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--members", type=int, default=8, help="ensemble members per GPU (config 4: 64 members over 8 GPUs)")
+    ap.add_argument("--batch", type=int, default=1, help="members forecast together in one batched forward")
+    ap.add_argument("--steps", type=int, default=112, help="6 h steps per member (28 days = 112)")
+    ap.add_argument("--precision", default="tf32")
+    a = ap.parse_args()
+    assert a.members % a.batch == 0, "--members must be a multiple of --batch"
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    msfno_b200.set_precision(a.precision)
+    torch.manual_seed(0)
+    net = msfno_b200.FourierNeuralOperatorNet(dev, None, filter_type="non-linear").to(dev).eval()
+    g = torch.Generator().manual_seed(1000 + rank)
+    members = torch.randn(a.members, 73, 721, 1440, generator=g).to(dev)
+    final = torch.empty_like(members)
+    with msfno_b200.precision.library_scope():
+        gf = GraphedForward(net, members[: a.batch])
+        gf.rollout(members[: a.batch], 2)  # warm-up replays
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(0, a.members, a.batch):
+        final[i : i + a.batch].copy_(gf.rollout(members[i : i + a.batch], a.steps), non_blocking=True)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    finite = torch.tensor([float(torch.isfinite(final).all())], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(finite, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        total = world * a.members * a.steps
+        print(json.dumps({
+            "metric": "sfno_rollout_member_steps_per_sec_721x1440x73", "value": total / (ms.item() * 1e-3), "unit": "member-steps/s",
+            "n_gpus": world, "members_per_gpu": a.members, "batch": a.batch, "steps_per_member": a.steps,
+            "ms_per_member_step": ms.item() / (a.members * a.steps), "rollout_seconds_per_member": ms.item() * 1e-3 / a.members,
+            "wall_ms": ms.item(), "scaling": "weak", "dtype": a.precision, "data": "synthetic (random-init weights: the "
+            "iterated map is not a forecast, only its cost is meaningful)", "output_finite": bool(finite.item()),
+            "config": {"workload": "configs[3]: 112-step autoregressive rollout, ensemble members sharded across GPUs, "
+                                   "no inter-GPU traffic", "filter_type": "non-linear", "cuda_graph": True}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
