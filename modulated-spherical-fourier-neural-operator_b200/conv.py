@@ -83,14 +83,21 @@ def mlp1x1_supported(chid, cout, HW):
 
 
 def mlp1x1(x, w1, cin, b1, w2, b2=None, add=None, x2=None, w1b=None, cin2=0, per_sample_w1=False, per_sample_b1=False,
-           final=False, w1_rounded=False, stats=None):
+           final=False, w1_rounded=False, stats=None, out=None):
     """y = conv1x1(gelu(conv1x1(x, w1) [+ conv1x1(x2, w1b)] + b1), w2) + b2 + add in ONE kernel; the hidden activation
     never reaches HBM.  w1: [Chid, ld] (or [B, Chid, ld]), w1b: [Chid, ld2], w2: [Cout, ld3] zero-padded rows.
-    stats: optional [B*Cout, 2] float64 tensor that receives the plane sums / sums of squares of y."""
+    stats: optional [B*Cout, 2] float64 tensor that receives the plane sums / sums of squares of y.
+    out: optional preallocated [B, Cout, H, W] result.  It may alias x2 (the in-place rollout step): a CTA reads every
+    operand block of a pixel tile before it stores that tile, and no other CTA touches those pixels."""
     B, _, H, W = x.shape
     HW = H * W
     chid, cout = w1.shape[-2], w2.shape[-2]
-    y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
+    if out is not None:
+        if out.shape != (B, cout, H, W) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != x.device:
+            raise RuntimeError("mlp1x1: out must be a contiguous float32 [B, Cout, H, W] tensor on x's device")
+        y = out
+    else:
+        y = torch.empty((B, cout, H, W), dtype=torch.float32, device=x.device)
     if per_sample_w1 and not w1_rounded:
         w1 = round_tf32(w1)
     add_bs = 0

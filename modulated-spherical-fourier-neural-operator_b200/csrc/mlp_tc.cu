@@ -41,7 +41,7 @@ static constexpr int ML_WBLK = 256 * TC_BK * 4;         // weight k-block slot: 
 static constexpr int ML_NSX = MSFNO_ML_NSX, ML_NSW = MSFNO_ML_NSW;
 static constexpr int ML_MAX_HID = 1024;
 static constexpr int ML_IDBLK = 32 * TC_BK * 4;         // resident 32 x 32 identity (K-major, 128-byte swizzle) = 4 KB
-static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + ML_IDBLK + (ML_MAX_HID + 256 + 512) * 4 + 512;
+static constexpr int ML_SMEM = 1024 + ML_NSX * ML_XBLK + ML_NSW * ML_WBLK + ML_IDBLK + (ML_MAX_HID + 256 + 4 * 512) * 4 + 512;
 
 struct MlpTcParams {
   float* D;
@@ -94,8 +94,8 @@ __device__ __forceinline__ void warp_channel_sums(const float (&v)[16], float* a
   // lane bits (4,3,2,1) selected the upper half at steps (8,4,2,1): channel = 8 b4 + 4 b3 + 2 b2 + b1 = lane >> 1
   const int ch = lane >> 1;
   if ((lane & 1) == 0 && ch < nv) {
-    atomicAdd(acc + ch, s[0]);
-    atomicAdd(acc + 256 + ch, q[0]);
+    acc[ch] += s[0];         // the slot belongs to this warp alone (pixel quadrant x channel quarter): no atomics, and the
+    acc[256 + ch] += q[0];   // order of the additions is the CTA's fixed tile order -> bit-reproducible plane sums
   }
 }
 
@@ -145,8 +145,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   uint8_t* idblk = wring + ML_NSW * ML_WBLK;                           // identity block (add path)
   float* b1_s = reinterpret_cast<float*>(idblk + ML_IDBLK);           // [ML_MAX_HID]
   float* b2_s = b1_s + ML_MAX_HID;                                    // [256]
-  float* stat_s = b2_s + 256;                                         // [2][256] per-CTA plane sums of the output
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 512);
+  float* stat_s = b2_s + 256;                                         // [4 pixel quadrants][2][256] per-CTA plane sums of the output
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stat_s + 4 * 512);
   uint64_t* xfull = bars;            // [NSX]
   uint64_t* xempty = bars + 8;       // [NSX]
   uint64_t* wfull = bars + 16;       // [NSW]
@@ -182,8 +182,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const int c = (int)threadIdx.x - 64;
     for (int h = c; h < ML_MAX_HID; h += 256) b1_s[h] = (p.b1 && h < p.Chid) ? p.b1[(long long)b * p.sb1 + h] : 0.0f;
     b2_s[c] = (p.b2 && c < p.Cout) ? p.b2[c] : 0.0f;
-    stat_s[c] = 0.0f;
-    stat_s[256 + c] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) stat_s[j * 256 + c] = 0.0f;
   }
   __syncthreads();
   const uint32_t tmem_acc1 = tmem_base, tmem_acc2 = tmem_base + 256;
@@ -370,7 +370,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] = 0.0f;
             }
-            if (p.stats) warp_channel_sums(v, stat_s + c0 + jb, nv, lane);
+            if (p.stats) warp_channel_sums(v, stat_s + q * 512 + c0 + jb, nv, lane);
           }
         }
       };
@@ -395,7 +395,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   __syncthreads();
   if (p.stats && threadIdx.x < 512) {
     const int ch = threadIdx.x & 255, which = threadIdx.x >> 8;
-    if (ch < p.Cout) atomicAdd(&p.stats[2 * ((size_t)b * p.Cout + ch) + which], (double)stat_s[which * 256 + ch]);
+    if (ch < p.Cout) {   // quadrant slots summed in a fixed order; only the cross-CTA fp64 atomics are unordered (1e-16)
+      const float* sp = stat_s + which * 256 + ch;
+      atomicAdd(&p.stats[2 * ((size_t)b * p.Cout + ch) + which], ((double)sp[0] + (double)sp[512]) + ((double)sp[1024] + (double)sp[1536]));
+    }
   }
   if (warp == 1) {
     tc_fence_after();

@@ -37,9 +37,43 @@ class GraphedForward:
         self.graph.replay()
         return self.static_y
 
+    def _capture_inplace(self):
+        """Second graph for rollouts: the decoder writes the forecast straight into the input buffer (`_decode_out`
+        hook of the fused forward), so a 6 h step needs no feedback copy (303 MB read + write, 0.1 ms of a 5 ms step).
+        Nets without that hook keep the copying loop."""
+        self.inplace_graph = None
+        if (not hasattr(self.net, "_decode_fused") or self.static_args
+                or getattr(self.net, "in_chans", None) != getattr(self.net, "out_chans", -1)):
+            return
+        self.net._decode_out = self.static_x
+        try:
+            keep = self.static_x.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.no_grad(), torch.cuda.stream(side):
+                y = self.net(self.static_x)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            if y.data_ptr() == self.static_x.data_ptr():
+                g = torch.cuda.CUDAGraph()
+                with torch.no_grad(), torch.cuda.graph(g, pool=self.graph.pool()):
+                    y = self.net(self.static_x)
+                if y.data_ptr() == self.static_x.data_ptr():
+                    self.inplace_graph = g
+            self.static_x.copy_(keep)
+        finally:
+            del self.net._decode_out
+
     def rollout(self, x0, steps):
-        """Autoregressive rollout x <- net(x) (reference: /root/reference MSFNO/Models/sfno/model.py:327-331)."""
+        """Autoregressive rollout x <- net(x) (reference: /root/reference MSFNO/Models/sfno/model.py:327-331).
+        Returns the state after `steps` steps (valid until the next call)."""
+        if not hasattr(self, "inplace_graph"):
+            self._capture_inplace()
         self.static_x.copy_(x0, non_blocking=True)
+        if self.inplace_graph is not None:
+            for _ in range(steps):
+                self.inplace_graph.replay()
+            return self.static_x
         for _ in range(steps):
             self.graph.replay()
             self.static_x.copy_(self.static_y, non_blocking=True)

@@ -559,7 +559,7 @@ class FourierNeuralOperatorNet(nn.Module):
         if mlp1x1_supported(dec[0].out_channels, dec[2].out_channels, y.shape[2] * y.shape[3]):
             return mlp1x1(y, Wb, E, bias_b.contiguous(), padded_weight(dec[2].weight), dec[2].bias,
                           x2=residual.contiguous().float(), w1b=W2, cin2=self.in_chans, per_sample_w1=True,
-                          per_sample_b1=True, final=True, w1_rounded=True)
+                          per_sample_b1=True, final=True, w1_rounded=True, out=getattr(self, "_decode_out", None))
         h = conv1x1(y, Wb, E, bias=bias_b.contiguous(), act_gelu=True, x2=residual.contiguous().float(), w2=W2,
                     cin2=self.in_chans, per_sample_w=True, per_sample_bias=True, w_rounded=True)
         return conv1x1(h, padded_weight(dec[2].weight), dec[2].in_channels, bias=dec[2].bias, final=True)

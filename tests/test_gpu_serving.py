@@ -54,6 +54,45 @@ def test_rollout_matches_step_by_step():
     assert torch.equal(out, ref)
 
 
+def test_rollout_in_place_graph_tf32_tier():
+    """Tensor-core tier: the rollout graph lets the fused decoder write the forecast into the input buffer (no feedback
+    copy).  The decoder reads its big-skip operand (the same buffer) tile by tile before storing that tile, so the
+    in-place steps must reproduce the out-of-place eager steps (and the oracle on the same weights)."""
+    from conftest import TOL_TF32
+    cfg = dict(filter_type="non-linear", img_size=(36, 72), scale_factor=2, in_chans=7, out_chans=7, embed_dim_sfno=32,
+               num_layers=3, mlp_ratio=2.0, spectral_layers=2)
+    torch.manual_seed(11)
+    net = msfno_b200.FourierNeuralOperatorNet("cuda", None, **cfg).cuda().eval()
+    x = torch.randn(2, 7, 36, 72, generator=torch.Generator().manual_seed(12))
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    tr = sfno_oracle.Transforms(cfg["img_size"], cfg["scale_factor"])
+    want = x
+    with torch.no_grad():
+        for _ in range(3):
+            want = sfno_oracle.sfno_forward(want, sd, tr, "non-linear", cfg["num_layers"])
+    xd = x.cuda()
+    msfno_b200.set_precision("tf32")
+    try:
+        with torch.no_grad():
+            ref = xd
+            for _ in range(3):
+                ref = net(ref)
+            one_ref = net(xd).clone()
+        g = msfno_b200.GraphedForward(net, xd)
+        out = g.rollout(xd, 3).clone()
+        in_place = g.inplace_graph is not None
+        again = g.rollout(xd, 3).clone()     # the static input is reloaded from x0 on every call
+        one = g(xd).clone()                  # the out-of-place graph still works after the in-place capture
+    finally:
+        msfno_b200.set_precision("fp32")
+    assert in_place, "fused decoder (mlp1x1, hidden 32) not taken: the in-place rollout graph was not captured"
+    assert not hasattr(net, "_decode_out")
+    assert rel_l2(out, ref) < 1e-5, "in-place rollout differs from eager steps of the same tier"
+    assert torch.equal(out, again)
+    assert rel_l2(one, one_ref) < 1e-5
+    assert rel_l2(out, want) < 3 * TOL_TF32
+
+
 def test_host_pipeline_matches_eager():
     net, d = _small_net()
     gen = torch.Generator().manual_seed(3)
