@@ -122,6 +122,14 @@ def test_full_sfno_12_blocks_vs_oracle(tier, tol):
         net = net.cuda().eval()
         with torch.no_grad():
             got = net(x.cuda())
+            again = net(x.cuda().clone())
         assert rel_l2(got, want) < tol
+        # run-to-run reproducibility: in the tensor-core tier a 1-ulp change of a normalisation coefficient re-draws
+        # the TF32 rounding of every later activation (1e-3 rel-L2 after 12 blocks), so the plane statistics must be
+        # accumulated in a fixed order (mlp_tc.cu: per-warp slots, no shared-memory atomics)
+        if tier == "tf32":
+            assert torch.equal(got, again), "two forwards of the same input differ: rel-L2 %.2e" % rel_l2(again, got)
+        else:
+            assert rel_l2(again, got) < 1e-6
     finally:
         msfno_b200.set_precision("fp32")
