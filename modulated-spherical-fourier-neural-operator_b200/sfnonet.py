@@ -18,6 +18,7 @@ The 1x1-conv MLPs (encoder, decoder, block MLP, inner skip) are the callers eith
  and still use the PyTorch library convolution.
 """
 import math
+import os
 from functools import partial
 
 import torch
@@ -68,6 +69,17 @@ class FiLM(nn.Module):
         if torch.is_tensor(scale):
             scale = float(scale)
         return _FiLMFn.apply(x.contiguous().float(), gammas.contiguous().float(), betas.contiguous().float(), scale).to(x.dtype)
+
+
+_SIDE_SKIP = os.environ.get("MSFNO_SIDE_SKIP", "0") == "1"
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]
 
 
 def plane_stats(x):
@@ -282,14 +294,24 @@ class FourierNeuralOperatorBlock(nn.Module):
         B, C = x.shape[0], x.shape[1]
         A0, S0 = norm_film_coeffs(in_stats if in_stats is not None else plane_stats(x), self.norm0, B, C, x[0, 0].numel())
         skip = None
+        join = None
         if hasattr(self, "inner_skip"):
             if isinstance(self.inner_skip, nn.Conv2d):
-                skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
+                if _SIDE_SKIP:
+                    # the skip conv depends only on x: it runs on a side stream beside the SHT -> spectral MLP chain (its
+                    # CTAs fill the SMs the second wave of the spectral GEMMs leaves idle) and is joined before the inverse
+                    cur, side = torch.cuda.current_stream(), _side_stream(x.device)
+                    side.wait_stream(cur)
+                    with torch.cuda.stream(side):
+                        skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
+                    join = lambda: cur.wait_stream(side)
+                else:
+                    skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
             else:
                 skip = self.inner_skip(residual)
         stats1 = torch.empty((B * C, 2), dtype=torch.float64, device=x.device)
         y = self.filter_layer(x, in_scale=A0, in_shift=S0, skip_add=skip, act_gelu=hasattr(self, "act_layer"),
-                              stats=stats1)
+                              stats=stats1, **({"pre": join} if join is not None else {}))
         A1, S1 = norm_film_coeffs(stats1, self.norm1, B, C, y[0, 0].numel(), gamma, beta, scale)
         if prefilm:   # training: the caller applies norm1's affine, then FiLM / MLP / skip under autograd
             return y, A1, S1

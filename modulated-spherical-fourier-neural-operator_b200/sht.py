@@ -242,12 +242,15 @@ class InverseRealSHT(_SHTBase):
     _analysis = False
     _table_name = "pct"
 
-    def inverse_packed(self, coef_cm, skip_add=None, act_gelu=False, stats=None):
+    def inverse_packed(self, coef_cm, skip_add=None, act_gelu=False, stats=None, pre=None):
         """coefficients in the CM layout [B,2C,P] -> y [B,C,nlat,nlon].  skip_add / act_gelu / stats
-        select the fused epilogue (inference only: not differentiable)."""
+        select the fused epilogue (inference only: not differentiable).  pre: optional callable run right before the
+        launches (the block joins the side stream that produced skip_add there)."""
         _require_cuda(coef_cm, "InverseRealSHT")
         coef_cm = coef_cm.contiguous()
         if skip_add is None and not act_gelu and stats is None:
+            if pre is not None:
+                pre()
             return _ISHTForward.apply(coef_cm, self)
         if torch.is_grad_enabled() and (coef_cm.requires_grad or (skip_add is not None and skip_add.requires_grad)):
             raise RuntimeError("InverseRealSHT fused epilogue is inference-only; call under torch.no_grad()")
@@ -259,6 +262,8 @@ class InverseRealSHT(_SHTBase):
             skip_add = skip_add.contiguous().float()
             assert skip_add.shape == y.shape
         flags = (1 if act_gelu else 0) | (2 if _precision.get_precision() == "tf32" else 0)   # bit 1: TF32-round y
+        if pre is not None:
+            pre()
         check(lib.msfno_isht_fwd(plan.h, ptr(coef_cm), ptr(y), ptr(ws), B, C, ptr(skip_add), flags,
                                  ptr(stats), _stream()), "isht_fwd")
         return y
