@@ -190,6 +190,11 @@ int msfno_norm_film_coeffs(const double* stats, const float* nw, const float* nb
  * round_tf32), bb[b][o] = sum_c W[o][c] S[b][c] + bias[o] (bias may be NULL).  W: [O][ld] zero-padded rows. */
 int msfno_fold_affine(const float* W, const float* A, const float* S, const float* bias, float* Wb, float* bb,
                       int B, int O, int C, int ld, int round_tf32, void* stream);
+/* msfno_norm_film_coeffs + msfno_fold_affine in one launch (same arithmetic, bit-identical Wb / bb): the
+ * InstanceNorm -> FiLM -> fc1 hand-over of every block (sfnonet.py:380-386) costs one small kernel instead of two. */
+int msfno_fold_norm_affine(const float* W, const double* stats, const float* nw, const float* nb, const float* gamma,
+                           const float* beta, float scale, float eps, long HW, const float* bias, float* Wb,
+                           float* bb, int B, int O, int C, int ld, int round_tf32, void* stream);
 /* out = g * gelu'(h), exact (erf) GELU: activation adjoint of the frozen-weight channel-MLP backward (a14) */
 int msfno_gelu_bwd_mul(const float* g, const float* h, float* out, long long n, void* stream);
 /* y[plane][:] = A[plane]*x[plane][:] + S[plane] */

@@ -130,6 +130,64 @@ __global__ void fold_affine_kernel(const float* __restrict__ W, const float* __r
   }
 }
 
+// InstanceNorm(eps, affine nw / nb) followed by optional FiLM(gamma, beta, scale) of one plane as y = a x + s, from the
+// plane's fp64 (sum, sum of squares).  One definition for norm_film_coeffs_kernel and fold_norm_affine_kernel, so the
+// fused launch reproduces the two-launch result bit for bit.
+__device__ __forceinline__ void norm_film_coeff(const double* __restrict__ stats, const float* __restrict__ nw,
+                                                const float* __restrict__ nb, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float scale, float eps, double inv_hw, int i,
+                                                int c, float& A, float& S) {
+  const double mean = stats[2 * i] * inv_hw;
+  double var = stats[2 * i + 1] * inv_hw - mean * mean;  // biased variance, as InstanceNorm uses
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  double a = rstd * (nw ? (double)nw[c] : 1.0);
+  double s = (nb ? (double)nb[c] : 0.0) - mean * a;
+  if (gamma) {
+    const double f = 1.0 + (double)gamma[i] * (double)scale;
+    a *= f;
+    s = s * f + (double)beta[i] * (double)scale;
+  }
+  A = (float)a;
+  S = (float)s;
+}
+
+// fold_affine_kernel with the coefficients computed in place from the plane statistics (norm_film_coeffs + fold_affine in
+// one launch on the InstanceNorm -> FiLM -> fc1 path of every block)
+__global__ void fold_norm_affine_kernel(const float* __restrict__ W, const double* __restrict__ stats,
+                                        const float* __restrict__ nw, const float* __restrict__ nb,
+                                        const float* __restrict__ gamma, const float* __restrict__ beta, float scale, float eps,
+                                        double inv_hw, const float* __restrict__ bias, float* __restrict__ Wb,
+                                        float* __restrict__ bb, int O, int C, int ld, int round_tf32) {
+  pdl_trigger();
+  pdl_wait();
+  const int o = blockIdx.x, b = blockIdx.y;
+  const float* w = W + (size_t)o * ld;
+  float* wb = Wb + ((size_t)b * O + o) * ld;
+  float acc = 0.0f;
+  for (int c = threadIdx.x; c < ld; c += blockDim.x) {
+    float v = 0.0f;
+    if (c < C) {
+      float A, S;
+      norm_film_coeff(stats, nw, nb, gamma, beta, scale, eps, inv_hw, b * C + c, c, A, S);
+      const float wv = w[c];
+      v = wv * A;
+      acc = fmaf(wv, S, acc);
+      if (round_tf32) v = __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u);
+    }
+    wb[c] = v;
+  }
+  __shared__ float red[32];
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    bb[(size_t)b * O + o] = t + (bias ? bias[o] : 0.0f);
+  }
+}
+
 // out[i] = g[i] * gelu'(h[i])  (exact erf GELU): the activation's adjoint in the frozen-weight MLP backward
 __global__ void gelu_bwd_mul_kernel(const float* __restrict__ g, const float* __restrict__ h, float* __restrict__ out, long long n) {
   const long long n4 = n >> 2;
@@ -156,20 +214,10 @@ __global__ void norm_film_coeffs_kernel(const double* __restrict__ stats, const 
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
-  const int c = i % C;
-  const double mean = stats[2 * i] * inv_hw;
-  double var = stats[2 * i + 1] * inv_hw - mean * mean;  // biased variance, as InstanceNorm uses
-  if (var < 0.0) var = 0.0;
-  const double rstd = 1.0 / sqrt(var + (double)eps);
-  double a = rstd * (nw ? (double)nw[c] : 1.0);
-  double s = (nb ? (double)nb[c] : 0.0) - mean * a;
-  if (gamma) {
-    const double f = 1.0 + (double)gamma[i] * (double)scale;
-    a *= f;
-    s = s * f + (double)beta[i] * (double)scale;
-  }
-  A[i] = (float)a;
-  S[i] = (float)s;
+  float a, s;
+  norm_film_coeff(stats, nw, nb, gamma, beta, scale, eps, inv_hw, i, i % C, a, s);
+  A[i] = a;
+  S[i] = s;
 }
 
 // one CTA per plane: gx = (1 + gamma*scale) * gy, ggamma = scale * sum(gy*x), gbeta = scale * sum(gy)
@@ -271,6 +319,18 @@ int msfno_fold_affine(const float* W, const float* A, const float* S, const floa
                       int ld, int round_tf32, void* stream) {
   if (!W || !A || !S || !Wb || !bb || B < 1 || O < 1 || C < 1 || ld < C) return record_error(MSFNO_ERR_BAD_SHAPE, "fold_affine: bad argument");
   MSFNO_CUDA_OK(launch_pdl(fold_affine_kernel, dim3(O, B), dim3(128), 0, (cudaStream_t)stream, W, A, S, bias, Wb, bb, O, C, ld, round_tf32));
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+int msfno_fold_norm_affine(const float* W, const double* stats, const float* nw, const float* nb, const float* gamma,
+                           const float* beta, float scale, float eps, long HW, const float* bias, float* Wb, float* bb, int B,
+                           int O, int C, int ld, int round_tf32, void* stream) {
+  if (!W || !stats || !Wb || !bb || B < 1 || O < 1 || C < 1 || ld < C || HW < 1 || ((gamma == nullptr) != (beta == nullptr)))
+    return record_error(MSFNO_ERR_BAD_SHAPE, "fold_norm_affine: bad argument");
+  MSFNO_CUDA_OK(launch_pdl(fold_norm_affine_kernel, dim3(O, B), dim3(128), 0, (cudaStream_t)stream, W, stats, nw, nb, gamma, beta,
+                           scale, eps, 1.0 / (double)HW, bias, Wb, bb, O, C, ld, round_tf32));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

@@ -113,6 +113,20 @@ def fold_affine(W, A, S, bias):
     return Wb, bb
 
 
+def fold_norm_affine(W, stats, norm, HW, bias, gamma=None, beta=None, scale=1.0):
+    """fold_affine(W, *norm_film_coeffs(stats, norm, ...), bias) in one launch (msfno_fold_norm_affine, bit-identical)."""
+    B, C = stats.shape[0] // norm.num_features, norm.num_features
+    O, ld = W.shape
+    Wb = torch.empty((B, O, ld), dtype=torch.float32, device=W.device)
+    bb = torch.empty((B, O), dtype=torch.float32, device=W.device)
+    g = gamma.contiguous().float() if gamma is not None else None
+    b = beta.contiguous().float() if beta is not None else None
+    check(lib.msfno_fold_norm_affine(ptr(W), ptr(stats), ptr(norm.weight), ptr(norm.bias), ptr(g), ptr(b), float(scale),
+                                     float(norm.eps), HW, ptr(bias), ptr(Wb), ptr(bb), B, O, C, ld,
+                                     1 if _precision.get_precision() == "tf32" else 0, _stream()), "fold_norm_affine")
+    return Wb, bb
+
+
 class _FrozenMLPFn(torch.autograd.Function):
     """y = conv1x1(gelu(conv1x1(x, W1a) + conv1x1(x2, W1b) + b1), W2) + b2 for FROZEN weights: the forward is the fused
     tensor-memory kernel (msfno_mlp1x1_fwd, or two msfno_conv1x1_fwd in the fp32 tier), the backward returns the
@@ -312,17 +326,21 @@ class FourierNeuralOperatorBlock(nn.Module):
         stats1 = torch.empty((B * C, 2), dtype=torch.float64, device=x.device)
         y = self.filter_layer(x, in_scale=A0, in_shift=S0, skip_add=skip, act_gelu=hasattr(self, "act_layer"),
                               stats=stats1, **({"pre": join} if join is not None else {}))
-        A1, S1 = norm_film_coeffs(stats1, self.norm1, B, C, y[0, 0].numel(), gamma, beta, scale)
+        mlp = getattr(self, "mlp", None)
+        fused_mlp = (not prefilm and mlp is not None and len(mlp.fwd) == 3 and isinstance(mlp.fwd[0], nn.Conv2d)
+                     and isinstance(mlp.fwd[1], nn.GELU) and getattr(mlp.fwd[1], "approximate", "none") == "none"
+                     and isinstance(mlp.fwd[2], nn.Conv2d))
+        if not fused_mlp:
+            A1, S1 = norm_film_coeffs(stats1, self.norm1, B, C, y[0, 0].numel(), gamma, beta, scale)
         if prefilm:   # training: the caller applies norm1's affine, then FiLM / MLP / skip under autograd
             return y, A1, S1
-        mlp = getattr(self, "mlp", None)
         no_drop = isinstance(self.drop_path, nn.Identity) or not self.training
         if mlp is None and defer_affine and not hasattr(self, "outer_skip"):
             return y, A1, S1
-        if (mlp is not None and len(mlp.fwd) == 3 and isinstance(mlp.fwd[0], nn.Conv2d) and isinstance(mlp.fwd[1], nn.GELU)
-                and getattr(mlp.fwd[1], "approximate", "none") == "none" and isinstance(mlp.fwd[2], nn.Conv2d)):
+        if fused_mlp:
             fc1, fc2 = mlp.fwd[0], mlp.fwd[2]
-            Wb, bias_b = fold_affine(padded_weight(fc1.weight), A1, S1, fc1.bias)   # norm1 o FiLM folded into fc1
+            # norm1 o FiLM folded into fc1; the coefficients are computed inside the folding kernel
+            Wb, bias_b = fold_norm_affine(padded_weight(fc1.weight), stats1, self.norm1, y[0, 0].numel(), fc1.bias, gamma, beta, scale)
             fuse_res = no_drop and not self.concat_skip and isinstance(getattr(self, "outer_skip", None), nn.Identity)
             if mlp1x1_supported(fc1.out_channels, fc2.out_channels, y.shape[2] * y.shape[3]):
                 # fc1 -> GELU -> fc2 (+ residual) in one kernel; the 512-channel hidden tile never leaves tensor memory

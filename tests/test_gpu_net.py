@@ -158,3 +158,40 @@ def test_fold_affine_matches_algebra():
     assert rel_l2(bb, S.double() @ W[:, :C].double().T + bias.double()) < 1e-6
     Wb2, bb2 = fold_affine(W.cuda(), A.cuda(), S.cuda(), None)
     assert rel_l2(bb2, S.double() @ W[:, :C].double().T) < 1e-6
+
+
+@pytest.mark.parametrize("tier", ["fp32", "tf32"])
+@pytest.mark.parametrize("film", [False, True])
+def test_fold_norm_affine_is_the_two_launch_result(tier, film):
+    """msfno_fold_norm_affine == msfno_norm_film_coeffs followed by msfno_fold_affine, bit for bit (the block's
+    InstanceNorm -> FiLM -> fc1 hand-over, sfnonet.py:380-386), and both match the fp64 algebra."""
+    from msfno_b200.sfnonet import fold_affine, fold_norm_affine, norm_film_coeffs, plane_stats
+    from msfno_b200.conv import padded_weight
+    msfno_b200.set_precision(tier)
+    try:
+        g = torch.Generator().manual_seed(21)
+        B, C, O, H, W = 2, 37, 50, 12, 20
+        y = (torch.randn(B, C, H, W, generator=g) * 3 + 1).cuda()
+        norm = torch.nn.InstanceNorm2d(C, eps=1e-6, affine=True).cuda()
+        with torch.no_grad():
+            norm.weight.copy_(torch.randn(C, generator=g)); norm.bias.copy_(torch.randn(C, generator=g))
+        fc = torch.nn.Conv2d(C, O, 1).cuda()
+        gam = torch.randn(B, C, generator=g).cuda() if film else None
+        bet = torch.randn(B, C, generator=g).cuda() if film else None
+        st = plane_stats(y)
+        Wp = padded_weight(fc.weight)
+        with torch.no_grad():
+            A, S = norm_film_coeffs(st, norm, B, C, H * W, gam, bet, 0.7)
+            Wb0, bb0 = fold_affine(Wp, A, S, fc.bias)
+            Wb1, bb1 = fold_norm_affine(Wp, st, norm, H * W, fc.bias, gam, bet, 0.7)
+        assert torch.equal(Wb0, Wb1) and torch.equal(bb0, bb1)
+        # fp64 algebra: conv(film(norm(y))) == conv_b(y) with the folded per-sample weights
+        with torch.no_grad():
+            z = norm(y).double()
+            if film:
+                z = (1 + gam.double()[:, :, None, None] * 0.7) * z + bet.double()[:, :, None, None] * 0.7
+            want = torch.nn.functional.conv2d(z, fc.weight.double(), fc.bias.double())
+            got = torch.einsum("boc,bchw->bohw", Wb1[:, :, :C].double(), y.double()) + bb1.double()[:, :, None, None]
+        assert rel_l2(got, want) < (1e-5 if tier == "fp32" else 2e-3)
+    finally:
+        msfno_b200.set_precision("fp32")
