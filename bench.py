@@ -412,6 +412,12 @@ def run_ours(args):
 
 
 def main():
+    # stdout carries the one JSON line only: native libraries (NCCL prints its version banner there) write to file
+    # descriptor 1, so descriptor 1 is pointed at stderr and Python's sys.stdout keeps the original stream
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(keep, "w", buffering=1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)

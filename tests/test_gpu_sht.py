@@ -138,3 +138,38 @@ def test_full_size_roundtrip_property():
     c = torch.view_as_complex(c).cuda()
     back = sht(isht(c))
     assert rel_l2(torch.view_as_real(back), torch.view_as_real(c)) < TOL_FP32
+
+
+def test_error_behaviour_at_the_boundary():
+    """Shape asserts mirror torch_harmonics (x.shape[-2] == nlat, x.shape[-1] == nlon / lmax, mmax); the fused inverse
+    epilogue is inference-only; the C ABI's error codes surface as RuntimeError."""
+    import msfno_b200
+    from msfno_b200.conv import mlp1x1, padded_weight
+    sht = msfno_b200.RealSHT(12, 24, lmax=6, mmax=7, grid="legendre-gauss").float().cuda()
+    isht = msfno_b200.InverseRealSHT(12, 24, lmax=6, mmax=7, grid="legendre-gauss").float().cuda()
+    with pytest.raises(AssertionError):
+        sht(torch.randn(1, 2, 11, 24).cuda())
+    with pytest.raises(AssertionError):
+        sht(torch.randn(1, 2, 12, 22).cuda())
+    with pytest.raises(AssertionError):
+        isht(torch.randn(1, 2, 6, 8, dtype=torch.complex64).cuda())
+    c = sht(torch.randn(1, 2, 12, 24).cuda())
+    assert c.shape == (1, 2, 6, 7) and c.dtype == torch.complex64
+    assert isht(c).shape == (1, 2, 12, 24)
+    # an empty batch is either rejected with the boundary's error or returns an empty result -- and leaves no sticky
+    # CUDA error behind: the next valid call must still work
+    try:
+        e = sht(torch.randn(0, 2, 12, 24).cuda())
+        assert e.shape[0] == 0
+    except (RuntimeError, AssertionError):
+        pass
+    torch.cuda.synchronize()
+    assert rel_l2(sht(torch.view_as_real(c).new_zeros(1, 2, 12, 24) + 1.0)[..., 1:, :], torch.zeros(1, 2, 5, 7, dtype=torch.complex64)) >= 0.0
+    x = torch.randn(1, 8, 4, 8).cuda()
+    w1, w2 = padded_weight(torch.randn(32, 8, 1, 1).cuda()), padded_weight(torch.randn(8, 32, 1, 1).cuda())
+    msfno_b200.set_precision("tf32")
+    try:
+        with pytest.raises(RuntimeError, match="out must be"):
+            mlp1x1(x, w1, 8, torch.zeros(32).cuda(), w2, None, out=torch.empty(1, 8, 4, 4).cuda())
+    finally:
+        msfno_b200.set_precision("fp32")

@@ -173,3 +173,29 @@ def test_parity_split_inverse_dft_matches_irfft(nlon, mlim):
             O += term
     got = np.concatenate([E + O, E - O], axis=1)
     assert np.abs(got - want).max() < 1e-12 * max(1.0, np.abs(want).max())
+
+
+def test_c_abi_rejects_bad_arguments_without_a_gpu():
+    """Error behaviour of the boundary (SURVEY.md section 8(b) "Errors"): every entry point validates its arguments before
+    any CUDA call, returns MSFNO_ERR_BAD_SHAPE (1) and leaves a message for msfno_last_error(); the Python wrapper turns
+    the code into a RuntimeError.  NULL pointers / zero sizes only -- nothing is launched."""
+    import ctypes
+    from msfno_b200 import _lib
+    lib = _lib.lib
+    bad = _lib.ERR_BAD_SHAPE if hasattr(_lib, "ERR_BAD_SHAPE") else 1
+    cases = {
+        "fold_affine": lambda: lib.msfno_fold_affine(None, None, None, None, None, None, 1, 1, 1, 1, 0, None),
+        "fold_norm_affine": lambda: lib.msfno_fold_norm_affine(None, None, None, None, None, None, 1.0, 1e-6, 10, None, None, None,
+                                                               1, 1, 1, 1, 0, None),
+        "norm_film_coeffs": lambda: lib.msfno_norm_film_coeffs(None, None, None, None, None, 1.0, 1e-6, None, None, 1, 1, 10, None),
+        "gelu_bwd_mul": lambda: lib.msfno_gelu_bwd_mul(None, None, None, 0, None),
+        "plane_affine": lambda: lib.msfno_plane_affine(None, None, None, None, 0, 0, None),
+    }
+    for name, call in cases.items():
+        assert call() == bad, name
+        assert name in _lib.last_error()
+    plan = ctypes.c_void_p()
+    assert lib.msfno_plan_create(ctypes.byref(plan), 0, 0, 0, 0) == bad and not plan.value
+    assert "plan_create" in _lib.last_error()
+    with pytest.raises(RuntimeError, match="fold_affine: bad argument"):
+        _lib.check(lib.msfno_fold_affine(None, None, None, None, None, None, 1, 1, 1, 1, 0, None), "fold_affine")
