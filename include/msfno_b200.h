@@ -50,9 +50,12 @@ extern "C" {
 #define MSFNO_Q_NTRIL 3  /* n: len(torch.tril_indices(lmax, mmax)[0]) of the reference */
 #define MSFNO_Q_LJ 4     /* padded degree extent of the re-laid tables */
 
-/* msfno_gemm precision tiers */
-#define MSFNO_PREC_FP32 0 /* CUDA-core FFMA, fp32 accumulate: the 1e-5 tier */
-#define MSFNO_PREC_TF32 1 /* tcgen05 kind::tf32 tensor-core path: the 2e-3 tier */
+/* precision tiers */
+#define MSFNO_PREC_FP32 0 /* the 1e-5 tier: fp32-grade products, fp32 accumulate (engine: msfno_set_fp32_engine) */
+#define MSFNO_PREC_TF32 1 /* the 2e-3 tier: tcgen05 kind::tf32, one MMA per k-step on TF32-rounded operands */
+/* engines of the fp32 tier's GEMM-shaped stages */
+#define MSFNO_FP32_ENGINE_TC3X 0 /* tcgen05 kind::tf32, three MMAs per k-step on hi / lo operand splits ("3xTF32") */
+#define MSFNO_FP32_ENGINE_FFMA 1 /* CUDA-core FFMA kernels */
 
 typedef struct msfno_plan msfno_plan;
 
@@ -61,6 +64,11 @@ const char* msfno_last_error(void);
 const char* msfno_build_info(void);
 /* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
 unsigned long long msfno_launch_count(void);
+/* Process-wide engine of the fp32 tier (default MSFNO_FP32_ENGINE_TC3X).  The reference forces fp32 arithmetic inside
+ * the transforms and the spectral MLP (MSFNO/Models/sfno/layers.py:403-407,418-422,627-639); both engines meet that
+ * tier's 1e-5 rel-L2, the FFMA one is kept as the cross-check and for operands the TMA path cannot address. */
+int msfno_set_fp32_engine(int engine);
+int msfno_get_fp32_engine(void);
 
 /* ---- plans ------------------------------------------------------------------------------
  * replaces: torch_harmonics.RealSHT.__init__ / InverseRealSHT.__init__ device-side state
@@ -75,8 +83,8 @@ long msfno_plan_query(const msfno_plan* plan, int what);
  * (RealSHT.weights); analysis == 0 -> used by isht_fwd/bwd (InverseRealSHT.pct).
  * Entries with l < m must be zero (they are by construction); otherwise MSFNO_ERR_UNSUPPORTED. */
 int msfno_plan_set_table(msfno_plan* plan, const float* table, int analysis, void* stream);
-/* precision tier of the Legendre contractions of the FORWARD transforms (adjoints always run fp32):
- * MSFNO_PREC_FP32 (default) or MSFNO_PREC_TF32 (tcgen05 tensor-core GEMM). */
+/* precision tier of the longitude transforms and Legendre contractions of the FORWARD transforms: MSFNO_PREC_FP32
+ * (default) or MSFNO_PREC_TF32.  The adjoints always run at fp32 grade (3xTF32 tensor-core GEMMs or FFMA). */
 int msfno_plan_set_precision(msfno_plan* plan, int precision);
 /* host copies of the packed-position maps: poff[mmax] and n2p[ntril] (reference tril order) */
 int msfno_plan_get_maps(const msfno_plan* plan, int32_t* poff_host, int32_t* n2p_host);
@@ -237,6 +245,14 @@ int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const float* w1, l
  * Exposed for tests and for the 1x1-conv MLPs either side of the path. */
 int msfno_gemm_nt(const float* A, long lda, const float* Bm, long ldb, float* D, long ldd, int M, int N,
                   int K, int relu_even_cols, int precision, void* stream);
+
+/* General form (the GEMMs of the adjoints; exposed for the tests): D[M][N] (+)= mask(relu(opA(A) opB(B)^T)).
+ * a_kmajor / b_kmajor: 1 = element (r, k) at r*ld + k, 0 = at k*ld + r.  mask (optional, indexed like D with ldmask):
+ * even columns of D are zeroed where mask <= 0 (ReLU backward on the real parts).  engine: 0 = CUDA-core FFMA,
+ * 1 = plain TF32 MMA, 3 = 3xTF32 (fp32 grade); tensor-core engines fall back to FFMA for unaligned operands. */
+int msfno_gemm_ex(const float* A, long lda, int a_kmajor, const float* Bm, long ldb, int b_kmajor, float* D, long ldd,
+                  int M, int N, int K, int relu_even_cols, const float* mask, long ldmask, int accumulate, int engine,
+                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ There is no CPU fallback: importing requires libmsfno_b200.so (see __graft_entry
 """
 from . import _lib  # noqa: F401  (loads the shared library; raises loudly when it is missing)
 from . import legendre, quadrature
-from .precision import get_precision, set_precision
+from .precision import get_fp32_engine, get_precision, set_fp32_engine, set_precision
 from .sht import InverseRealSHT, RealSHT
 from .layers import MLP, ComplexReLU, DropPath, SpectralAttentionS2, SpectralConvS2, trunc_normal_
 from .sfnonet import (FeedForward, FiLM, Film_wrapper, FourierNeuralOperatorBlock, FourierNeuralOperatorBlock_Filmed,
@@ -21,7 +21,7 @@ from .pipeline import HostPipeline
 from .graph import GraphedForward
 
 __all__ = [
-    "RealSHT", "InverseRealSHT", "quadrature", "legendre", "harmonics", "set_precision", "get_precision",
+    "RealSHT", "InverseRealSHT", "quadrature", "legendre", "harmonics", "set_precision", "get_precision", "set_fp32_engine", "get_fp32_engine",
     "SpectralConvS2", "SpectralAttentionS2", "ComplexReLU", "MLP", "DropPath", "trunc_normal_",
     "SpectralFilterLayer", "FiLM", "FourierNeuralOperatorBlock", "FourierNeuralOperatorBlock_Filmed",
     "FourierNeuralOperatorNet", "FourierNeuralOperatorNet_Filmed", "Film_wrapper", "FeedForward", "HostPipeline", "GraphedForward",

@@ -17,6 +17,7 @@ OK = 0
 LAYOUT_STD, LAYOUT_PM, LAYOUT_CM = 0, 1, 2
 Q_KPAD, Q_MLIM, Q_NPACK, Q_NTRIL, Q_LJ = 0, 1, 2, 3, 4
 PREC_FP32, PREC_TF32 = 0, 1
+FP32_ENGINE_TC3X, FP32_ENGINE_FFMA = 0, 1
 
 c_void_p, c_int, c_long, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_size_t
 
@@ -46,6 +47,8 @@ _SIGS = {
     "msfno_last_error": (ctypes.c_char_p, []),
     "msfno_build_info": (ctypes.c_char_p, []),
     "msfno_launch_count": (ctypes.c_ulonglong, []),
+    "msfno_set_fp32_engine": (c_int, [c_int]),
+    "msfno_get_fp32_engine": (c_int, []),
     "msfno_plan_create": (c_int, [ctypes.POINTER(c_void_p), c_int, c_int, c_int, c_int]),
     "msfno_plan_destroy": (c_int, [_P]),
     "msfno_plan_query": (c_long, [_P, c_int]),
@@ -82,6 +85,7 @@ _SIGS = {
     "msfno_mlp1x1_fwd": (c_int, [_P, c_long, c_int, _P, c_long, c_long, _P, c_long, c_int, _P, c_long, _P, c_long, c_int, _P, c_long,
                                  _P, _P, c_long, _P, _P, c_int, c_int, c_long, c_int, _P]),
     "msfno_gemm_nt": (c_int, [_P, c_long, _P, c_long, _P, c_long, c_int, c_int, c_int, c_int, c_int, _P]),
+    "msfno_gemm_ex": (c_int, [_P, c_long, c_int, _P, c_long, c_int, _P, c_long, c_int, c_int, c_int, c_int, _P, c_long, c_int, c_int, _P]),
 }
 
 

@@ -38,15 +38,19 @@ extern "C" int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const 
     g.A2 = w2; g.B2 = x2; g.lda2 = ldw2; g.ldb2 = HW; g.sa2 = 0; g.sb2 = x2_bstride; g.K2 = Cin2;
   }
   if (HW > 0x7fffffffL) return record_error(MSFNO_ERR_UNSUPPORTED, "conv1x1_fwd: plane too large");
-  if (precision == MSFNO_PREC_TF32 && (HW % 4 == 0) && (x_bstride % HW == 0) && (!x2 || x2_bstride % HW == 0) &&
+  const bool tf32 = precision == MSFNO_PREC_TF32;
+  if ((tf32 || fp32_engine_x3()) && (HW % 4 == 0) && (x_bstride % HW == 0) && (!x2 || x2_bstride % HW == 0) &&
       (w_bstride % ldw == 0) && gemm_tc_supported(g)) {
     const long long a_rows = (long long)(B - 1) * (w_bstride / ldw) + Cout;
     const long long b_rows = (long long)(B - 1) * (x_bstride / HW) + Cin;
     const long long b2_rows = x2 ? (long long)(B - 1) * (x2_bstride / HW) + Cin2 : 0;
-    int handled = 0;
-    int rc = launch_conv_tc(g, a_rows, ldw, b_rows, HW, Cout, ldw2, b2_rows, HW, &handled, st, round_out);
-    if (rc || handled) return rc;
-    return launch_gemm_tc(g, a_rows, ldw, b_rows, HW, round_out, st, Cout, ldw2, b2_rows, HW);
+    if (tf32) {   // persistent weight-stationary kernel (plain TF32 only)
+      int handled = 0;
+      int rc = launch_conv_tc(g, a_rows, ldw, b_rows, HW, Cout, ldw2, b2_rows, HW, &handled, st, round_out);
+      if (rc || handled) return rc;
+    }
+    g.x3 = tf32 ? 0 : 1;   // fp32 tier: 3xTF32 on the grouped tensor-core GEMM
+    return launch_gemm_tc(g, a_rows, ldw, b_rows, HW, tf32 ? round_out : 0, st, Cout, ldw2, b2_rows, HW);
   }
   return launch_gemm_ffma(g, st);
 }

@@ -1,21 +1,33 @@
-// Grouped TF32 GEMM on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) issued by one thread,
-// operands staged in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), fp32 accumulators in
-// TMEM, read back with tcgen05.ld for the epilogue.  This is the "tensor-core tier" (<= 2e-3 rel-L2) engine of
-// the spectral complex MLP, of the Legendre contractions and of the 1x1-conv MLPs either side of the path.
+// Grouped GEMM on the 5th-generation tensor cores: tcgen05.mma (kind::tf32) issued by one thread, operands staged
+// in shared memory by TMA (cp.async.bulk.tensor, 128-byte swizzle), fp32 accumulators in TMEM, read back with
+// tcgen05.ld for the epilogue.  Engine of the spectral complex MLP, of the Legendre contractions (forward AND adjoint)
+// and of the 1x1 convolutions either side of the path, in BOTH precision tiers:
+//
+//   tf32 tier (<= 2e-3 rel-L2): one MMA per k-step on operands the producers rounded to TF32.
+//   fp32 tier (<= 1e-5 rel-L2): "3xTF32".  The tensor core reads only the upper 19 bits of an fp32 operand, i.e. it
+//     sees hi(x) = x with the low 13 mantissa bits cleared.  lo(x) = x - hi(x) is exact in fp32, so
+//         a b  =  hi(a) hi(b) + hi(a) lo(b) + lo(a) hi(b)  +  lo(a) lo(b)          (last term <= 2^-20 |a b|, dropped)
+//     Four converter warps compute lo() of every staged operand tile in shared memory (same swizzled layout, the
+//     operation is elementwise) while the previous stage is being multiplied; the issuing thread then launches three
+//     MMAs per k-step into the same TMEM accumulator, small terms first.  The truncation of lo() itself (13 -> 11
+//     bits) leaves <= 3 * 2^-24 |x| per operand.  The reference computes these contractions in fp32 (autocast is forced
+//     off, /root/reference MSFNO/Models/sfno/layers.py:403-407,627-639); this is that tier on the tensor pipe.
 //
 // replaces: the cuBLAS / cuDNN GEMMs behind torch.einsum and nn.Conv2d(1x1) in /root/reference
-//   MSFNO/Models/sfno/contractions.py:132-137 ("bixy,io->boxy"), torch_harmonics' Legendre einsums and
-//   MSFNO/Models/sfno/layers.py:161-168 (MLP.fwd).
+//   MSFNO/Models/sfno/contractions.py:132-137 ("bixy,io->boxy"), torch_harmonics' Legendre einsums, their autograd
+//   adjoints, and MSFNO/Models/sfno/layers.py:161-168 (MLP.fwd).
 //
-// D[M][N] = A[M][K] * op(B) (+ A2 * op(B2)),  D = act(D + bias[row]) + add
-//   A  : K-major  [M][lda]                      (weights / tables)
-//   B  : K-major  [N][ldb]   (B_MN = false)     or   MN-major [K][ldb], N contiguous (B_MN = true: NCHW activations)
-// Operands are described to TMA as plain 2-D tensors; a group selects its sub-problem by (row, column)
-// coordinates, so one tensor map per operand serves all groups of a launch.  Out-of-range boxes are zero-filled.
+// D[M][N] = op(A) * op(B) (+ A2 * op(B2)),  D = mask( act(D + bias[row]) + add )  [+= D]
+//   A : K-major [M][lda]  or  MN-major [K][lda] (M contiguous: adjoint of a K-major forward operand)
+//   B : K-major [N][ldb]  or  MN-major [K][ldb] (N contiguous: NCHW activations, tables in the adjoints)
+// Operands are described to TMA as plain 2-D tensors; a group selects its sub-problem by (row, column) coordinates, so
+// one tensor map per operand serves all groups of a launch.  Out-of-range boxes are zero-filled.  An MN-major B that
+// is a stack of equally sized tables can be described as a 3-D tensor (b_group_rows) so that the K rows past the end
+// of one table read zeros instead of the next table.
 //
-// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator; afterwards all
-// 8 warps drain the accumulator (TMEM lane quarter q = warp % 4, column half = warp / 4).  BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32 fp32
-// (= one 128-byte swizzle span = 4 UMMA K-steps of 8).
+// Warp roles (256 threads): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM allocator, warps 4-7 = lo()
+// converters (fp32 tier); afterwards all 8 warps drain the accumulator (TMEM lane quarter q = warp % 4, column half =
+// warp / 4).  BLOCK_M = 128, BLOCK_N = 128, BLOCK_K = 32 fp32 (= one 128-byte swizzle span = 4 UMMA K-steps of 8).
 #include <cstdio>
 #include <cstdlib>
 
@@ -24,15 +36,16 @@
 
 namespace msfno {
 
-static constexpr int TC_BM = 128, TC_BN = 128, TC_STAGES = 3;  // 3 x 32 KB stages -> two CTAs per SM (one's epilogue overlaps the other's main loop)
+static constexpr int TC_BM = 128, TC_BN = 128, TC_STAGES = 3;
 static constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;  // 16 KB
 static constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;  // 16 KB
-static constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-static constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+static constexpr int TC_HI_BYTES = TC_A_BYTES + TC_B_BYTES;   // what TMA writes per stage
+static constexpr int TC_NCONV = 128;                          // converter threads (warps 4-7)
+// tf32 tier: 3 x 32 KB stages -> two CTAs per SM (one's epilogue overlaps the other's main loop)
+static constexpr int TC_SMEM_BYTES = TC_STAGES * TC_HI_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 struct TcParams {
   float* D;
-  long long* trace;   // debug (MSFNO_GEMM_TRACE): clock stamps of every CTA of the pair kernel, or null
   long long lda, ldb, ldd;
   const GemmGroup* groups;
   GemmGroup single;
@@ -43,16 +56,188 @@ struct TcParams {
   int tilesN, tilesM;
   const float* bias; long long sbias;
   const float* add; long long ldadd, sadd;
+  const float* mask; long long ldmask;
+  int accumulate;
   int act_gelu;
   long long lda2, ldb2, sa2, sb2;
   int K2;
+  int b_group_rows;   // > 0: B (MN-major) is a 3-D tensor [tables][b_group_rows][ldb]
 };
 
-template <bool B_MN>
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+#define MSFNO_TC_LD32(r, taddr)                                                                                          \
+  asm volatile(                                                                                                          \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                          \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                          \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"                        \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),      \
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),           \
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),          \
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])                        \
+      : "r"(taddr))
+
+// lo(x) = x - (x with the 13 low mantissa bits cleared): what the tensor core does not see of an fp32 operand
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// one stage: lo() of `bytes` bytes at src -> dst (same offsets: the swizzled layout is preserved), by `nthr` threads
+__device__ __forceinline__ void convert_stage_lo(const uint8_t* src, uint8_t* dst, int bytes, int t, int nthr) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+  for (int i = t; i < bytes / 16; i += nthr) {
+    const float4 v = s4[i];
+    d4[i] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+  }
+}
+
+// Epilogue of one 32 x 32 block held one row per lane: v[j] = raw accumulator of (row, n0 + c0 + j).
+// EXACT: fp32 tier (erf GELU instead of the fit).
+template <bool EXACT>
+__device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const GemmGroup& grp, float (&v)[32], float* wtile, int q,
+                                                  int lane, int m0, int n0, int c0) {
+  const int gn = n0 + c0;
+  if (gn >= grp.N) return;                              // warp-uniform
+  const int row = m0 + q * 32 + lane;
+  const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
+  const bool row_ok = row < grp.M;
+  const bool full_vec = vec && gn + 31 < grp.N;         // warp-uniform
+  if (p.bias || p.act_gelu) {
+    const float bv = (p.bias && row_ok) ? p.bias[blockIdx.y * p.sbias + row] : 0.0f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float t = v[j] + bv;
+      if (p.act_gelu) t = EXACT ? gelu_erf(t) : gelu_tanh3(t);
+      v[j] = t;
+    }
+  }
+  if (p.add && row_ok) {
+    const float* arow = p.add + blockIdx.y * p.sadd + (long long)row * p.ldadd;
+    if (full_vec && ((p.ldadd | p.sadd) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.add) & 15) == 0) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 a4 = *reinterpret_cast<const float4*>(arow + gn + j);
+        v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (gn + j < grp.N) v[j] += arow[gn + j];
+    }
+  }
+  if (p.mask && row_ok) {   // ReLU backward on the real parts: zero where the forward activation was not positive
+    const float* mrow = p.mask + grp.d_off + (long long)row * p.ldmask;
+#pragma unroll
+    for (int j = 0; j < 32; j += 2)
+      if (gn + j < grp.N && !(mrow[gn + j] > 0.f)) v[j] = 0.f;
+  }
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (p.relu_even && !(j & 1)) v[j] = fmaxf(v[j], 0.f);
+    if (p.round_tf32) v[j] = round_to_tf32(v[j]);
+  }
+  if (vec) {   // all lanes take part: rows beyond M and columns beyond N are masked inside
+    store_block_transposed(v, wtile, p.D + grp.d_off + (long long)(m0 + q * 32) * p.ldd + gn, p.ldd, grp.M - (m0 + q * 32),
+                           lane, grp.N - gn, p.accumulate != 0);
+  } else if (row_ok) {
+    float* drow = p.D + grp.d_off + (long long)row * p.ldd;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (gn + j < grp.N) drow[gn + j] = p.accumulate ? drow[gn + j] + v[j] : v[j];
+  }
+}
+
+// Epilogue from TMEM (tf32 tier: the accumulator lived in tensor memory): this warp drains TMEM lane quarter q, columns
+// [c_begin, c_end) of a tile whose first row / column are m0 / n0.
+template <bool EXACT>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, const GemmGroup& grp, uint32_t tmem_base, float* wtile, int q,
+                                            int lane, int m0, int n0, int c_begin, int c_end, bool have_acc) {
+#pragma unroll 1
+  for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+    uint32_t r[32];
+    if (have_acc) {
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      MSFNO_TC_LD32(r, taddr);
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) r[j] = 0u;
+    }
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    tc_epilogue_chunk<EXACT>(p, grp, v, wtile, q, lane, m0, n0, c0);
+  }
+}
+
+// shared-memory matrix descriptor of k-step k (8 tf32) of an operand tile at shared address `tile`.
+// K-major: advance 32 bytes inside the swizzle span; MN-major (SW128_BASE32B): 8 k-rows = two 512-byte atoms (SBO),
+// 32-element M / N blocks 4096 bytes apart (LBO)
+template <bool MN>
+__device__ __forceinline__ uint64_t tc_desc(uint32_t tile, int k) {
+  return MN ? make_smem_desc(tile + 1024 * k, TC_BK * 128, 512, 1) : make_smem_desc(tile + 32 * k, 16, 1024);
+}
+
+// TMA producer loop of the single-CTA kernels (one thread): A tile at stage offset 0, B tile at TC_A_BYTES.
+// first operand pair: offsets come from the group; second pair: plain strided batch (blockIdx.y * s?2)
+template <bool A_MN, bool B_MN>
+__device__ __forceinline__ void tc_producer(const TcParams& p, const GemmGroup& grp, const CUtensorMap& tmA, const CUtensorMap& tmB,
+                                            const CUtensorMap& tmA2, const CUtensorMap& tmB2, uint8_t* tiles, int stage_bytes,
+                                            int nstages, uint64_t* full, uint64_t* empty, int m0, int n0, int nkb1, int nkb) {
+  const long long a_off2 = blockIdx.y * p.sa2, b_off2 = blockIdx.y * p.sb2;
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb % nstages;
+    const uint32_t ph = (uint32_t)((kb / nstages) & 1);
+    const bool second = kb >= nkb1;
+    const int kk = (second ? kb - nkb1 : kb) * TC_BK;
+    const long long aoff = second ? a_off2 : grp.a_off, boff = second ? b_off2 : grp.b_off;
+    const long long lda = second ? p.lda2 : p.lda, ldb = second ? p.ldb2 : p.ldb;
+    const CUtensorMap* ma = second ? &tmA2 : &tmA;
+    const CUtensorMap* mb = second ? &tmB2 : &tmB;
+    mbar_wait_bounded(&empty[s], ph ^ 1u);
+    mbar_arrive_expect_tx(&full[s], TC_HI_BYTES);
+    uint8_t* sa = tiles + s * stage_bytes;
+    if (!A_MN) {
+      tma_load_2d(sa, ma, &full[s], (int)(aoff % lda) + kk, (int)(aoff / lda) + m0);
+    } else {
+      // [K][M] operand: four boxes of 32 (m) x 32 (k); box j holds m in [m0 + 32 j, +32)
+      const int mcol = (int)(aoff % lda) + m0, krow = (int)(aoff / lda) + kk;
+#pragma unroll
+      for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d(sa + j * (TC_BK * 128), ma, &full[s], mcol + 32 * j, krow);
+    }
+    if (!B_MN) {
+      tma_load_2d(sa + TC_A_BYTES, mb, &full[s], (int)(boff % ldb) + kk, (int)(boff / ldb) + n0);
+    } else {
+      // [K][N] operand: four boxes of 32 (n) x 32 (k); box j holds n in [n0 + 32 j, +32)
+      const int ncol = (int)(boff % ldb) + n0;
+      const long long brow = boff / ldb;
+      if (p.b_group_rows > 0 && !second) {
+        const int tab = (int)(brow / p.b_group_rows), krow = (int)(brow % p.b_group_rows) + kk;
+#pragma unroll
+        for (int j = 0; j < TC_BN / 32; ++j) tma_load_3d(sa + TC_A_BYTES + j * (TC_BK * 128), mb, &full[s], ncol + 32 * j, krow, tab);
+      } else {
+        const int krow = (int)brow + kk;
+#pragma unroll
+        for (int j = 0; j < TC_BN / 32; ++j) tma_load_2d(sa + TC_A_BYTES + j * (TC_BK * 128), mb, &full[s], ncol + 32 * j, krow);
+      }
+    }
+  }
+}
+
+// =============================================================================================================
+// tf32 tier: one MMA per k-step, accumulator in TMEM for the whole K loop.
+template <bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(256, 2)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, TcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  constexpr int STAGE = TC_HI_BYTES;
   GemmGroup grp;
   if (p.use_single) {
     grp = p.single;
@@ -67,14 +252,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int m0 = tm * TC_BM, n0 = tn * TC_BN;
   if (m0 >= grp.M || n0 >= grp.N) return;  // uniform for the CTA, before any barrier / allocation
   pdl_trigger();
-  const long long t_start = clock64();
-  const int cta_lin = blockIdx.y * gridDim.x + blockIdx.x;
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle-128B tiles need 1024-byte alignment
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * TC_STAGE_BYTES);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + TC_STAGES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + TC_STAGES * STAGE);
+  uint64_t* full = bars;                          // TMA bytes of the stage have landed
+  uint64_t* empty = bars + TC_STAGES;             // the MMAs that read the stage have completed
   uint64_t* tmem_full = bars + 2 * TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 1);
 
@@ -99,56 +282,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // the prologue above overlapped the previous kernel; its outputs are visible from here on
-  if (p.trace && threadIdx.x == 0 && cta_lin < 1024) p.trace[cta_lin * 8 + 1] = clock64() - t_start;
 
   if (nkb > 0) {
     if (warp == 0 && lane == 0) {
-      // ---------------- TMA producer ----------------
-      // first pair: offsets come from the group; second pair: plain strided batch (blockIdx.y * s?2)
-      const long long a_off2 = blockIdx.y * p.sa2, b_off2 = blockIdx.y * p.sb2;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % TC_STAGES;
-        const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
-        const bool second = kb >= nkb1;
-        const int kk = (second ? kb - nkb1 : kb) * TC_BK;
-        const long long aoff = second ? a_off2 : grp.a_off, boff = second ? b_off2 : grp.b_off;
-        const long long lda = second ? p.lda2 : p.lda, ldb = second ? p.ldb2 : p.ldb;
-        const CUtensorMap* ma = second ? &tmA2 : &tmA;
-        const CUtensorMap* mb = second ? &tmB2 : &tmB;
-        mbar_wait_bounded(&empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[s], TC_STAGE_BYTES);
-        uint8_t* sa = tiles + s * TC_STAGE_BYTES;
-        tma_load_2d(sa, ma, &full[s], (int)(aoff % lda) + kk, (int)(aoff / lda) + m0);
-        if (!B_MN) {
-          tma_load_2d(sa + TC_A_BYTES, mb, &full[s], (int)(boff % ldb) + kk, (int)(boff / ldb) + n0);
-        } else {
-          // [K][N] operand: four boxes of 32 (n) x 32 (k); box j holds n in [n0 + 32 j, +32)
-          const int ncol = (int)(boff % ldb) + n0, krow = (int)(boff / ldb) + kk;
-#pragma unroll
-          for (int j = 0; j < TC_BN / 32; ++j)
-            tma_load_2d(sa + TC_A_BYTES + j * (TC_BK * 128), mb, &full[s], ncol + 32 * j, krow);
-        }
-      }
+      tc_producer<A_MN, B_MN>(p, grp, tmA, tmB, tmA2, tmB2, tiles, STAGE, TC_STAGES, full, empty, m0, n0, nkb1, nkb);
     } else if (warp == 1 && lane == 0) {
       // ---------------- MMA issuer ----------------
-      // instruction descriptor: D=f32 (bit 4), A=B=tf32 (bits 7,10), B major (bit 16), N>>3 at bit 17, M>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((B_MN ? 1u : 0u) << 16) |
+      // instruction descriptor: D=f32 (bit 4), A=B=tf32 (bits 7,10), A / B major (bits 15, 16), N>>3 at bit 17, M>>4 at bit 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
         mbar_wait_bounded(&full[s], ph);
         tc_fence_after();
-        const uint32_t sa = base + s * TC_STAGE_BYTES;
+        const uint32_t sa = base + s * STAGE;
         const uint32_t sb = sa + TC_A_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          // A (K-major): advance 8 tf32 = 32 bytes inside the swizzle span
-          const uint64_t adesc = make_smem_desc(sa + 32 * k, 16, 1024);
-          // B K-major: same; B MN-major (SW128_BASE32B): 8 k-rows = two 512-byte atoms (SBO), N blocks 4096 bytes apart (LBO)
-          const uint64_t bdesc = B_MN ? make_smem_desc(sb + 1024 * k, TC_BK * 128, 512, 1) : make_smem_desc(sb + 32 * k, 16, 1024);
-          tc_mma_tf32(tmem_base, adesc, bdesc, idesc, (kb | k) ? 1u : 0u);
-        }
+        for (int k = 0; k < TC_BK / 8; ++k)
+          tc_mma_tf32(tmem_base, tc_desc<A_MN>(sa, k), tc_desc<B_MN>(sb, k), idesc, (kb | k) ? 1u : 0u);
         tc_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
       }
       tc_commit(tmem_full);    // accumulator complete
@@ -161,102 +313,257 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // warp w drains TMEM lane quarter q = w % 4 (hardware restriction) and column half w / 4
     const int q = warp & 3;
     const int chalf = warp >> 2;
-    const int row = m0 + q * 32 + lane;
     if (nkb > 0) {
       mbar_wait_bounded(tmem_full, 0);
       tc_fence_after();
-      if (p.trace && threadIdx.x == 0 && cta_lin < 1024) p.trace[cta_lin * 8 + 2] = clock64() - t_start;
     }
-    float* drow = p.D + grp.d_off + (long long)row * p.ldd;
-    const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
-    const float bv = (p.bias && row < grp.M) ? p.bias[blockIdx.y * p.sbias + row] : 0.0f;
-    const float* arow = p.add ? p.add + blockIdx.y * p.sadd + (long long)row * p.ldadd : nullptr;
-#pragma unroll 1
-    for (int c0 = chalf * (TC_BN / 2); c0 < (chalf + 1) * (TC_BN / 2); c0 += 32) {
-      uint32_t r[32];
-      if (nkb > 0) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      const int gn = n0 + c0;
-      if (gn < grp.N) {                                     // warp-uniform
-        const bool full_vec = vec && gn + 31 < grp.N;       // warp-uniform
-        const bool row_ok = row < grp.M;
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(r[j]) + bv;
-          if (p.act_gelu) t = gelu_tanh3(t);
-          v[j] = t;
-        }
-        if (arow && row_ok) {
-          if (full_vec && ((p.ldadd | p.sadd) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.add) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 a4 = *reinterpret_cast<const float4*>(arow + gn + j);
-              v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (gn + j < grp.N) v[j] += arow[gn + j];
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          if (p.relu_even && !(j & 1)) v[j] = fmaxf(v[j], 0.f);
-          if (p.round_tf32) v[j] = round_to_tf32(v[j]);
-        }
-        if (vec) {   // all lanes take part: rows beyond M and columns beyond N are masked inside
-          store_block_transposed(v, reinterpret_cast<float*>(tiles) + warp * (32 * 36),
-                                 p.D + grp.d_off + (long long)(m0 + q * 32) * p.ldd + gn, p.ldd, grp.M - (m0 + q * 32), lane, grp.N - gn);
-        } else if (row_ok) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (gn + j < grp.N) drow[gn + j] = v[j];
-        }
-      }
-    }
+    tc_epilogue<false>(p, grp, tmem_base, reinterpret_cast<float*>(tiles) + warp * (32 * 36), q, lane, m0, n0, chalf * (TC_BN / 2),
+                       (chalf + 1) * (TC_BN / 2), nkb > 0);
     tc_fence_before();
   }
   __syncthreads();
-  if (p.trace && threadIdx.x == 0 && cta_lin < 1024) p.trace[cta_lin * 8 + 3] = clock64() - t_start;
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(TC_BN));
   }
 }
 
+// =============================================================================================================
+// fp32 tier: 3xTF32 with the K loop accumulated OUTSIDE the tensor core.
+//
+// The tensor core adds into its TMEM accumulator with truncation, not round-to-nearest: measured on B200, the relative
+// error of a K = 1024 product accumulated in TMEM is 7.6e-6 (biased towards zero, growing with K) against 5.8e-7 for
+// FFMA.  So every 32-wide k-block is multiplied into a FRESH accumulator (accumulate = 0 on its first MMA; two TMEM
+// buffers alternate) -- the eight small-term MMAs first, then the four hi*hi ones -- and eight accumulator warps drain
+// it with tcgen05.ld into fp32 registers, adding with round-to-nearest while the tensor core works on the next k-block.
+// 16 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = converters, 8-15 = accumulators / epilogue.
+//
+// Converters (thread = tile row): a K-major A tile is read once from shared memory (one swizzled 16-byte chunk per lane
+// and access: conflict-free), split and written to TENSOR MEMORY as the A operand (hi and lo, 32 columns each per
+// stage), so the MMAs read only B from shared memory: 3 x 4 KB per k-step instead of 6 x 4 KB -- with 4-byte operands
+// the 128 B/clk shared-memory port, not the tensor pipe, is what bounds these kernels.  An MN-major A (adjoints) keeps
+// its lo() tile in shared memory.  B's lo() tile is always made in shared memory (elementwise, layout preserved).
+template <bool A_MN> struct Tc3Cfg {
+  static constexpr bool A_TMEM = !A_MN;
+  static constexpr int STAGE_BYTES = TC_HI_BYTES + TC_B_BYTES + (A_TMEM ? 0 : TC_A_BYTES);   // A, B, lo(B) [, lo(A)]
+  static constexpr int STAGES = A_TMEM ? 4 : 3;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = A_TMEM ? 512 : 256;    // 2 accumulators of 128 [+ 4 stages x (32 hi + 32 lo) of A]
+};
+static constexpr int TC3_THREADS = 512;
+
+#define MSFNO_TC_ST32(taddr, r)                                                                                          \
+  asm volatile(                                                                                                          \
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "                                                                    \
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "                                         \
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),                 \
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),      \
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),        \
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),        \
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])                                                                     \
+      : "memory")
+
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC3_THREADS, 1)
+gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2, TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  using Cfg = Tc3Cfg<A_MN>;
+  constexpr int STAGE = Cfg::STAGE_BYTES, NST = Cfg::STAGES;
+  constexpr bool A_TMEM = Cfg::A_TMEM;
+  constexpr uint32_t LO_B = TC_HI_BYTES;                   // byte offset of lo(B) in a stage
+  constexpr uint32_t LO_A = TC_HI_BYTES + TC_B_BYTES;      // byte offset of lo(A) in a stage (MN-major A only)
+  GemmGroup grp;
+  if (p.use_single) {
+    grp = p.single;
+    grp.a_off += blockIdx.y * p.sa;
+    grp.b_off += blockIdx.y * p.sb;
+    grp.d_off += blockIdx.y * p.sd;
+  } else {
+    grp = p.groups[blockIdx.y];
+  }
+  const int tn = blockIdx.x / p.tilesM, tm = blockIdx.x - tn * p.tilesM;
+  const int m0 = tm * TC_BM, n0 = tn * TC_BN;
+  if (m0 >= grp.M || n0 >= grp.N) return;  // uniform for the CTA, before any barrier / allocation
+  pdl_trigger();
+
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + NST * STAGE);
+  uint64_t* full = bars;                 // TMA bytes of the stage have landed
+  uint64_t* empty = bars + NST;          // the MMAs that read the stage have completed
+  uint64_t* conv = bars + 2 * NST;       // the lo() tiles (and the TMEM copy of A) of the stage are written
+  uint64_t* acc_full = bars + 3 * NST;   // [2] the k-block product in TMEM buffer b is complete
+  uint64_t* acc_empty = acc_full + 2;    // [2] the accumulator warps have read TMEM buffer b
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb1 = (grp.K + TC_BK - 1) / TC_BK;
+  const int nkb = nkb1 + (p.K2 + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NST; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&conv[s], TC_NCONV);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&acc_full[b], 1);
+      mbar_init(&acc_empty[b], 8);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(Cfg::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_a = tmem_base + 256u;   // A operand: stage s at columns 256 + 64 s (hi) and + 32 (lo)
+  pdl_wait();
+
+  float acc[64];   // accumulator warps: rows q*32 + lane, columns chalf*64 .. +64 of the tile
+#pragma unroll
+  for (int j = 0; j < 64; ++j) acc[j] = 0.f;
+
+  if (nkb > 0) {
+    if (warp == 0 && lane == 0) {
+      tc_producer<A_MN, B_MN>(p, grp, tmA, tmB, tmA2, tmB2, tiles, STAGE, NST, full, empty, m0, n0, nkb1, nkb);
+    } else if (warp == 1 && lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NST, b = kb & 1;
+        mbar_wait_bounded(&full[s], (uint32_t)((kb / NST) & 1));
+        mbar_wait_bounded(&conv[s], (uint32_t)((kb / NST) & 1));
+        mbar_wait_bounded(&acc_empty[b], (uint32_t)(((kb >> 1) & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t sa = base + s * STAGE, sb = sa + TC_A_BYTES;
+        const uint32_t d = tmem_base + (uint32_t)(b * TC_BN);
+        const uint32_t ta = tmem_a + (uint32_t)(s * 64);
+        // small terms first (they add up among themselves at 2^-11 of the magnitude), then hi * hi
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          if (A_TMEM) tc_mma_tf32_ts(d, ta + 32u + 8u * k, tc_desc<B_MN>(sb, k), idesc, k ? 1u : 0u);          // lo(a) hi(b)
+          else tc_mma_tf32(d, tc_desc<A_MN>(sa + LO_A, k), tc_desc<B_MN>(sb, k), idesc, k ? 1u : 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          if (A_TMEM) tc_mma_tf32_ts(d, ta + 8u * k, tc_desc<B_MN>(sa + LO_B, k), idesc, 1u);                  // hi(a) lo(b)
+          else tc_mma_tf32(d, tc_desc<A_MN>(sa, k), tc_desc<B_MN>(sa + LO_B, k), idesc, 1u);
+        }
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          if (A_TMEM) tc_mma_tf32_ts(d, ta + 8u * k, tc_desc<B_MN>(sb, k), idesc, 1u);                         // hi(a) hi(b)
+          else tc_mma_tf32(d, tc_desc<A_MN>(sa, k), tc_desc<B_MN>(sb, k), idesc, 1u);
+        }
+        tc_commit(&empty[s]);       // the stage (and its TMEM copy of A) may be refilled
+        tc_commit(&acc_full[b]);    // the k-block product is complete
+      }
+    } else if (warp >= 4 && warp < 8) {
+      // ---------------- converters ----------------
+      const int t = threadIdx.x - 128;            // = tile row of A (TMEM lane): warp 4 + q owns lane quarter q
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % NST;
+        mbar_wait_bounded(&full[s], (uint32_t)((kb / NST) & 1));
+        uint8_t* st = tiles + s * STAGE;
+        if (A_TMEM) {
+          // row t of the K-major A tile: 128 bytes, its 16-byte chunk c stored at chunk position c ^ (t % 8)
+          uint32_t hi[32], lo[32];
+          const uint8_t* rowp = st + t * 128;
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 v = *reinterpret_cast<const float4*>(rowp + ((c ^ (t & 7)) << 4));
+            hi[4 * c] = __float_as_uint(v.x); hi[4 * c + 1] = __float_as_uint(v.y);
+            hi[4 * c + 2] = __float_as_uint(v.z); hi[4 * c + 3] = __float_as_uint(v.w);
+            lo[4 * c] = __float_as_uint(tf32_lo(v.x)); lo[4 * c + 1] = __float_as_uint(tf32_lo(v.y));
+            lo[4 * c + 2] = __float_as_uint(tf32_lo(v.z)); lo[4 * c + 3] = __float_as_uint(tf32_lo(v.w));
+          }
+          const uint32_t ta = tmem_a + (uint32_t)(s * 64) + ((uint32_t)((warp & 3) * 32) << 16);
+          MSFNO_TC_ST32(ta, hi);
+          MSFNO_TC_ST32(ta + 32u, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+        } else {
+          convert_stage_lo(st, st + LO_A, TC_A_BYTES, t, TC_NCONV);
+        }
+        convert_stage_lo(st + TC_A_BYTES, st + LO_B, TC_B_BYTES, t, TC_NCONV);
+        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) reads
+        tc_fence_before();
+        mbar_arrive(&conv[s]);
+      }
+    } else if (warp >= 8) {
+      // ---------------- accumulators: acc += TMEM buffer (round-to-nearest adds on the CUDA cores) ----------------
+      const int q = warp & 3, chalf = (warp - 8) >> 2;
+      const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int b = kb & 1;
+        mbar_wait_bounded(&acc_full[b], (uint32_t)((kb >> 1) & 1));
+        tc_fence_after();
+        const uint32_t src = tmem_base + lane_off + (uint32_t)(b * TC_BN + chalf * 64);
+        uint32_t r[32];
+        MSFNO_TC_LD32(r, src);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] += __uint_as_float(r[j]);
+        MSFNO_TC_LD32(r, src + 32u);
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&acc_empty[b]);   // the tensor core may overwrite the buffer
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[32 + j] += __uint_as_float(r[j]);
+      }
+    }
+  }
+
+  if (warp >= 8) {
+    // ---------------- epilogue from the register accumulators ----------------
+    // (all MMAs have completed and every converter has finished: the last acc_full was observed above)
+    const int q = warp & 3, chalf = (warp - 8) >> 2;
+    float* wtile = reinterpret_cast<float*>(tiles) + (warp - 8) * (32 * 36);
+    float v[32];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = acc[32 * h + j];
+      tc_epilogue_chunk<true>(p, grp, v, wtile, q, lane, m0, n0, chalf * 64 + 32 * h);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
-// CTA-pair variant (cta_group::2): two CTAs of a cluster (the two SMs of a TPC) compute one 256 x 256 tile.
+// CTA-pair variant (cta_group::2), tf32 tier: two CTAs of a cluster (the two SMs of a TPC) compute one 256 x 256 tile.
 // Each CTA stages ITS 128 rows of A and ITS 128 rows of B (= 128 of the 256 output columns); the leader's single
 // thread issues tcgen05.mma.cta_group::2 (M = 256, N = 256), which reads both CTAs' shared memory and writes each
 // CTA's 128 x 256 accumulator slice into that CTA's TMEM.  With 4-byte operands a single-CTA 128 x 128 tile needs
 // 128 B/clk of smem reads for the MMA plus 128 B/clk of TMA writes, twice what an SM's shared memory delivers; the
 // pair halves both (each operand byte is staged once per pair), which is what lets the TF32 MLP GEMMs leave the
 // 40 % plateau.  Barriers: full[s] lives in the leader (both producers' TMA bytes complete on it), empty[s] and
-// tmem_full exist in both CTAs and are signalled by multicast commits.  K-major B, single operand pair only.
+// tmem_full exist in both CTAs and are signalled by multicast commits.  K-major operands, single operand pair only.
 static constexpr int TC2_BN = 256;
 static constexpr int TC2_STAGE_BYTES = TC_A_BYTES + TC_A_BYTES;   // 128 rows of A + 128 rows of B per CTA
 static constexpr int TC2_SMEM_BYTES = TC_STAGES * TC2_STAGE_BYTES + 1024 + 256;
 
-__device__ __forceinline__ uint32_t __smid() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%smid;\n" : "=r"(r));
-  return r;
-}
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
   asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
@@ -311,8 +618,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int n0 = tn * TC2_BN;
   if (tm * 256 >= grp.M || n0 >= grp.N) return;                // uniform for the PAIR
   pdl_trigger();
-  long long t_start = 0;
-  if (p.trace && threadIdx.x == 0) { t_start = clock64(); p.trace[blockIdx.x * 8 + 0] = (long long)(__smid()); }
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
@@ -342,7 +647,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
-  if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 1] = clock64() - t_start;
 
   if (nkb > 0) {
     if (warp == 0 && lane == 0) {
@@ -383,59 +687,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ---------------- epilogue: this CTA's 128 rows x 256 columns ----------------
     const int q = warp & 3;
     const int chalf = warp >> 2;
-    const int row = m0 + q * 32 + lane;
     if (nkb > 0) {
       mbar_wait_bounded(tmem_full, 0);
       tc_fence_after();
-      if (p.trace && threadIdx.x == 0) p.trace[blockIdx.x * 8 + 2] = clock64() - t_start;
     }
-    float* drow = p.D + grp.d_off + (long long)row * p.ldd;
-    const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
-    const float bv = (p.bias && row < grp.M) ? p.bias[blockIdx.y * p.sbias + row] : 0.0f;
-#pragma unroll 1
-    for (int c0 = chalf * (TC2_BN / 2); c0 < (chalf + 1) * (TC2_BN / 2); c0 += 32) {
-      uint32_t r[32];
-      if (nkb > 0) {
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-              "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-              "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-              "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      const int gn = n0 + c0;
-      if (gn < grp.N) {                                     // warp-uniform
-        const bool full_vec = vec && gn + 31 < grp.N;       // warp-uniform
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(r[j]) + bv;
-          if (p.act_gelu) t = gelu_tanh3(t);
-          if (p.relu_even && !(j & 1)) t = fmaxf(t, 0.f);
-          if (p.round_tf32) t = round_to_tf32(t);
-          v[j] = t;
-        }
-        if (vec) {   // all lanes take part: rows beyond M and columns beyond N are masked inside
-          store_block_transposed(v, reinterpret_cast<float*>(tiles) + warp * (32 * 36),
-                                 p.D + grp.d_off + (long long)(m0 + q * 32) * p.ldd + gn, p.ldd, grp.M - (m0 + q * 32), lane, grp.N - gn);
-        } else if (row < grp.M) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (gn + j < grp.N) drow[gn + j] = v[j];
-        }
-      }
-    }
+    tc_epilogue<false>(p, grp, tmem_base, reinterpret_cast<float*>(tiles) + warp * (32 * 36), q, lane, m0, n0, chalf * (TC2_BN / 2),
+                       (chalf + 1) * (TC2_BN / 2), nkb > 0);
     tc_fence_before();
   }
-  if (p.trace && threadIdx.x == 0) { p.trace[blockIdx.x * 8 + 3] = clock64() - t_start; p.trace[blockIdx.x * 8 + 4] = t_start; }
   cluster_sync_all();   // neither CTA may retire (or free TMEM) while its peer can still touch it
   if (warp == 2) {
     tc_fence_after();
@@ -447,24 +706,94 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 bool gemm_tc_supported(const GemmLaunch& g) {
-  if (!g.a_kmajor || g.mask || g.accumulate) return false;
   if ((g.lda & 3) || (g.ldb & 3) || !aligned16(g.A) || !aligned16(g.B)) return false;
-  if (g.A2 && ((g.lda2 & 3) || (g.ldb2 & 3) || !aligned16(g.A2) || !aligned16(g.B2))) return false;
+  if (g.A2 && (!g.a_kmajor || (g.lda2 & 3) || (g.ldb2 & 3) || !aligned16(g.A2) || !aligned16(g.B2))) return false;
+  if (g.mask && (g.ldmask & 1)) return false;
   return get_encode() != nullptr;
 }
 
-// a_rows / b_rows: rows of the underlying 2-D buffers (TMA zero-fills beyond them); a_cols / b_cols: valid columns.
-// For an MN-major B (g.b_kmajor == 0) the buffer is [K rows][N cols].
+// 3-D fp32 tensor [tables][rows][ld] (cols valid), box = 32 columns x 32 rows x 1 table, 128-byte swizzle with 32-byte atoms
+static int make_map_3d(CUtensorMap* tm, const float* base, long long tables, long long rows, long long cols, long long ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
+  cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)tables};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 4, (cuuint64_t)ld * 4 * (cuuint64_t)rows};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BK, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return record_error(MSFNO_ERR_CUDA, "cuTensorMapEncodeTiled failed (3-D table map)");
+  return MSFNO_OK;
+}
+
+template <typename K>
+static cudaError_t opt_in_smem(K kern, int bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+
+// a_rows / a_cols (b_rows / b_cols): rows and valid columns of the underlying 2-D buffers as they lie in memory (TMA
+// zero-fills beyond them).  For an MN-major operand the buffer is [K rows][M or N cols].  g.b_group_rows > 0 (MN-major
+// B only): the buffer is b_rows / b_group_rows stacked tables of b_group_rows rows each.
 int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
                    int round_tf32, cudaStream_t st, long long a2_rows, long long a2_cols, long long b2_rows,
                    long long b2_cols) {
   if (g.ngroups <= 0 || g.maxM <= 0 || g.maxN <= 0) return MSFNO_OK;
-  const bool bmn = !g.b_kmajor;
-  static const bool pair_off = getenv("MSFNO_GEMM_NO_PAIR") != nullptr;
-  // 256-column pair tiles: with N = 512 only 60 pairs exist for the 7440-row MLP (< 74 TPCs) and the single-CTA
-  // kernel's finer tiles win (tools/gemm_bench.py); MSFNO_GEMM_PAIR_MIN_N overrides for experiments
-  static const int pair_min_n = getenv("MSFNO_GEMM_PAIR_MIN_N") ? atoi(getenv("MSFNO_GEMM_PAIR_MIN_N")) : 768;
-  if (!bmn && !g.A2 && !g.add && g.maxM >= 1024 && g.maxN >= pair_min_n && !pair_off) {
+  const bool amn = !g.a_kmajor, bmn = !g.b_kmajor;
+  const bool x3 = g.x3 != 0;
+  TcParams p{};
+  p.D = g.D; p.lda = g.lda; p.ldb = g.ldb; p.ldd = g.ldd;
+  p.groups = g.groups; p.single = g.single; p.sa = g.sa; p.sb = g.sb; p.sd = g.sd; p.use_single = g.use_single;
+  p.relu_even = g.relu_even; p.round_tf32 = x3 ? 0 : round_tf32;
+  p.bias = g.bias; p.sbias = g.sbias; p.add = g.add; p.ldadd = g.ldadd; p.sadd = g.sadd; p.act_gelu = g.act_gelu;
+  p.mask = g.mask; p.ldmask = g.ldmask; p.accumulate = g.accumulate;
+  p.b_group_rows = (bmn && g.b_group_rows > 0) ? g.b_group_rows : 0;
+
+  if (x3) {
+    // ---- fp32 tier: 3xTF32, K loop accumulated in registers (gemm_tc3_kernel) ----
+    CUtensorMap tmA, tmB, tmA2, tmB2;
+    int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, amn ? TC_BK : TC_BM, amn);
+    if (rc) return rc;
+    if (p.b_group_rows > 0) rc = make_map_3d(&tmB, g.B, b_rows / p.b_group_rows, p.b_group_rows, b_cols, g.ldb);
+    else rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, bmn ? TC_BK : TC_BN, bmn);
+    if (rc) return rc;
+    if (g.A2) {
+      rc = make_map(&tmA2, g.A2, a2_rows, a2_cols, g.lda2, TC_BM);
+      if (rc) return rc;
+      rc = make_map(&tmB2, g.B2, b2_rows, b2_cols, g.ldb2, bmn ? TC_BK : TC_BN, bmn);
+      if (rc) return rc;
+    } else {
+      tmA2 = tmA;
+      tmB2 = tmB;
+    }
+    static std::once_flag once3;
+    static cudaError_t attr_err3 = cudaSuccess;
+    std::call_once(once3, [] {
+      cudaError_t e = cudaSuccess;
+      auto set = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+      set(opt_in_smem(gemm_tc3_kernel<false, false>, Tc3Cfg<false>::SMEM_BYTES));
+      set(opt_in_smem(gemm_tc3_kernel<false, true>, Tc3Cfg<false>::SMEM_BYTES));
+      set(opt_in_smem(gemm_tc3_kernel<true, false>, Tc3Cfg<true>::SMEM_BYTES));
+      set(opt_in_smem(gemm_tc3_kernel<true, true>, Tc3Cfg<true>::SMEM_BYTES));
+      attr_err3 = e;
+    });
+    MSFNO_CUDA_OK(attr_err3);
+    p.lda2 = g.A2 ? g.lda2 : 4; p.ldb2 = g.A2 ? g.ldb2 : 4; p.sa2 = g.sa2; p.sb2 = g.sb2; p.K2 = g.A2 ? g.K2 : 0;
+    p.tilesM = (g.maxM + TC_BM - 1) / TC_BM;
+    p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;
+    dim3 grid(p.tilesM * p.tilesN, g.ngroups);
+    if (amn && bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<true, true>, grid, dim3(TC3_THREADS), Tc3Cfg<true>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+    else if (amn) MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<true, false>, grid, dim3(TC3_THREADS), Tc3Cfg<true>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+    else if (bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<false, true>, grid, dim3(TC3_THREADS), Tc3Cfg<false>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+    else MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<false, false>, grid, dim3(TC3_THREADS), Tc3Cfg<false>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+    count_launch();
+    MSFNO_CUDA_OK(cudaGetLastError());
+    return MSFNO_OK;
+  }
+
+  // CTA pair (tf32 tier): 256-column tiles; with N = 512 only 60 pairs exist for the 7440-row MLP (< 74 TPCs) and the
+  // single-CTA kernel's finer tiles win (tools/gemm_bench.py)
+  if (!amn && !bmn && !g.A2 && !g.add && !g.mask && !g.accumulate && g.maxM >= 1024 && g.maxN >= 768) {
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, TC_BM);
     if (rc) return rc;
@@ -472,42 +801,22 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     if (rc) return rc;
     static std::once_flag once2;
     static cudaError_t attr_err2 = cudaSuccess;
-    std::call_once(once2, [] { attr_err2 = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC2_SMEM_BYTES); });
+    std::call_once(once2, [] { attr_err2 = opt_in_smem(gemm_tc2_kernel, TC2_SMEM_BYTES); });
     MSFNO_CUDA_OK(attr_err2);
-    TcParams p{};
-    p.D = g.D; p.lda = g.lda; p.ldb = g.ldb; p.ldd = g.ldd;
-    p.groups = g.groups; p.single = g.single; p.sa = g.sa; p.sb = g.sb; p.sd = g.sd; p.use_single = g.use_single;
-    p.relu_even = g.relu_even; p.round_tf32 = round_tf32;
-    p.bias = g.bias; p.sbias = g.sbias; p.act_gelu = g.act_gelu;
     p.tilesM = (g.maxM + 255) / 256;
     p.tilesN = (g.maxN + TC2_BN - 1) / TC2_BN;
     dim3 grid(2 * p.tilesM * p.tilesN, g.ngroups);
-    static const bool trace_on = getenv("MSFNO_GEMM_TRACE") != nullptr;
-    static long long* d_trace = nullptr;
-    if (trace_on) {
-      if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 1024 * 8 * sizeof(long long)));
-      MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 1024 * 8 * sizeof(long long), st));
-      if (grid.x <= 1024 && grid.y == 1) p.trace = d_trace;
-    }
     MSFNO_CUDA_OK(launch_pdl(gemm_tc2_kernel, grid, dim3(256), TC2_SMEM_BYTES, st, tmA, tmB, p));
-    if (trace_on && p.trace) {
-      static long long h[1024 * 8];
-      MSFNO_CUDA_OK(cudaStreamSynchronize(st));
-      MSFNO_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
-      long long t0 = h[4];
-      for (unsigned i = 0; i < grid.x; ++i) if (h[i * 8 + 4] && h[i * 8 + 4] < t0) t0 = h[i * 8 + 4];
-      fprintf(stderr, "gemm_tc2 trace: cta sm | start(rel) prologue_done mainloop_done epilogue_done (clk since CTA start)\n");
-      for (unsigned i = 0; i < grid.x; i += (grid.x > 64 ? 7 : 1))
-        fprintf(stderr, "%4u %3lld | %8lld %8lld %8lld %8lld\n", i, h[i * 8], h[i * 8 + 4] - t0, h[i * 8 + 1], h[i * 8 + 2], h[i * 8 + 3]);
-    }
     count_launch();
     MSFNO_CUDA_OK(cudaGetLastError());
     return MSFNO_OK;
   }
+
   CUtensorMap tmA, tmB, tmA2, tmB2;
-  int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, TC_BM);
+  int rc = make_map(&tmA, g.A, a_rows, a_cols, g.lda, amn ? TC_BK : TC_BM, amn);
   if (rc) return rc;
-  rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, bmn ? TC_BK : TC_BN, bmn);
+  if (p.b_group_rows > 0) rc = make_map_3d(&tmB, g.B, b_rows / p.b_group_rows, p.b_group_rows, b_cols, g.ldb);
+  else rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, bmn ? TC_BK : TC_BN, bmn);
   if (rc) return rc;
   if (g.A2) {
     rc = make_map(&tmA2, g.A2, a2_rows, a2_cols, g.lda2, TC_BM);
@@ -521,39 +830,23 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+    cudaError_t e = cudaSuccess;
+    auto set = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+    set(opt_in_smem(gemm_tc_kernel<false, false>, TC_SMEM_BYTES));
+    set(opt_in_smem(gemm_tc_kernel<false, true>, TC_SMEM_BYTES));
+    set(opt_in_smem(gemm_tc_kernel<true, false>, TC_SMEM_BYTES));
+    set(opt_in_smem(gemm_tc_kernel<true, true>, TC_SMEM_BYTES));
+    attr_err = e;
   });
   MSFNO_CUDA_OK(attr_err);
-  TcParams p{};
-  p.D = g.D; p.lda = g.lda; p.ldb = g.ldb; p.ldd = g.ldd;
-  p.groups = g.groups; p.single = g.single; p.sa = g.sa; p.sb = g.sb; p.sd = g.sd; p.use_single = g.use_single;
-  p.relu_even = g.relu_even; p.round_tf32 = round_tf32;
-  p.bias = g.bias; p.sbias = g.sbias; p.add = g.add; p.ldadd = g.ldadd; p.sadd = g.sadd; p.act_gelu = g.act_gelu;
   p.lda2 = g.A2 ? g.lda2 : 4; p.ldb2 = g.A2 ? g.ldb2 : 4; p.sa2 = g.sa2; p.sb2 = g.sb2; p.K2 = g.A2 ? g.K2 : 0;
-  const int tilesM = (g.maxM + TC_BM - 1) / TC_BM;
+  p.tilesM = (g.maxM + TC_BM - 1) / TC_BM;
   p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;
-  p.tilesM = tilesM;
-  dim3 grid(tilesM * p.tilesN, g.ngroups);
-  static const bool trace1_on = getenv("MSFNO_GEMM_TRACE") != nullptr;
-  static long long* d_trace1 = nullptr;
-  if (trace1_on && (long long)grid.x * grid.y <= 1024) {
-    if (!d_trace1) MSFNO_CUDA_OK(cudaMalloc(&d_trace1, 1024 * 8 * sizeof(long long)));
-    MSFNO_CUDA_OK(cudaMemsetAsync(d_trace1, 0, 1024 * 8 * sizeof(long long), st));
-    p.trace = d_trace1;
-  }
-  if (bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<true>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
-  else MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<false>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
-  if (p.trace) {
-    static long long h[1024 * 8];
-    MSFNO_CUDA_OK(cudaStreamSynchronize(st));
-    MSFNO_CUDA_OK(cudaMemcpy(h, d_trace1, sizeof(h), cudaMemcpyDeviceToHost));
-    double a1 = 0, a2 = 0, a3 = 0; int n = 0;
-    for (int i = 0; i < 1024; ++i) if (h[i * 8 + 3]) { a1 += h[i * 8 + 1]; a2 += h[i * 8 + 2]; a3 += h[i * 8 + 3]; ++n; }
-    if (n) fprintf(stderr, "gemm_tc trace grid=(%u,%u) maxM=%d maxN=%d: mean clk since CTA start: prologue %.0f  mainloop_done %.0f  cta_done %.0f  (n=%d)\n",
-                   grid.x, grid.y, g.maxM, g.maxN, a1 / n, a2 / n, a3 / n, n);
-  }
+  dim3 grid(p.tilesM * p.tilesN, g.ngroups);
+  if (amn && bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<true, true>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+  else if (amn) MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<true, false>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+  else if (bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<false, true>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+  else MSFNO_CUDA_OK(launch_pdl(gemm_tc_kernel<false, false>, grid, dim3(256), TC_SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

@@ -26,6 +26,10 @@ bool pdl_enabled() {
 
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
+// engine of the fp32 (1e-5) tier's GEMM-shaped stages: 3xTF32 on the tensor cores (default) or CUDA-core FFMA
+static std::atomic<int> g_fp32_engine{MSFNO_FP32_ENGINE_TC3X};
+bool fp32_engine_x3() { return g_fp32_engine.load(std::memory_order_relaxed) == MSFNO_FP32_ENGINE_TC3X; }
+
 int record_error(int code, const char* msg) {
   g_last_error = msg;
   return code;
@@ -181,8 +185,16 @@ const char* msfno_last_error(void) { return g_last_error.c_str(); }
 
 unsigned long long msfno_launch_count(void) { return g_launches.load(); }
 
+int msfno_set_fp32_engine(int engine) {
+  if (engine != MSFNO_FP32_ENGINE_TC3X && engine != MSFNO_FP32_ENGINE_FFMA)
+    return record_error(MSFNO_ERR_BAD_SHAPE, "set_fp32_engine: bad argument");
+  g_fp32_engine.store(engine, std::memory_order_relaxed);
+  return MSFNO_OK;
+}
+int msfno_get_fp32_engine(void) { return g_fp32_engine.load(std::memory_order_relaxed); }
+
 const char* msfno_build_info(void) {
-  return "{\"arch\": \"sm_100a\", \"abi\": 2, \"tiers\": [\"fp32\", \"tf32\"], \"fft\": \"four-step in-register (fp32 tier)\", "
+  return "{\"arch\": \"sm_100a\", \"abi\": 3, \"tiers\": [\"fp32 (3xTF32 on tcgen05, or FFMA)\", \"tf32\"], \"fft\": \"four-step in-register (fp32 tier)\", "
          "\"tensor_core\": [\"tcgen05 tf32 gemm (cta_group::1 and ::2)\", \"dft gemm\", \"parity-split persistent inverse dft (tma stores)\", \"fused mlp (A operand in TMEM)\", \"1x1 conv\"], "
          "\"streams\": [\"specconv tma ring\"]}";
 }

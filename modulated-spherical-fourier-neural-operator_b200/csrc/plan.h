@@ -90,15 +90,23 @@ struct GemmLaunch {
   int use_single;           // 1: ignore `groups`; group y = `single` shifted by y * (sa, sb, sd) (strided batch)
   GemmGroup single;
   long long sa, sb, sd;
+  // tensor-core engine only (gemm_tc.cu)
+  int x3;                   // fp32 tier: three TF32 MMAs per k-step on hi / lo operand splits ("3xTF32")
+  int b_group_rows;         // > 0 with an MN-major B: B is a stack of tables of this many rows each; K rows past the end of
+                            // a table read zeros (3-D tensor map) instead of the next table
 };
 int launch_gemm_ffma(const GemmLaunch& g, cudaStream_t st);
 int launch_gemm_single(const float* A, long long lda, int a_kmajor, const float* B, long long ldb, int b_kmajor,
                        float* D, long long ldd, int M, int N, int K, int relu_even, const float* mask,
                        long long ldmask, int accumulate, cudaStream_t st);
 
-// tcgen05 / TMEM / TMA TF32 path (gemm_tc.cu).  Supported when both operands are K-major, 16-byte aligned,
-// no ReLU-mask / accumulate epilogue.  a_rows/a_cols (b_rows/b_cols) describe the whole 2-D buffer behind A (B).
+// tcgen05 / TMEM / TMA path (gemm_tc.cu): TF32 (one MMA per k-step) or, with g.x3, fp32-grade 3xTF32.  Supported when the
+// operands are 16-byte aligned with leading dimensions that are multiples of 4; either majorness, ReLU-mask and
+// accumulate epilogues included.  a_rows/a_cols (b_rows/b_cols) describe the whole 2-D buffer behind A (B).
+// fp32_engine_x3(): true unless msfno_set_fp32_engine(MSFNO_FP32_ENGINE_FFMA) selected the CUDA-core engine for the
+// fp32 tier (kept for shapes the tensor-core path rejects, and as the cross-check in the tests).
 bool gemm_tc_supported(const GemmLaunch& g);
+bool fp32_engine_x3();
 int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
                    int round_tf32, cudaStream_t st, long long a2_rows = 0, long long a2_cols = 0, long long b2_rows = 0,
                    long long b2_cols = 0);

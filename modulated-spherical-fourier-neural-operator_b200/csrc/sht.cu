@@ -9,6 +9,11 @@
 
 using namespace msfno;
 
+// One grouped Legendre contraction (forward or adjoint) over the azimuthal orders [m_lo, m_hi).
+// Engine: tensor cores whenever TMA can address the operands -- plain TF32 for the forward transforms of the tf32 tier,
+// 3xTF32 (fp32 grade) for the fp32 tier and for every adjoint (gradients are not TF32-rounded by their producers, and
+// the truncation bias of a plain TF32 MMA would compound over the 24 transforms of a backward pass); the CUDA-core
+// FFMA kernel otherwise (msfno_set_fp32_engine(FFMA), unaligned operands).
 static int legendre_gemm(msfno_plan* p, int kind, const float* A, long long lda, int a_k, const float* B, long long ldb,
                          int b_k, float* D, long long ldd, int maxM, int maxN, int Bsz, int C, cudaStream_t st,
                          int m_lo = 0, int m_hi = -1, int round_out = 0) {
@@ -21,12 +26,27 @@ static int legendre_gemm(msfno_plan* p, int kind, const float* A, long long lda,
   g.lda = lda; g.ldb = ldb; g.ldd = ldd;
   g.a_kmajor = a_k; g.b_kmajor = b_k;
   g.groups = groups; g.ngroups = ng; g.maxM = maxM; g.maxN = maxN;
-  if (p->precision == MSFNO_PREC_TF32 && (kind == GK_ANALYSIS || kind == GK_SYNTHESIS) && gemm_tc_supported(g)) {
-    // tensor-core tier: the 2-D buffers behind A and B as TMA sees them (zero-fill outside)
-    const int mloc = (m_hi < 0 ? p->mlim : m_hi) - m_lo;
-    if (kind == GK_ANALYSIS)
-      return launch_gemm_tc(g, (long long)p->mlim * p->Lj, p->kpad, (long long)Bsz * mloc * 2 * C, p->kpad, 0, st);
-    return launch_gemm_tc(g, (long long)Bsz * 2 * C, lda, (long long)p->mlim * p->nlat, p->Lj, round_out, st);
+  const bool fwd = kind == GK_ANALYSIS || kind == GK_SYNTHESIS;
+  const bool tf32 = p->precision == MSFNO_PREC_TF32 && fwd;
+  if ((tf32 || fp32_engine_x3()) && gemm_tc_supported(g)) {
+    g.x3 = tf32 ? 0 : 1;
+    // the 2-D buffers behind A and B as TMA sees them (zero-fill outside)
+    if (m_hi < 0 || m_hi > p->mlim) m_hi = p->mlim;
+    const long long mloc = m_hi - m_lo;
+    const long long Ploc = ((m_hi < p->mlim) ? p->h_poff[m_hi] : p->P) - p->h_poff[m_lo];
+    const long long C2 = 2 * C;
+    switch (kind) {
+      case GK_ANALYSIS:       // tab_lk [mlim Lj][kpad] x Xt [B mloc 2C][kpad]
+        return launch_gemm_tc(g, (long long)p->mlim * p->Lj, p->kpad, Bsz * mloc * C2, p->kpad, 0, st);
+      case GK_SYNTHESIS:      // coef_cm [B 2C][Ploc] x tab_kl [mlim nlat][Lj]
+        return launch_gemm_tc(g, Bsz * C2, Ploc, (long long)p->mlim * p->nlat, p->Lj, tf32 ? round_out : 0, st);
+      case GK_ANALYSIS_ADJ:   // g_pm [B Ploc][2C] (M contiguous) x tab_lk [mlim][Lj][kpad] (N contiguous, stacked tables)
+        g.b_group_rows = p->Lj;
+        return launch_gemm_tc(g, Bsz * Ploc, C2, (long long)p->mlim * p->Lj, p->kpad, 0, st);
+      default:                // gYt [B mloc 2C][kpad] x tab_kl [mlim][nlat][Lj] (N contiguous, stacked tables)
+        g.b_group_rows = p->nlat;
+        return launch_gemm_tc(g, Bsz * mloc * C2, p->kpad, (long long)p->mlim * p->nlat, p->Lj, 0, st);
+    }
   }
   return launch_gemm_ffma(g, st);
 }

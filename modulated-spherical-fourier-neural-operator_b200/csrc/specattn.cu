@@ -48,21 +48,38 @@ __global__ void unpack_cweight_grad_kernel(const float* __restrict__ g, float* _
   }
 }
 
-// D[M][N] = A[M][K] * B[N][K]^T on the selected engine (tensor cores when the tier and the operands allow it)
-static int gemm_nt_any(int tc, const float* A, long long lda, const float* Bm, long long ldb, float* D, long long ldd, int M,
-                       int N, int K, int relu_even, int round_tf32, cudaStream_t st) {
-  if (tc) {
-    GemmLaunch g{};
-    g.A = A; g.B = Bm; g.D = D;
-    g.lda = lda; g.ldb = ldb; g.ldd = ldd;
-    g.a_kmajor = 1; g.b_kmajor = 1;
-    g.relu_even = relu_even;
-    g.ngroups = 1; g.maxM = M; g.maxN = N;
-    g.use_single = 1;
-    g.single = GemmGroup{0, 0, 0, M, N, K, 0};
-    if (gemm_tc_supported(g)) return launch_gemm_tc(g, M, K, N, K, round_tf32, st);
+// engine of a GEMM of this file: 0 = CUDA-core FFMA, 1 = plain TF32 MMA, 3 = 3xTF32 (fp32 grade)
+static int engine_of(int tf32) { return tf32 ? 1 : (fp32_engine_x3() ? 3 : 0); }
+
+// One GEMM (single problem or strided batch described by g) on the selected engine; falls back to FFMA when TMA cannot
+// address the operands.  a_rows .. b_cols: the 2-D buffers behind A and B (launch_gemm_tc).
+static int gemm_on(int engine, GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,
+                   int round_tf32, cudaStream_t st) {
+  if (engine && gemm_tc_supported(g)) {
+    g.x3 = engine == 3;
+    return launch_gemm_tc(g, a_rows, a_cols, b_rows, b_cols, engine == 1 ? round_tf32 : 0, st);
   }
-  return launch_gemm_single(A, lda, 1, Bm, ldb, 1, D, ldd, M, N, K, relu_even, nullptr, 0, 0, st);
+  return launch_gemm_ffma(g, st);
+}
+
+static GemmLaunch single_problem(const float* A, long long lda, int a_k, const float* Bm, long long ldb, int b_k, float* D,
+                                 long long ldd, int M, int N, int K) {
+  GemmLaunch g{};
+  g.A = A; g.B = Bm; g.D = D;
+  g.lda = lda; g.ldb = ldb; g.ldd = ldd;
+  g.a_kmajor = a_k; g.b_kmajor = b_k;
+  g.ngroups = 1; g.maxM = M; g.maxN = N;
+  g.use_single = 1;
+  g.single = GemmGroup{0, 0, 0, M, N, K, 0};
+  return g;
+}
+
+// D[M][N] = A[M][K] * B[N][K]^T on the selected engine
+static int gemm_nt_any(int engine, const float* A, long long lda, const float* Bm, long long ldb, float* D, long long ldd, int M,
+                       int N, int K, int relu_even, int round_tf32, cudaStream_t st) {
+  GemmLaunch g = single_problem(A, lda, 1, Bm, ldb, 1, D, ldd, M, N, K);
+  g.relu_even = relu_even;
+  return gemm_on(engine, g, M, K, N, K, round_tf32, st);
 }
 
 struct AttnWs {
@@ -114,7 +131,8 @@ int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* cons
   const AttnWs L = attn_layout(p->P, B, C, hid, nl);
   const int rows = B * p->P;
   const int skip_pack = (precision >> 2) & 1;   // bit 2: ws already holds the packed weights of these parameters
-  const int tc = ((precision & 1) == MSFNO_PREC_TF32);
+  const int tc = ((precision & 1) == MSFNO_PREC_TF32);   // TF32-round the packed weights and the hidden states
+  const int engine = engine_of(tc);
   const float* in = a_pm;
   int cin = C;
   for (int l = 0; l < nl; ++l) {
@@ -122,7 +140,7 @@ int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* cons
       pack_cweight_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(w[l], ws + L.wbig[l], cin, hid, tc);
       count_launch();
     }
-    int rc = gemm_nt_any(tc, in, 2 * cin, ws + L.wbig[l], 2 * cin, ws + L.h[l], 2 * hid, rows, 2 * hid, 2 * cin,
+    int rc = gemm_nt_any(engine, in, 2 * cin, ws + L.wbig[l], 2 * cin, ws + L.h[l], 2 * hid, rows, 2 * hid, 2 * cin,
                          /*relu_even=*/1, /*round_tf32=*/tc, st);
     if (rc) return rc;
     in = ws + L.h[l];
@@ -141,9 +159,7 @@ int msfno_specattn_fwd(const msfno_plan* p, const float* a_pm, const float* cons
   g.use_single = 1;
   g.single = GemmGroup{0, 0, 0, 2 * C, p->P, 2 * hid, 0};
   g.sa = 0; g.sb = (long long)p->P * 2 * hid; g.sd = (long long)2 * C * p->P;
-  int rc;
-  if (tc && gemm_tc_supported(g)) rc = launch_gemm_tc(g, 2 * C, 2 * hid, (long long)B * p->P, 2 * hid, /*round_tf32=*/1, st);
-  else rc = launch_gemm_ffma(g, st);
+  int rc = gemm_on(engine, g, 2 * C, 2 * hid, (long long)B * p->P, 2 * hid, /*round_tf32=*/1, st);
   if (rc) return rc;
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
@@ -162,12 +178,17 @@ int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm
   float* gwbig = scratch + 2 * act;
   const float* hlast = ws + L.h[nl - 1];
 
+  // every GEMM of the backward runs at fp32 grade: 3xTF32 on the tensor cores, or FFMA (msfno_set_fp32_engine)
+  const int engine = engine_of(0);
+
   // ---- output layer: out[b][ch][p] = sum_k Wout_big[ch][k] h[b*P+p][k]
   // gWout_big[ch][k] = sum_{b,p} g_cm[b][ch][p] * h[b*P+p][k]
   if (gwout) {
     for (int b = 0; b < B; ++b) {
-      int rc = launch_gemm_single(g_cm + (size_t)b * 2 * C * P, P, 1, hlast + (size_t)b * P * 2 * hid, 2 * hid, 0, gwbig,
-                                  2 * hid, 2 * C, 2 * hid, P, 0, nullptr, 0, /*accumulate=*/b > 0, st);
+      GemmLaunch g = single_problem(g_cm + (size_t)b * 2 * C * P, P, 1, hlast + (size_t)b * P * 2 * hid, 2 * hid, 0, gwbig,
+                                    2 * hid, 2 * C, 2 * hid, P);
+      g.accumulate = b > 0;
+      int rc = gemm_on(engine, g, 2 * C, P, P, 2 * hid, 0, st);
       if (rc) return rc;
     }
     unpack_cweight_grad_kernel<<<(hid * C + 255) / 256, 256, 0, st>>>(gwbig, gwout, hid, C);
@@ -184,7 +205,7 @@ int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm
     g.use_single = 1;
     g.single = GemmGroup{0, 0, 0, P, 2 * hid, 2 * C, 0};
     g.sa = (long long)2 * C * P; g.sb = 0; g.sd = (long long)P * 2 * hid;
-    int rc = launch_gemm_ffma(g, st);
+    int rc = gemm_on(engine, g, (long long)B * 2 * C, P, 2 * C, 2 * hid, 0, st);
     if (rc) return rc;
   }
   int cur = 0;
@@ -194,15 +215,17 @@ int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm
     // gWbig_l[hidcol][cincol] = sum_rows gz[row][hidcol] * in[row][cincol]
     int rc = MSFNO_OK;
     if (gw[l]) {
-      rc = launch_gemm_single(gz[cur], 2 * hid, 0, in, 2 * cin, 0, gwbig, 2 * cin, 2 * hid, 2 * cin, rows, 0, nullptr, 0, 0, st);
+      GemmLaunch g = single_problem(gz[cur], 2 * hid, 0, in, 2 * cin, 0, gwbig, 2 * cin, 2 * hid, 2 * cin, rows);
+      rc = gemm_on(engine, g, rows, 2 * hid, rows, 2 * cin, 0, st);
       if (rc) return rc;
       unpack_cweight_grad_kernel<<<(cin * hid + 255) / 256, 256, 0, st>>>(gwbig, gw[l], cin, hid);
       count_launch();
     }
     // g_in[row][cincol] = sum_hidcol gz[row][hidcol] * Wbig_l[hidcol][cincol]  (masked by ReLU of the layer below)
     float* dst = (l == 0) ? ga_pm : gz[cur ^ 1];
-    rc = launch_gemm_single(gz[cur], 2 * hid, 1, ws + L.wbig[l], 2 * cin, 0, dst, 2 * cin, rows, 2 * cin, 2 * hid, 0,
-                            (l == 0) ? nullptr : in, 2 * cin, 0, st);
+    GemmLaunch g = single_problem(gz[cur], 2 * hid, 1, ws + L.wbig[l], 2 * cin, 0, dst, 2 * cin, rows, 2 * cin, 2 * hid);
+    if (l > 0) { g.mask = in; g.ldmask = 2 * cin; }
+    rc = gemm_on(engine, g, rows, 2 * hid, 2 * hid, 2 * cin, 0, st);
     if (rc) return rc;
     cur ^= 1;
   }
@@ -213,7 +236,16 @@ int msfno_specattn_bwd(const msfno_plan* p, const float* a_pm, const float* g_cm
 int msfno_gemm_nt(const float* A, long lda, const float* Bm, long ldb, float* D, long ldd, int M, int N, int K,
                   int relu_even_cols, int precision, void* stream) {
   if (!A || !Bm || !D || M < 0 || N < 0 || K < 0) return record_error(MSFNO_ERR_BAD_SHAPE, "gemm_nt: bad argument");
-  return gemm_nt_any(precision == MSFNO_PREC_TF32, A, lda, Bm, ldb, D, ldd, M, N, K, relu_even_cols, 0, (cudaStream_t)stream);
+  return gemm_nt_any(engine_of(precision == MSFNO_PREC_TF32), A, lda, Bm, ldb, D, ldd, M, N, K, relu_even_cols, 0, (cudaStream_t)stream);
+}
+
+int msfno_gemm_ex(const float* A, long lda, int a_kmajor, const float* Bm, long ldb, int b_kmajor, float* D, long ldd, int M,
+                  int N, int K, int relu_even_cols, const float* mask, long ldmask, int accumulate, int engine, void* stream) {
+  if (!A || !Bm || !D || M < 0 || N < 0 || K < 0 || (engine != 0 && engine != 1 && engine != 3))
+    return record_error(MSFNO_ERR_BAD_SHAPE, "gemm_ex: bad argument");
+  GemmLaunch g = single_problem(A, lda, a_kmajor, Bm, ldb, b_kmajor, D, ldd, M, N, K);
+  g.relu_even = relu_even_cols; g.mask = mask; g.ldmask = ldmask; g.accumulate = accumulate;
+  return gemm_on(engine, g, a_kmajor ? M : K, a_kmajor ? K : M, b_kmajor ? N : K, b_kmajor ? K : N, 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -85,7 +85,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // 32 x 36 shared-memory tile (conflict-free 16-byte writes and reads), every instruction writes four full 128-byte lines.
 //   wt: this warp's 32 x 36 floats, 16-byte aligned;  dst: address of (first row, first column);  rows: valid rows (<= 32)
 __device__ __forceinline__ void store_block_transposed(const float (&v)[32], float* wt, float* dst, long long ldd, int rows,
-                                                       int lane, int cols = 32) {
+                                                       int lane, int cols = 32, bool accumulate = false) {
   float4* wrow = reinterpret_cast<float4*>(wt + lane * 36);
 #pragma unroll
   for (int jj = 0; jj < 8; ++jj) wrow[jj] = make_float4(v[4 * jj], v[4 * jj + 1], v[4 * jj + 2], v[4 * jj + 3]);
@@ -94,15 +94,19 @@ __device__ __forceinline__ void store_block_transposed(const float (&v)[32], flo
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = rr + 4 * i;
-    const float4 t = *reinterpret_cast<const float4*>(wt + row * 36 + 4 * c4);
+    float4 t = *reinterpret_cast<const float4*>(wt + row * 36 + 4 * c4);
     if (row < rows) {
       float* o = dst + (long long)row * ldd + 4 * c4;
       if (4 * c4 + 3 < cols) {
+        if (accumulate) {   // D += tile (weight gradients summed over the batch)
+          const float4 old = *reinterpret_cast<const float4*>(o);
+          t.x += old.x; t.y += old.y; t.z += old.z; t.w += old.w;
+        }
         *reinterpret_cast<float4*>(o) = t;
       } else {   // ragged right edge: the last (partial) group of four columns
-        if (4 * c4 < cols) o[0] = t.x;
-        if (4 * c4 + 1 < cols) o[1] = t.y;
-        if (4 * c4 + 2 < cols) o[2] = t.z;
+        if (4 * c4 < cols) o[0] = accumulate ? o[0] + t.x : t.x;
+        if (4 * c4 + 1 < cols) o[1] = accumulate ? o[1] + t.y : t.y;
+        if (4 * c4 + 2 < cols) o[2] = accumulate ? o[2] + t.z : t.z;
       }
     }
   }

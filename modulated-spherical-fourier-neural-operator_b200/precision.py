@@ -1,8 +1,10 @@
 """Precision tiers of the hot path (north_star: <= 1e-5 rel-L2 for "fp32", <= 2e-3 for the tensor-core tier).
 
-"fp32": every contraction accumulates fp32 products of fp32 operands (CUDA-core FFMA kernels; library
-        1x1 convolutions with TF32 disabled).
-"tf32": the GEMM-shaped stages (spectral complex MLP, 1x1-conv MLPs) run on the tensor cores in TF32.
+"fp32": every contraction is fp32-grade with fp32 accumulation.  Default engine "tc3x": the GEMM-shaped stages (spectral
+        complex MLP, Legendre contractions, 1x1 convs, all adjoints) run on the tcgen05 tensor cores as 3xTF32 -- three
+        MMAs per k-step on hi / lo operand splits made in shared memory (csrc/gemm_tc.cu); engine "ffma": CUDA-core FFMA
+        kernels (set_fp32_engine).  The longitude transforms are the four-step FFT kernels.
+"tf32": the GEMM-shaped stages run as plain TF32 MMAs on TF32-rounded operands, the longitude transforms as TF32 DFT GEMMs.
 The tier is an explicit setting, never autocast-driven: the reference forces fp32 inside the transforms
 (/root/reference MSFNO/Models/sfno/layers.py:403-407,418-422,627-639)."""
 import contextlib
@@ -17,6 +19,20 @@ def set_precision(tier):
     if tier not in ("fp32", "tf32"):
         raise ValueError("precision tier must be 'fp32' or 'tf32'")
     _TIER = tier
+
+
+def set_fp32_engine(engine):
+    """Engine of the fp32 tier's GEMM-shaped stages: "tc3x" (3xTF32 on the tensor cores, default) or "ffma"."""
+    from . import _lib
+    codes = {"tc3x": _lib.FP32_ENGINE_TC3X, "ffma": _lib.FP32_ENGINE_FFMA}
+    if engine not in codes:
+        raise ValueError("fp32 engine must be 'tc3x' or 'ffma'")
+    _lib.check(_lib.lib.msfno_set_fp32_engine(codes[engine]), "set_fp32_engine")
+
+
+def get_fp32_engine():
+    from . import _lib
+    return "ffma" if _lib.lib.msfno_get_fp32_engine() == _lib.FP32_ENGINE_FFMA else "tc3x"
 
 
 _LEGENDRE_TC = True
