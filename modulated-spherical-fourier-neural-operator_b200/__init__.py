@@ -10,6 +10,7 @@ Public surface (mirrors /root/reference MSFNO/Models/sfno/{sfnonet,layers}.py an
 There is no CPU fallback: importing requires libmsfno_b200.so (see __graft_entry__.build()).
 """
 from . import _lib  # noqa: F401  (loads the shared library; raises loudly when it is missing)
+from ._lib import invalidate_caches
 from . import legendre, quadrature
 from .precision import get_fp32_engine, get_precision, set_fp32_engine, set_precision
 from .sht import InverseRealSHT, RealSHT
@@ -21,7 +22,7 @@ from .pipeline import HostPipeline
 from .graph import GraphedForward
 
 __all__ = [
-    "RealSHT", "InverseRealSHT", "quadrature", "legendre", "harmonics", "set_precision", "get_precision", "set_fp32_engine", "get_fp32_engine",
+    "RealSHT", "InverseRealSHT", "quadrature", "legendre", "harmonics", "set_precision", "get_precision", "set_fp32_engine", "get_fp32_engine", "invalidate_caches",
     "SpectralConvS2", "SpectralAttentionS2", "ComplexReLU", "MLP", "DropPath", "trunc_normal_",
     "SpectralFilterLayer", "FiLM", "FourierNeuralOperatorBlock", "FourierNeuralOperatorBlock_Filmed",
     "FourierNeuralOperatorNet", "FourierNeuralOperatorNet_Filmed", "Film_wrapper", "FeedForward", "HostPipeline", "GraphedForward",

@@ -117,3 +117,53 @@ def check(rc, what=""):
 def ptr(t):
     """Device pointer of a tensor (None -> NULL)."""
     return None if t is None else t.data_ptr()
+
+
+def on_input_device(fn):
+    """Decorator of the public entry points (module forwards, conv1x1 / mlp1x1): run with the first tensor argument's
+    device as the CURRENT device.  The C side launches on the current device (stream handles, tensor-map encoding,
+    per-device constants), and PyTorch's own operators guard the device themselves -- so a module living on cuda:1
+    must work while cuda:0 is current, exactly like the reference's modules do."""
+    import functools
+
+    import torch
+
+    @functools.wraps(fn)
+    def wrapped(*args, **kwargs):
+        dev = None
+        for a in args:
+            if torch.is_tensor(a):
+                dev = a.device if a.is_cuda else None
+                break
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapped
+
+
+# ---- derived-weight caches (padded / TF32-packed copies of parameters) ------------------------------------------------
+# They are keyed on the parameter object and its autograd version counter, which in-place writes through `param.data`
+# (p.data.copy_(...), EMA utilities) do NOT bump.  `invalidate_caches()` bumps a global epoch that is part of every
+# key; load_state_dict / .to() / .float() on the nets call it, and callers that write through `.data` must too.
+_CACHE_EPOCH = [0]
+_capture_refs = None   # list while a GraphedForward is warming up / capturing: every cached tensor a launch used
+
+
+def cache_epoch():
+    return _CACHE_EPOCH[0]
+
+
+def invalidate_caches():
+    """Forget every derived copy of a parameter (padded / TF32-rounded / packed weights, re-laid Legendre tables).
+    Call after writing parameters through `.data` (the version counter does not see such writes).  A CUDA graph
+    captured earlier (GraphedForward) keeps replaying the OLD derived copies: re-capture it."""
+    _CACHE_EPOCH[0] += 1
+
+
+def note_cached(t):
+    """Called by the caches with every tensor they hand to a launch: a graph being captured keeps it alive."""
+    if _capture_refs is not None and t is not None:
+        _capture_refs.append(t)
+    return t

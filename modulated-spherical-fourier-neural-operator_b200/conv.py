@@ -30,10 +30,10 @@ def padded_weight(weight, cols=None):
         wid = id(weight)
         ent = (weakref.ref(weight, lambda _r, k=wid: _pad_cache.pop(k, None)), {})
         _pad_cache[wid] = ent
-    key = (weight._version, tf32, cols)
+    key = (weight._version, _lib.cache_epoch(), tf32, cols)
     hit = ent[1].get(key)
     if hit is not None:
-        return hit
+        return _lib.note_cached(hit)
     w2 = weight.detach().reshape(weight.shape[0], -1).float()
     if cols is not None:
         w2 = w2[:, cols[0]:cols[1]]
@@ -44,12 +44,13 @@ def padded_weight(weight, cols=None):
     w2 = w2.contiguous()
     if tf32:
         w2 = round_tf32(w2)
-    for k in [k for k in ent[1] if k[0] != weight._version]:
+    for k in [k for k in ent[1] if k[:2] != key[:2]]:
         del ent[1][k]   # drop entries of older versions of this tensor
     ent[1][key] = w2
-    return w2
+    return _lib.note_cached(w2)
 
 
+@_lib.on_input_device
 def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, cin2=0, per_sample_w=False,
             per_sample_bias=False, final=False, w_rounded=False):
     """y = act(conv1x1(x, w) [+ conv1x1(x2, w2)] + bias) + add   for contiguous NCHW fp32 CUDA tensors.
@@ -82,6 +83,7 @@ def mlp1x1_supported(chid, cout, HW):
     return _precision.get_precision() == "tf32" and ok_hid and cout <= 256 and HW % 4 == 0
 
 
+@_lib.on_input_device
 def mlp1x1(x, w1, cin, b1, w2, b2=None, add=None, x2=None, w1b=None, cin2=0, per_sample_w1=False, per_sample_b1=False,
            final=False, w1_rounded=False, stats=None, out=None):
     """y = conv1x1(gelu(conv1x1(x, w1) [+ conv1x1(x2, w1b)] + b1), w2) + b2 + add in ONE kernel; the hidden activation

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/msfno_b200.h"
 
@@ -12,6 +13,16 @@ namespace msfno {
     cudaError_t _e = (expr);                                 \
     if (_e != cudaSuccess) return msfno::record_cuda_error(_e, __FILE__, __LINE__); \
   } while (0)
+
+// Experiment switches read from the environment exist only in builds with -DMSFNO_DEBUG_SWITCHES (csrc/build.sh:
+// MSFNO_EXTRA_FLAGS); the product build compiles every one of them to its default.
+#ifdef MSFNO_DEBUG_SWITCHES
+inline bool dbg_env(const char* name) { return getenv(name) != nullptr; }
+inline int dbg_env_int(const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; }
+#else
+constexpr bool dbg_env(const char*) { return false; }
+constexpr int dbg_env_int(const char*, int dflt) { return dflt; }
+#endif
 
 int record_cuda_error(cudaError_t e, const char* file, int line);
 int record_error(int code, const char* msg);

@@ -680,7 +680,7 @@ static float host_round_tf32(float x) {
 }
 
 bool dft_tc_supported(const msfno_plan* p) {
-  static const bool off = getenv("MSFNO_DFT_FFT") != nullptr;
+  static const bool off = dbg_env("MSFNO_DFT_FFT");
   return !off && p->nlon % 4 == 0 && 2 * p->mlim <= DF_BN && (2 * p->mlim) % 4 == 0 && p->mlim <= p->nlon / 2 && get_encode() != nullptr;
 }
 
@@ -726,7 +726,7 @@ static int launch_dft(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUte
   constexpr int smem = NS * (MT * DF_A_BYTES + DF_B_BYTES) + 4096 + 1024 + 512;
   auto kern = dft_tc_kernel<INV, MT, NS>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  static const bool trace_on = getenv("MSFNO_DFT_TRACE") != nullptr;
+  static const bool trace_on = dbg_env("MSFNO_DFT_TRACE");
   static long long* d_trace = nullptr;
   DftParams prm2 = prm;
   if (trace_on) {
@@ -764,7 +764,7 @@ int launch_dft_fwd(msfno_plan* p, const float* x, float* Xt, const float* in_sca
   prm.nkb = (p->nlon + TC_BK - 1) / TC_BK;
   prm.flags = 1;
   prm.dc = (float)(2.0 * M_PI);
-  static const int fwd_mt = getenv("MSFNO_DFT_FWD_MT") ? atoi(getenv("MSFNO_DFT_FWD_MT")) : 2;
+  static const int fwd_mt = dbg_env_int("MSFNO_DFT_FWD_MT", 2);
   if (p->kpad > 128 && fwd_mt == 2) return launch_dft<false, 2, 3>(tmA, tmB, tmA, tmB, tmA, prm, dim3(1, (p->kpad + 255) / 256, B * C), st);
   if (p->kpad > 128) return launch_dft<false, 1, 2>(tmA, tmB, tmA, tmB, tmA, prm, dim3(1, (p->kpad + 127) / 128, B * C), st);
   return launch_dft<false, 1, 2>(tmA, tmB, tmA, tmB, tmA, prm, dim3(1, 1, B * C), st);
@@ -794,7 +794,7 @@ static int dft_eo_build(msfno_plan* p) {
 }
 
 static bool dft_eo_supported(const msfno_plan* p, const float* y) {
-  static const bool off = getenv("MSFNO_DFT_NO_EO") != nullptr;
+  static const bool off = dbg_env("MSFNO_DFT_NO_EO");
   return !off && p->nlat > 128 && p->nlon % 8 == 0 && p->mlim + 1 <= 128 && (reinterpret_cast<uintptr_t>(y) & 15) == 0;
 }
 
@@ -842,7 +842,7 @@ static int launch_idft_eo(msfno_plan* p, const float* Yt, float* y, int act_flag
   auto kern = (act_flags & 3) == 0 ? idft_eo_kernel<0> : (act_flags & 3) == 1 ? idft_eo_kernel<1> : (act_flags & 3) == 2 ? idft_eo_kernel<2> : idft_eo_kernel<3>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, EO_SMEM));
   const int grid = prm.nitems < n_sm ? prm.nitems : n_sm;
-  static const bool trace_on = getenv("MSFNO_DFT_TRACE") != nullptr;
+  static const bool trace_on = dbg_env("MSFNO_DFT_TRACE");
   static long long* d_trace = nullptr;
   if (trace_on) {
     if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 512 * 8 * sizeof(long long)));
@@ -886,11 +886,11 @@ int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, 
   prm.nkb = (2 * p->mlim + TC_BK - 1) / TC_BK;
   prm.flags = act_flags;
   const int tilesN = (p->nlon + DF_BN - 1) / DF_BN;
-  static const int inv_mt = getenv("MSFNO_DFT_INV_MT") ? atoi(getenv("MSFNO_DFT_INV_MT")) : 1;   // 1: 128-row tiles, two CTAs per SM overlap each other's load / MMA / store phases (faster than one 256-row tile per SM)
+  static const int inv_mt = dbg_env_int("MSFNO_DFT_INV_MT", 1);   // 1: 128-row tiles, two CTAs per SM overlap each other's load / MMA / store phases (faster than one 256-row tile per SM)
   // skip operand on the tensor cores: TMA-able tensor (16-byte aligned rows) and the shared identity block
   CUtensorMap tmS = tmB, tmI = tmB;
   const float* d_ident = identity32_device();
-  static const bool skip_lsu = getenv("MSFNO_DFT_SKIP_LSU") != nullptr;
+  static const bool skip_lsu = dbg_env("MSFNO_DFT_SKIP_LSU");
   if (skip && !skip_lsu && d_ident != nullptr && (reinterpret_cast<uintptr_t>(skip) & 15) == 0) {
     rc = make_map(&tmS, skip, (long long)B * C * p->nlat, p->nlon, p->nlon, 128);
     if (rc) return rc;
@@ -900,7 +900,7 @@ int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, 
   }
   // output through TMA tensor stores: [B C][nlat][nlon] map, 32 x 32 boxes in the 128-byte-swizzle layout
   CUtensorMap tmO = tmB;
-  static const bool out_lsu = getenv("MSFNO_DFT_OUT_LSU") != nullptr;
+  static const bool out_lsu = dbg_env("MSFNO_DFT_OUT_LSU");
   if (!out_lsu && (skip == nullptr || prm.skip_tma) && (reinterpret_cast<uintptr_t>(y) & 15) == 0) {
     EncodeTiledFn enc = get_encode();
     const cuuint64_t odims[3] = {(cuuint64_t)p->nlon, (cuuint64_t)p->nlat, (cuuint64_t)B * C};

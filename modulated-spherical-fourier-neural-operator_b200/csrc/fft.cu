@@ -236,7 +236,7 @@ irfft_trunc_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf
 // ---------------------------------------------------------------------------------------------
 // MSFNO_FFT_GENERIC=1 forces the radix-stage kernels (A/B comparison and debugging)
 static bool force_generic_fft() {
-  static const bool v = [] { const char* e = getenv("MSFNO_FFT_GENERIC"); return e && e[0] == '1'; }();
+  static const bool v = dbg_env("MSFNO_FFT_GENERIC");
   return v;
 }
 

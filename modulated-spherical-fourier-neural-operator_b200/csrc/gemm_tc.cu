@@ -62,6 +62,7 @@ struct TcParams {
   long long lda2, ldb2, sa2, sb2;
   int K2;
   int b_group_rows;   // > 0: B (MN-major) is a 3-D tensor [tables][b_group_rows][ldb]
+  long long* trace;   // builds with -DMSFNO_TRACE only: per-role clock64 totals of CTA (0, 0)
 };
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
@@ -398,6 +399,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int m0 = tm * TC_BM, n0 = tn * TC_BN;
   if (m0 >= grp.M || n0 >= grp.N) return;  // uniform for the CTA, before any barrier / allocation
   pdl_trigger();
+#ifdef MSFNO_TRACE
+  const long long t_cta0 = clock64();
+#endif
 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* tiles = smem_raw + (base - smem_u32(smem_raw));
@@ -417,7 +421,7 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&conv[s], TC_NCONV);
+      mbar_init(&conv[s], 12);   // one arrival per A-converter warp (4) and per accumulator warp (8, they make lo(B))
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&acc_full[b], 1);
@@ -447,11 +451,29 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // ---------------- MMA issuer ----------------
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+#ifdef MSFNO_TRACE
+      long long tr_full = 0, tr_conv = 0, tr_acc = 0, tr_first = 0, tr_last = 0, tr_issue = 0;
+#endif
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % NST, b = kb & 1;
+#ifdef MSFNO_TRACE
+        const long long w0 = clock64();
+#endif
         mbar_wait_bounded(&full[s], (uint32_t)((kb / NST) & 1));
+#ifdef MSFNO_TRACE
+        const long long w1 = clock64();
+#endif
         mbar_wait_bounded(&conv[s], (uint32_t)((kb / NST) & 1));
+#ifdef MSFNO_TRACE
+        const long long w2 = clock64();
+#endif
         mbar_wait_bounded(&acc_empty[b], (uint32_t)(((kb >> 1) & 1) ^ 1));
+#ifdef MSFNO_TRACE
+        const long long w3 = clock64();
+        tr_full += w1 - w0; tr_conv += w2 - w1; tr_acc += w3 - w2;
+        if (kb == 0) tr_first = w3;
+        tr_last = w3;
+#endif
         tc_fence_after();
         const uint32_t sa = base + s * STAGE, sb = sa + TC_A_BYTES;
         const uint32_t d = tmem_base + (uint32_t)(b * TC_BN);
@@ -474,10 +496,18 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         tc_commit(&empty[s]);       // the stage (and its TMEM copy of A) may be refilled
         tc_commit(&acc_full[b]);    // the k-block product is complete
+#ifdef MSFNO_TRACE
+        tr_issue += clock64() - w3;
+#endif
       }
+#ifdef MSFNO_TRACE
+      if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) {
+        p.trace[0] = tr_full; p.trace[1] = tr_conv; p.trace[2] = tr_acc; p.trace[3] = tr_first; p.trace[4] = tr_last; p.trace[8] = tr_issue;
+      }
+#endif
     } else if (warp >= 4 && warp < 8) {
-      // ---------------- converters ----------------
-      const int t = threadIdx.x - 128;            // = tile row of A (TMEM lane): warp 4 + q owns lane quarter q
+      // ---------------- A converters (thread = tile row of A = TMEM lane: warp 4 + q owns lane quarter q) ----------------
+      const int t = threadIdx.x - 128;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % NST;
         mbar_wait_bounded(&full[s], (uint32_t)((kb / NST) & 1));
@@ -498,19 +528,35 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           MSFNO_TC_ST32(ta, hi);
           MSFNO_TC_ST32(ta + 32u, lo);
           asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+          tc_fence_before();
         } else {
           convert_stage_lo(st, st + LO_A, TC_A_BYTES, t, TC_NCONV);
+          fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) reads
         }
-        convert_stage_lo(st + TC_A_BYTES, st + LO_B, TC_B_BYTES, t, TC_NCONV);
-        fence_proxy_async();   // generic-proxy writes -> visible to the tensor core's (async proxy) reads
-        tc_fence_before();
-        mbar_arrive(&conv[s]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
       }
     } else if (warp >= 8) {
       // ---------------- accumulators: acc += TMEM buffer (round-to-nearest adds on the CUDA cores) ----------------
+      // They also make lo(B) in shared memory, two k-blocks ahead of the product they drain: the A converters alone
+      // (one warp per scheduler, a serial chain of shared loads, ALU, tensor-memory stores and fences per k-block) were
+      // the slowest stage of the pipeline.
       const int q = warp & 3, chalf = (warp - 8) >> 2;
+      const int t = threadIdx.x - 256;
       const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+      auto convert_b = [&](int kb) {
+        const int s = kb % NST;
+        mbar_wait_bounded(&full[s], (uint32_t)((kb / NST) & 1));
+        uint8_t* st = tiles + s * STAGE;
+        convert_stage_lo(st + TC_A_BYTES, st + LO_B, TC_B_BYTES, t, 256);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
+      };
+      convert_b(0);
+      if (nkb > 1) convert_b(1);
       for (int kb = 0; kb < nkb; ++kb) {
+        if (kb + 2 < nkb) convert_b(kb + 2);
         const int b = kb & 1;
         mbar_wait_bounded(&acc_full[b], (uint32_t)((kb >> 1) & 1));
         tc_fence_after();
@@ -530,6 +576,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
   }
 
+#ifdef MSFNO_TRACE
+  if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 256) p.trace[5] = clock64();
+#endif
   if (warp >= 8) {
     // ---------------- epilogue from the register accumulators ----------------
     // (all MMAs have completed and every converter has finished: the last acc_full was observed above)
@@ -545,6 +594,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+#ifdef MSFNO_TRACE
+  if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 256) { p.trace[6] = clock64(); p.trace[7] = t_cta0; }
+#endif
   if (warp == 2) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS));
@@ -782,10 +834,26 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     p.tilesM = (g.maxM + TC_BM - 1) / TC_BM;
     p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;
     dim3 grid(p.tilesM * p.tilesN, g.ngroups);
+#ifdef MSFNO_TRACE
+    static long long* d_trace = nullptr;
+    if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 16 * sizeof(long long)));
+    MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 16 * sizeof(long long), st));
+    p.trace = d_trace;
+#endif
     if (amn && bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<true, true>, grid, dim3(TC3_THREADS), Tc3Cfg<true>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
     else if (amn) MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<true, false>, grid, dim3(TC3_THREADS), Tc3Cfg<true>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
     else if (bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<false, true>, grid, dim3(TC3_THREADS), Tc3Cfg<false>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
     else MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<false, false>, grid, dim3(TC3_THREADS), Tc3Cfg<false>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
+#ifdef MSFNO_TRACE
+    {
+      long long h[16];
+      MSFNO_CUDA_OK(cudaStreamSynchronize(st));
+      MSFNO_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+      fprintf(stderr, "gemm_tc3 trace CTA(0,0) maxM=%d maxN=%d: issuer waits full %lld conv %lld acc_empty %lld | first MMA at %lld, last issue at %lld, "
+                      "mainloop done %lld, cta done %lld (clk since CTA start); issue blocks %lld\n", g.maxM, g.maxN, h[0], h[1], h[2], h[3] - h[7], h[4] - h[7],
+              h[5] - h[7], h[6] - h[7], h[8]);
+    }
+#endif
     count_launch();
     MSFNO_CUDA_OK(cudaGetLastError());
     return MSFNO_OK;

@@ -448,7 +448,7 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
   // `add` on the tensor cores: needs a TMA-able operand (16-byte aligned, plane stride HW) and the identity block
   CUtensorMap tmAdd = tmX, tmId = tmW2;
   const float* d_ident = identity32_device();
-  static const bool add_tma_off = getenv("MSFNO_MLP_ADD_LSU") != nullptr;
+  static const bool add_tma_off = dbg_env("MSFNO_MLP_ADD_LSU");
   const bool add_tma = add && !add_tma_off && al16(add) && add_bstride % HW == 0 && d_ident != nullptr;
   if (add_tma) {
     rc = make_map(&tmAdd, add, (add_bstride ? (long long)(B - 1) * (add_bstride / HW) : 0) + Cout, HW, HW, TC_BK, true);

@@ -20,7 +20,7 @@ namespace msfno {
 static thread_local std::string g_last_error;
 static std::atomic<unsigned long long> g_launches{0};
 bool pdl_enabled() {
-  static const bool on = getenv("MSFNO_NO_PDL") == nullptr;
+  static const bool on = !dbg_env("MSFNO_NO_PDL");
   return on;
 }
 

@@ -13,18 +13,41 @@ class GraphedForward:
 
     def __init__(self, net, example_x, *example_args, warmup=2):
         self.net = net
+        self.warmup = warmup
         self.static_x = example_x.clone()
         self.static_args = tuple(a.clone() if torch.is_tensor(a) else a for a in example_args)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.no_grad(), torch.cuda.stream(side):
-            for _ in range(warmup):
+        self._capture()
+
+    def _capture(self):
+        """The graph bakes in the addresses of the derived weight copies the launches read (padded / TF32-packed
+        weights, packed spectral-MLP weights) and skips their re-packing: `self._refs` keeps every one of them alive for
+        the life of the graph, so a later cache eviction can never leave a replay reading freed memory.  The graph does
+        NOT see later parameter changes -- call recapture() after changing weights."""
+        from . import _lib
+        net = self.net
+        _lib._capture_refs = refs = []
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.no_grad(), torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self.static_y = net(self.static_x, *self.static_args)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(self.graph):
                 self.static_y = net(self.static_x, *self.static_args)
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
-            self.static_y = net(self.static_x, *self.static_args)
+        finally:
+            _lib._capture_refs = None
+        self._refs = refs
+        if hasattr(self, "inplace_graph"):
+            del self.inplace_graph
+
+    def recapture(self):
+        """Forget every derived weight copy and capture again (after the net's parameters changed)."""
+        from . import _lib
+        _lib.invalidate_caches()
+        self._capture()
 
     def __call__(self, x=None, *args):
         """Copies x (and tensor args) into the static buffers, replays, returns the static output tensor
@@ -45,7 +68,9 @@ class GraphedForward:
         if (not hasattr(self.net, "_decode_fused") or self.static_args
                 or getattr(self.net, "in_chans", None) != getattr(self.net, "out_chans", -1)):
             return
+        from . import _lib
         self.net._decode_out = self.static_x
+        _lib._capture_refs = self._refs
         try:
             keep = self.static_x.clone()
             side = torch.cuda.Stream()
@@ -62,6 +87,7 @@ class GraphedForward:
                     self.inplace_graph = g
             self.static_x.copy_(keep)
         finally:
+            _lib._capture_refs = None
             del self.net._decode_out
 
     def rollout(self, x0, steps):

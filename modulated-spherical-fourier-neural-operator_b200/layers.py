@@ -192,6 +192,7 @@ class SpectralConvS2(nn.Module):
             out = nn.functional.softshrink(out, lambd=self.sparsity_threshold)
         return out
 
+    @_lib.on_input_device
     def forward(self, x, in_scale=None, in_shift=None, **epilogue):
         _require_cuda(x, "SpectralConvS2")
         dtype = x.dtype
@@ -255,7 +256,7 @@ class SpectralAttentionS2(nn.Module):
         B, C = a_pm.shape[0], a_pm.shape[2] // 2
         hid, nl = wout.shape[0], len(ws)
         key = (B, str(a_pm.device), prec)
-        wkey = tuple((id(w), w.data_ptr(), w._version) for w in (self.wout, *self.w))
+        wkey = (_lib.cache_epoch(),) + tuple((id(w), w.data_ptr(), w._version) for w in (self.wout, *self.w))
         cache = self.__dict__.setdefault("_ws_cache", {})
         ent = cache.get(key)
         if ent is None:
@@ -267,8 +268,10 @@ class SpectralAttentionS2(nn.Module):
         check(lib.msfno_specattn_fwd(plan.h, ptr(a_pm), warr, nl, ptr(wout), ptr(out), ptr(ent[0]), B, C, hid, flags,
                                      _stream()), "specattn_fwd")
         ent[1] = wkey
+        _lib.note_cached(ent[0])
         return out
 
+    @_lib.on_input_device
     def forward_mlp(self, xr):
         """Reference-compatible entry: xr real view [B,C,L,M,2] -> [B,C,L,M,2]."""
         B, C = xr.shape[0], xr.shape[1]
@@ -276,6 +279,7 @@ class SpectralAttentionS2(nn.Module):
         c = self.spectral(a)
         return relayout(c, self._sht, _lib.LAYOUT_CM, _lib.LAYOUT_STD, B, C)
 
+    @_lib.on_input_device
     def forward(self, x, in_scale=None, in_shift=None, **epilogue):
         _require_cuda(x, "SpectralAttentionS2")
         dtype = x.dtype

@@ -15,10 +15,10 @@ inner skip -> [GELU] -> InstanceNorm -> FiLM) runs on the sm_100a kernels behind
     Appendix A.4); normalisation / residual glue stays in PyTorch so autograd can see it.
 
 The 1x1-conv MLPs (encoder, decoder, block MLP, inner skip) are the callers either side of the path
- and still use the PyTorch library convolution.
+(SURVEY.md 8(f) N2): without autograd they run on the fused tensor-core kernels (msfno_mlp1x1_fwd, msfno_conv1x1_fwd);
+layers that need weight gradients use nn.Conv2d.
 """
 import math
-import os
 from functools import partial
 
 import torch
@@ -63,23 +63,13 @@ class _FiLMFn(torch.autograd.Function):
 class FiLM(nn.Module):
     """Feature-wise linear modulation (sfnonet.py:689-697): (1 + gamma*scale) * x + beta*scale."""
 
+    @_lib.on_input_device
     def forward(self, x, gammas, betas, scale=1):
         if not x.is_cuda:
             raise RuntimeError("FiLM: msfno_b200 runs on CUDA only (no CPU fallback)")
         if torch.is_tensor(scale):
             scale = float(scale)
         return _FiLMFn.apply(x.contiguous().float(), gammas.contiguous().float(), betas.contiguous().float(), scale).to(x.dtype)
-
-
-_SIDE_SKIP = os.environ.get("MSFNO_SIDE_SKIP", "0") == "1"
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
-    return _SIDE_STREAMS[key]
 
 
 def plane_stats(x):
@@ -232,6 +222,7 @@ class SpectralFilterLayer(nn.Module):
         else:
             raise NotImplementedError
 
+    @_lib.on_input_device
     def forward(self, x, **fused):
         return self.filter(x, **fused)
 
@@ -281,7 +272,9 @@ class FourierNeuralOperatorBlock(nn.Module):
 
     # -- helpers ------------------------------------------------------------------------------
     def _can_fuse(self, x):
+        # (stochastic depth is applied by _tail; the fused paths that skip _tail are only valid when it is the identity)
         return (x.is_cuda and not torch.is_grad_enabled() and not self.concat_skip
+                and (not self.training or isinstance(self.drop_path, nn.Identity))
                 and _is_plain_instance_norm(self.norm0) and _is_plain_instance_norm(self.norm1)
                 and not (hasattr(self, "act_layer") and not isinstance(self.act_layer, nn.GELU))
                 and not (hasattr(self, "act_layer") and getattr(self.act_layer, "approximate", "none") != "none"))
@@ -308,24 +301,13 @@ class FourierNeuralOperatorBlock(nn.Module):
         B, C = x.shape[0], x.shape[1]
         A0, S0 = norm_film_coeffs(in_stats if in_stats is not None else plane_stats(x), self.norm0, B, C, x[0, 0].numel())
         skip = None
-        join = None
         if hasattr(self, "inner_skip"):
             if isinstance(self.inner_skip, nn.Conv2d):
-                if _SIDE_SKIP:
-                    # the skip conv depends only on x: it runs on a side stream beside the SHT -> spectral MLP chain (its
-                    # CTAs fill the SMs the second wave of the spectral GEMMs leaves idle) and is joined before the inverse
-                    cur, side = torch.cuda.current_stream(), _side_stream(x.device)
-                    side.wait_stream(cur)
-                    with torch.cuda.stream(side):
-                        skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
-                    join = lambda: cur.wait_stream(side)
-                else:
-                    skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
+                skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
             else:
                 skip = self.inner_skip(residual)
         stats1 = torch.empty((B * C, 2), dtype=torch.float64, device=x.device)
-        y = self.filter_layer(x, in_scale=A0, in_shift=S0, skip_add=skip, act_gelu=hasattr(self, "act_layer"),
-                              stats=stats1, **({"pre": join} if join is not None else {}))
+        y = self.filter_layer(x, in_scale=A0, in_shift=S0, skip_add=skip, act_gelu=hasattr(self, "act_layer"), stats=stats1)
         mlp = getattr(self, "mlp", None)
         fused_mlp = (not prefilm and mlp is not None and len(mlp.fwd) == 3 and isinstance(mlp.fwd[0], nn.Conv2d)
                      and isinstance(mlp.fwd[1], nn.GELU) and getattr(mlp.fwd[1], "approximate", "none") == "none"
@@ -382,6 +364,7 @@ class FourierNeuralOperatorBlock(nn.Module):
             x = self.mlp(x)
         return self._tail(x, residual)
 
+    @_lib.on_input_device
     def forward(self, x, *overflow):
         if self._can_fuse(x):
             return self._fused(x)
@@ -408,6 +391,7 @@ class FourierNeuralOperatorBlock_Filmed(FourierNeuralOperatorBlock):
             x = self.act_layer(x)
         return self.norm1(x)
 
+    @_lib.on_input_device
     def forward(self, x, gamma, beta, scale=1):
         if torch.is_tensor(scale):
             scale = float(scale)
@@ -554,6 +538,16 @@ class FourierNeuralOperatorNet(nn.Module):
             nn.init.constant_(m.bias, 0)
             nn.init.constant_(m.weight, 1.0)
 
+    # derived copies of the parameters (padded / TF32-packed weights) are cached per parameter version; wholesale
+    # parameter replacement goes through these two and forgets them (writes through `.data` need invalidate_caches())
+    def _apply(self, fn, *args, **kwargs):
+        _lib.invalidate_caches()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        _lib.invalidate_caches()
+        return super().load_state_dict(*args, **kwargs)
+
     @torch.jit.ignore
     def no_weight_decay(self):
         return {"pos_embed", "cls_token"}
@@ -620,6 +614,7 @@ class FourierNeuralOperatorNet(nn.Module):
                 x, stats = blk._fused(x, g, b, sc, in_stats=stats, want_stats=True)
         return self._decode_fused(y, A, S, residual)
 
+    @_lib.on_input_device
     def forward(self, x):
         with _precision.library_scope():
             if self._can_fuse_net(x):
@@ -702,6 +697,7 @@ class FourierNeuralOperatorNet_Filmed(FourierNeuralOperatorNet):
             use_complex_kernels=use_complex_kernels)
         self.film_gen = Film_wrapper(device, cfg)
 
+    @_lib.on_input_device
     def forward(self, x, sst, scale=1):
         with _precision.library_scope():
             return self._forward(x, sst, scale)

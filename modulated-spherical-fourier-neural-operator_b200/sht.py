@@ -55,7 +55,7 @@ class _Plan:
     def set_table(self, table, analysis):
         # identity + version of the tensor object; the plan keeps the tensor alive (self.table_ref) so its address
         # cannot be recycled for a different table while the key is still in use
-        key = (id(table), table._version)
+        key = (id(table), table._version, _lib.cache_epoch())
         if key != self.table_key or self.table_ref is not table:
             t = table.detach()
             if t.dtype != torch.float32 or not t.is_contiguous():
@@ -212,6 +212,7 @@ class RealSHT(_SHTBase):
     _analysis = True
     _table_name = "weights"
 
+    @_lib.on_input_device
     def forward_packed(self, x, in_scale=None, in_shift=None):
         """x [B,C,nlat,nlon] fp32 CUDA -> coefficients in the PM layout [B,P,2C].  Optional fused
         per-(b,c) affine x*in_scale + in_shift (shape [B,C] or [B*C])."""
@@ -223,6 +224,7 @@ class RealSHT(_SHTBase):
             in_shift = in_shift.contiguous().float()
         return _SHTForward.apply(x, self, in_scale, in_shift)
 
+    @_lib.on_input_device
     def forward(self, x):
         _require_cuda(x, "RealSHT")
         assert x.shape[-2] == self.nlat
@@ -242,15 +244,13 @@ class InverseRealSHT(_SHTBase):
     _analysis = False
     _table_name = "pct"
 
-    def inverse_packed(self, coef_cm, skip_add=None, act_gelu=False, stats=None, pre=None):
+    @_lib.on_input_device
+    def inverse_packed(self, coef_cm, skip_add=None, act_gelu=False, stats=None):
         """coefficients in the CM layout [B,2C,P] -> y [B,C,nlat,nlon].  skip_add / act_gelu / stats
-        select the fused epilogue (inference only: not differentiable).  pre: optional callable run right before the
-        launches (the block joins the side stream that produced skip_add there)."""
+        select the fused epilogue (inference only: not differentiable)."""
         _require_cuda(coef_cm, "InverseRealSHT")
         coef_cm = coef_cm.contiguous()
         if skip_add is None and not act_gelu and stats is None:
-            if pre is not None:
-                pre()
             return _ISHTForward.apply(coef_cm, self)
         if torch.is_grad_enabled() and (coef_cm.requires_grad or (skip_add is not None and skip_add.requires_grad)):
             raise RuntimeError("InverseRealSHT fused epilogue is inference-only; call under torch.no_grad()")
@@ -262,12 +262,11 @@ class InverseRealSHT(_SHTBase):
             skip_add = skip_add.contiguous().float()
             assert skip_add.shape == y.shape
         flags = (1 if act_gelu else 0) | (2 if _precision.get_precision() == "tf32" else 0)   # bit 1: TF32-round y
-        if pre is not None:
-            pre()
         check(lib.msfno_isht_fwd(plan.h, ptr(coef_cm), ptr(y), ptr(ws), B, C, ptr(skip_add), flags,
                                  ptr(stats), _stream()), "isht_fwd")
         return y
 
+    @_lib.on_input_device
     def forward(self, x):
         _require_cuda(x, "InverseRealSHT")
         assert x.shape[-2] == self.lmax

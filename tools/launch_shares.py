@@ -1,35 +1,76 @@
-"""Summarise an ncu launch list (gpu__time_duration.sum CSV) of bench.py: per-kernel share of ONE forward."""
+"""Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv`) of bench.py: per-kernel share of ONE forward step.
+
+The step boundary is found from the launch list itself: the (kernel name, grid) sequence of a forward repeats, so the
+smallest period L with rows[-L:] == rows[-2L:-L] is one step -- whatever the precision tier or workload launches.
+usage: python tools/launch_shares.py profiles/<launch list>.csv [--json]"""
 import collections
 import csv
+import json
 import re
 import sys
 
 
-def main(path):
+def load(path):
     with open(path) as f:
         lines = [l for l in f if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
     names = [r["Kernel Name"] for r in rows]
-    dur = [float(r["Metric Value"].replace(",", "")) / 1e6 for r in rows]
+    dur = [float(r["Metric Value"].replace(",", "")) / 1e6 for r in rows]   # ns -> ms
     grid = [r["Grid Size"] for r in rows]
-    def is_full_fwd_fft(n, g):
-        n = n.replace("msfno::", " ")
-        return (" rfft_trunc" in n or " rfft2d_kernel" in n) and g.startswith("(23,")
-    starts = [i for i, (n, g) in enumerate(zip(names, grid)) if is_full_fwd_fft(n, g)]
-    lead = starts[0]  # kernels of one forward that precede the first full-grid FFT (encoder, stats)
-    a, b = starts[1] - lead, starts[2] - lead
+    return names, grid, dur
+
+
+def short(name):
+    k = re.sub(r"\(.*", "", name).replace("void ", "").replace("msfno::", "")
+    return re.sub(r"at::native::|<unnamed>::", "", k)[:72]
+
+
+def period(keys, lo=8):
+    n = len(keys)
+    for L in range(lo, n // 2 + 1):
+        if keys[n - L:] == keys[n - 2 * L:n - L]:
+            return L
+    return None
+
+
+def shares(path):
+    names, grid, dur = load(path)
+    keys = list(zip(names, grid))
+    L = period(keys)
+    if L is None:
+        raise SystemExit("no repeating step found in %s (%d launches): profile at least two steps" % (path, len(keys)))
+    a, b = len(keys) - L, len(keys)
     agg = collections.defaultdict(lambda: [0, 0.0])
     for i in range(a, b):
-        k = re.sub(r"\(.*", "", names[i]).replace("void ", "").replace("msfno::", "")[:64]
-        if "gemm_" in names[i] or "rfft" in names[i] or "fft2d" in names[i]:
-            k += " grid" + grid[i]
+        k = short(names[i])
+        if "gemm_" in k or "fft" in k or "dft" in k:
+            k += " grid" + grid[i].replace(" ", "")
         agg[k][0] += 1
         agg[k][1] += dur[i]
     tot = sum(v[1] for v in agg.values())
-    print("launches in one forward: %d, serialized cold total %.3f ms" % (b - a, tot))
-    for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:32]:
-        print("%7.3f ms %5.1f%% x%3d  %s" % (v[1], 100 * v[1] / tot, v[0], k))
+    by_kernel = collections.defaultdict(lambda: [0, 0.0])
+    for i in range(a, b):
+        k = re.sub(r"<.*", "", short(names[i]))
+        by_kernel[k][0] += 1
+        by_kernel[k][1] += dur[i]
+    return {"launches_per_step": L, "serialized_cold_ms": tot,
+            "by_kernel": {k: {"launches": v[0], "ms": v[1], "share": v[1] / tot} for k, v in sorted(by_kernel.items(), key=lambda kv: -kv[1][1])},
+            "by_shape": {k: {"launches": v[0], "ms": v[1], "share": v[1] / tot} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}}
+
+
+def main():
+    path = sys.argv[1]
+    res = shares(path)
+    if "--json" in sys.argv:
+        print(json.dumps(res, indent=1))
+        return
+    print("launches in one forward: %d, serialized cold total %.3f ms" % (res["launches_per_step"], res["serialized_cold_ms"]))
+    for k, v in res["by_kernel"].items():
+        print("%7.3f ms %5.1f%% x%3d  %s" % (v["ms"], 100 * v["share"], v["launches"], k))
+    print("--- by kernel and grid")
+    for k, v in list(res["by_shape"].items())[:32]:
+        print("%7.3f ms %5.1f%% x%3d  %s" % (v["ms"], 100 * v["share"], v["launches"], k))
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main()
