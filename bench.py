@@ -11,9 +11,9 @@ through the public nn.Module API with HOST (pinned) input and output buffers, co
 region.  N > 1: one process per GPU (torchrun), each rank forecasts its own member -- the path shards over
 independent members with no data-path collective ("scaling": "weak").
 
-`--impl reference` times the reference's CPU implementation of the same path (the oracle port of the
-reference modules + restated torch_harmonics; the reference itself is Python that cannot travel to the GPU
-box) on the host cores.
+`--impl reference` times the reference's own CPU implementation of the same path on the host cores: the UNMODIFIED
+reference modules (staged under the git-ignored oracle/_ref/ by oracle/build_ref.sh so that they travel to the GPU
+box) over the restated torch_harmonics dependency (oracle/th_shim.py).
 """
 import argparse
 import json
@@ -92,18 +92,44 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------- reference arm
 def cpu_reference_step_factory(workload):
-    """Builds the oracle (CPU restatement of the reference path) for the workload; returns (step_fn, info)."""
+    """The reference's own CPU implementation of the path for the workload; returns (full, partial, info).
+
+    kind "reference": the UNMODIFIED reference modules (MSFNO/Models/sfno/{sfnonet,layers,contractions,activations}.py,
+    staged byte for byte under oracle/_ref/ by oracle/build_ref.sh, or the mounted /root/reference) driven through their
+    public API -- FourierNeuralOperatorNet(device, cfg, filter_type=...).forward(x) -- with the un-vendored
+    torch_harmonics dependency restated by oracle/th_shim.py.  kind "port": the functional oracle port
+    (oracle/sfno_oracle.py), used only when no copy of the reference is present."""
     import torch
-    from oracle import sfno_oracle
+    from oracle import ref_import, sfno_oracle
     torch.set_num_threads(os.cpu_count() or 1)
     g = torch.Generator().manual_seed(0)
     if workload == "filter_linear":
         raise SystemExit("--impl reference supports the sfno12_* workloads")
     ftype = "linear" if workload == "sfno12_linear" else "non-linear"
+    x = torch.randn(1, NVAR, *IMG, generator=g)
+    if ref_import.available():
+        ref = ref_import.load()
+        ref_import.use_harmonics(ref.th_shim)
+        torch.manual_seed(0)
+        net = ref.sfnonet.FourierNeuralOperatorNet("cpu", ref.Attributes(), filter_type=ftype).eval()
+
+        def full():
+            with torch.no_grad():
+                return net(x)
+
+        def partial(nblocks):
+            """encoder + first nblocks blocks (bounded sample); timing is extrapolated by the caller."""
+            with torch.no_grad():
+                h = net.encoder(x) + net.pos_embed
+                for blk in list(net.blocks)[:nblocks]:
+                    h = blk(h)
+                return h
+
+        return full, partial, dict(cores=torch.get_num_threads(), ftype=ftype, kind="reference",
+                                   what="unmodified reference modules (%s)" % ref_import.REFERENCE_ROOT)
     tr = sfno_oracle.Transforms(IMG, 6)
     sd = sfno_oracle.make_state_dict(filter_type=ftype, img_size=IMG, in_chans=NVAR, out_chans=NVAR, embed=EMBED,
                                      num_layers=NLAYERS, seed=0)
-    x = torch.randn(1, NVAR, *IMG, generator=g)
 
     def full():
         with torch.no_grad():
@@ -111,14 +137,13 @@ def cpu_reference_step_factory(workload):
 
     def partial(nblocks):
         """encoder + first nblocks blocks (bounded sample); timing is extrapolated by the caller."""
-        import torch.nn.functional as F
         with torch.no_grad():
             h = sfno_oracle.mlp_1x1(x, sd, "encoder.") + sd["pos_embed"]
             for i in range(nblocks):
                 h = sfno_oracle.block_forward(h, sd, i, NLAYERS, ftype, tr)
             return h
 
-    return full, partial, dict(cores=torch.get_num_threads(), ftype=ftype)
+    return full, partial, dict(cores=torch.get_num_threads(), ftype=ftype, kind="port", what="oracle port (no reference copy present)")
 
 
 def run_reference(args):
@@ -132,7 +157,7 @@ def run_reference(args):
     budget = 200.0
     total = args.steps + max(args.warmup - 1, 0)
     if t_full * total <= budget:
-        sample, scale, fn = "1 full 12-block forward per step", 1.0, full
+        sample, scale, fn = "1 full 12-block forward per step; " + info["what"], 1.0, full
     else:
         # bounded sample: encoder + the first nb blocks; scaled to a full step by the measured ratio
         nb = 2
@@ -140,7 +165,7 @@ def run_reference(args):
         partial(nb)
         t_part = time.perf_counter() - t0
         scale = t_full / t_part
-        sample = "encoder + first %d of 12 blocks per step, scaled x%.2f to a full forward (ratio measured on one full forward)" % (nb, scale)
+        sample = "encoder + first %d of 12 blocks per step, scaled x%.2f to a full forward (ratio measured on one full forward); %s" % (nb, scale, info["what"])
         fn = lambda: partial(nb)
     for _ in range(max(args.warmup - 1, 0)):
         fn()
@@ -154,7 +179,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, "cpu"),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -170,6 +195,31 @@ def workload_config(args, precision):
     return {"workload": names[args.workload], "precision_tier": precision, "batch_per_gpu": 1, "lmax": LMAX, "mmax": MMAX,
             "l2_policy": "inputs larger than L2 (x 303 MB, activations 1.06 GB per pass vs 126 MB L2)",
             "parallelism": "independent members, one per GPU, no data-path collective"}
+
+
+def ncu_traffic(csv_names, kernel_substr, which=0):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes) of the `which`-th launch whose kernel name contains
+    `kernel_substr`, read from the first of `csv_names` that exists under profiles/ (an `ncu --set full ... --page raw
+    --csv` export).  Returns (bytes or None, source or None): a missing capture gives null, never a literal."""
+    import csv
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for name in csv_names:
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        try:
+            rows = list(csv.reader(l for l in open(path) if not l.startswith("==")))
+            h = rows[0]
+            ik, ir, iw = h.index("Kernel Name"), h.index("dram__bytes_read.sum"), h.index("dram__bytes_write.sum")
+            units = rows[1]
+            hits = [r for r in rows[2:] if kernel_substr in r[ik]]
+            if len(hits) > which:
+                r = hits[which]
+                val = float(r[ir].replace(",", "")) * unit[units[ir]] + float(r[iw].replace(",", "")) * unit[units[iw]]
+                return val, "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this launch, profiles/%s" % name
+        except (ValueError, KeyError, IndexError):
+            continue
+    return None, None
 
 
 # ----------------------------------------------------------------------------------------- our arm
@@ -246,7 +296,8 @@ def dominant_kernel_roofline(args, net, dev, pk):
         ach = flops / (ms * 1e-3) / 1e12
         peak = pk["bf16_sustained"] / 2.0
         stages["spectral_mlp_hidden_gemm"] = {
-            "kernel": "gemm_tc2_kernel (CTA pair, cta_group::2): [7440 x 1024] x [1024 x 1024], 36 launches per step", "ms": ms,
+            "kernel": "%s: [7440 x 1024] x [1024 x 1024], 24 launches per step" % (
+                "gemm_tc2_kernel (CTA pair, cta_group::2)" if args.precision == "tf32" else "gemm_tc3_kernel (3xTF32, register accumulation)"), "ms": ms,
             "bound": "tensor", "achieved_TFLOPs": ach, "peak_TFLOPs": peak, "frac_of_tf32_peak": ach / peak,
             "peak_source": "%s bf16_tflops_sustained / 2 (TF32 = half of BF16, BASELINE.md section 2)" % pk["src"]}
         del A, W, D
@@ -258,15 +309,15 @@ def dominant_kernel_roofline(args, net, dev, pk):
                 ms = timed(lambda: net._encode_fused(xin))
             by = 4.0 * IMG[0] * IMG[1] * (net.in_chans + 2 * EMBED)   # input + pos_embed read, output written, once each
             ach = by / (ms * 1e-3) / 1e9
+            traffic, tsrc = ncu_traffic(["r02_ncu_mlp_tc_raw.csv", "r01_ncu_final_raw.csv"], "mlp_tc_kernel", 0)
             return {"kernel": "mlp_tc_kernel (fused encoder MLP 73->256->256 + pos_embed, hidden tile in TMEM; 1 of 13 launches per step)",
-                    "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": 2.386e9,
-                    "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this launch, "
-                                      "profiles/r01_ncu_final_raw.csv",
+                    "bound": "hbm", "achieved": ach, "peak": pk["hbm"], "unit": "GB/s", "frac": ach / pk["hbm"], "traffic": traffic,
+                    "traffic_source": tsrc,
                     "peak_source": "%s hbm_gbs" % pk["src"], "ms_per_launch": ms, "algorithmic_bytes": by, "stages": stages}
-        return {"kernel": "gemm (spectral complex-MLP hidden layer, M=7260 modes, N=K=1024 real)", "bound": "tensor",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": 35.5e6,
-                "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum of this launch (operands are L2 resident), "
-                                  "profiles/r01_ncu_full_fft_gemm_inner_raw.csv",
+        traffic, tsrc = ncu_traffic(["r02_ncu_x3_gemm_raw.csv"], "gemm_tc3_kernel", 0)
+        return {"kernel": "gemm_tc3_kernel (3xTF32 spectral complex-MLP hidden layer, M=7260 modes, N=K=1024 real)", "bound": "tensor",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                "traffic_source": tsrc,
                 "peak_source": "%s bf16_tflops_sustained / 2 (TF32 = half of BF16, BASELINE.md section 2)" % pk["src"],
                 "ms_per_launch": ms, "stages": stages}
     # linear workloads: the SpectralConvS2 weight stream
@@ -288,6 +339,34 @@ def dominant_kernel_roofline(args, net, dev, pk):
             "ms_per_launch": ms, "stages": stages}
 
 
+def copy_ceiling(dev, nbytes, iters=5):
+    """Bare pinned-memory copies of the e2e payload on this rank: H2D and D2H of `nbytes` each on two streams at once
+    (what HostPipeline overlaps), no kernels.  Returns ms per (H2D + D2H) pair: e2e cannot beat it."""
+    import torch
+    h_in = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    h_out = torch.empty(nbytes // 4, dtype=torch.float32).pin_memory()
+    d_in = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    d_out = torch.empty(nbytes // 4, dtype=torch.float32, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    main = torch.cuda.current_stream()
+    for rep in range(2):   # first pass warms the pinned mappings
+        e0.record(main)
+        s1.wait_stream(main)
+        s2.wait_stream(main)
+        for _ in range(iters):
+            with torch.cuda.stream(s1):
+                d_in.copy_(h_in, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+        main.wait_stream(s1)
+        main.wait_stream(s2)
+        e1.record(main)
+        torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -300,12 +379,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    import msfno_b200
     from msfno_b200 import _lib
     pk = peaks()
-    net, xshape = build_ours(args, dev)
-    g = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(*xshape, generator=g).pin_memory()
-    x_dev = x_host.to(dev)
 
     def sync_all():
         if world > 1:
@@ -319,56 +395,81 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    g = torch.Generator().manual_seed(1234 + rank)
+    xshape = (1, EMBED, *IMG) if args.workload == "filter_linear" else (1, NVAR, *IMG)
+    x_host = torch.randn(*xshape, generator=g).pin_memory()
+    x_dev = x_host.to(dev)
+
+    def measure(precision, want_clocks):
+        """One tier: device-resident leg (value) and host-buffer leg (e2e), each K steps after W warm-ups."""
+        targs = argparse.Namespace(**vars(args))
+        targs.precision = precision
+        net, _ = build_ours(targs, dev)
+        with torch.no_grad():
+            y = net(x_dev)
+            y_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
+            eager = net
+            launches_per_step = None
+            if not args.no_graph:
+                l_one = _lib.lib.msfno_launch_count()
+                eager(x_dev)
+                launches_per_step = _lib.lib.msfno_launch_count() - l_one   # kernels one replay contains
+                net = msfno_b200.GraphedForward(eager, x_dev)
+            for _ in range(max(args.warmup - 1, 0)):
+                net(x_dev)
+            # ---- device-resident leg ---------------------------------------------------------------
+            sampler = ClockSampler(local)
+            sync_all()
+            if rank == 0 and want_clocks:
+                sampler.start()
+            l0 = _lib.lib.msfno_launch_count()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if args.no_graph:
+                for _ in range(args.steps):
+                    y = net(x_dev)
+            else:  # the input already sits in the graph's static input buffer (resident in HBM)
+                for _ in range(args.steps):
+                    y = net()
+            e1.record()
+            sync_all()
+            launches = _lib.lib.msfno_launch_count() - l0
+            if not args.no_graph:
+                launches = launches_per_step * args.steps  # replayed inside the graph: the library counter does not see replays
+            ms_dev = max_over_ranks(e0.elapsed_time(e1))
+            clocks = sampler.stop() if (rank == 0 and want_clocks) else None
+            # ---- end-to-end leg: host buffers in, host buffers out, through the public HostPipeline API ----------
+            pipe = msfno_b200.HostPipeline(net, dev)
+            xs = [x_host, x_host.clone().pin_memory()]
+            ys = [y_host, torch.empty_like(y_host).pin_memory()]
+            pipe.run([xs[i % 2] for i in range(3)], [ys[i % 2] for i in range(3)])
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            pipe.run([xs[i % 2] for i in range(args.steps)], [ys[i % 2] for i in range(args.steps)])
+            e1.record()
+            sync_all()
+            ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        return dict(net=net, eager=eager, ms_dev=ms_dev, ms_e2e=ms_e2e, launches=int(launches), clocks=clocks,
+                    finite=bool(torch.isfinite(y_host).all()), h2d=x_host.numel() * 4, d2h=y_host.numel() * 4)
+
+    primary = measure(args.precision, True)
     with torch.no_grad():
-        y = net(x_dev)
-        y_host = torch.empty(y.shape, dtype=y.dtype).pin_memory()
-        eager = net
-        if not args.no_graph:
-            import msfno_b200
-            l_one = _lib.lib.msfno_launch_count()
-            eager(x_dev)
-            launches_per_step = _lib.lib.msfno_launch_count() - l_one   # kernels one replay contains
-            net = msfno_b200.GraphedForward(eager, x_dev)
-        for _ in range(max(args.warmup - 1, 0)):
-            net(x_dev)
-        # ---- device-resident leg ---------------------------------------------------------------
-        sampler = ClockSampler(local)
-        sync_all()
-        if rank == 0:
-            sampler.start()
-        l0 = _lib.lib.msfno_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        if args.no_graph:
-            for _ in range(args.steps):
-                y = net(x_dev)
-        else:  # the input already sits in the graph's static input buffer (resident in HBM)
-            for _ in range(args.steps):
-                y = net()
-        e1.record()
-        sync_all()
-        launches = _lib.lib.msfno_launch_count() - l0
-        if not args.no_graph:
-            launches = launches_per_step * args.steps  # replayed inside the graph: the library counter does not see replays
-        ms_dev = max_over_ranks(e0.elapsed_time(e1))
-        clocks = sampler.stop() if rank == 0 else None
-        # ---- end-to-end leg: host buffers in, host buffers out, through the public HostPipeline API ----------
-        import msfno_b200
-        pipe = msfno_b200.HostPipeline(net, dev)
-        xs = [x_host, x_host.clone().pin_memory()]
-        ys = [y_host, torch.empty_like(y_host).pin_memory()]
-        pipe.run([xs[i % 2] for i in range(3)], [ys[i % 2] for i in range(3)])
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        pipe.run([xs[i % 2] for i in range(args.steps)], [ys[i % 2] for i in range(args.steps)])
-        e1.record()
-        sync_all()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        roof = dominant_kernel_roofline(args, primary["eager"], dev, pk) if rank == 0 else None
+    ceiling_ms = max_over_ranks(copy_ceiling(dev, primary["h2d"]))
+    other_name = "fp32" if args.precision == "tf32" else "tf32"
+    other = None
+    if not args.one_tier and args.workload == "sfno12_nonlinear":
+        del primary["net"], primary["eager"]
+        torch.cuda.empty_cache()
+        other = measure(other_name, False)
+        del other["net"], other["eager"]
+        torch.cuda.empty_cache()
 
-        roof = dominant_kernel_roofline(args, eager, dev, pk) if rank == 0 else None
+    multi = None
+    if world > 1 and not args.no_multi_gpu_extras:
+        multi = multi_gpu_extras(args, dev, rank, world, max_over_ranks, sync_all)
 
-    bad = not torch.isfinite(y_host).all()
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -384,31 +485,75 @@ def run_ours(args):
             t0 = time.perf_counter()
             full()
             dt = time.perf_counter() - t0
-            cpu_baseline = {"value": 1.0 / dt, "unit": UNIT, "cores": info["cores"], "kind": "port",
-                            "sample": "1 full 12-block forward (after 1 warm-up) of the oracle port of the reference path, fp32"}
+            cpu_baseline = {"value": 1.0 / dt, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
+                            "sample": "1 full 12-block forward (after 1 warm-up), fp32; " + info["what"]}
         except Exception as e:  # the baseline is a reported number, never a reason to lose the GPU measurement
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (e,)}
 
-    value = world * args.steps / (ms_dev * 1e-3)
+    def tier_entry(m, name):
+        return {"dtype": "f32 (3xTF32 on tcgen05, fp32 accumulate, FFT longitude transforms)" if name == "fp32" else "tf32",
+                "tolerance_rel_l2": 1e-5 if name == "fp32" else 2e-3,
+                "value": world * args.steps / (m["ms_dev"] * 1e-3), "ms_per_step": m["ms_dev"] / args.steps,
+                "e2e": world * args.steps / (m["ms_e2e"] * 1e-3), "e2e_ms_per_step": m["ms_e2e"] / args.steps,
+                "gpu_launches": m["launches"], "output_finite": m["finite"]}
+
+    tiers = {args.precision: tier_entry(primary, args.precision)}
+    if other is not None:
+        tiers[other_name] = tier_entry(other, other_name)
+    value = world * args.steps / (primary["ms_dev"] * 1e-3)
+    e2e_ms = primary["ms_e2e"] / args.steps
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": primary["ms_dev"] / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "tf32", "data": "synthetic",
         "config": workload_config(args, args.precision),
-        "e2e": {"value": world * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
-                "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": y_host.numel() * 4,
-                "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
+        "e2e": {"value": world * args.steps / (primary["ms_e2e"] * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": primary["h2d"], "d2h_bytes_per_step": primary["d2h"],
+                "ms_per_step": e2e_ms,
+                # bare pinned H2D + D2H of the same payload on this box at this N (max over ranks), no kernels: the
+                # host-link floor of one step; e2e cannot beat it
+                "copy_ceiling_ms_per_step": ceiling_ms,
+                "copy_ceiling_GBps": world * (primary["h2d"] + primary["d2h"]) / (ceiling_ms * 1e-3) / 1e9,
+                "frac_of_copy_ceiling": ceiling_ms / e2e_ms},
+        "tiers": tiers,
+        "gpu_launches": primary["launches"],
+        "clocks": primary["clocks"],
         "roofline": roof,
         "cpu_baseline": cpu_baseline,
-        "output_finite": not bad,
+        "output_finite": primary["finite"] and (other is None or other["finite"]),
         "cuda_graph": not args.no_graph,
     }
+    if multi is not None:
+        line["multi_gpu"] = multi
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def multi_gpu_extras(args, dev, rank, world, max_over_ranks, sync_all):
+    """N > 1 only: the two paths that really communicate, timed in the same run (device time, max over ranks).
+    sharded_sht: BASELINE configs[4] (A): 1441 x 2880, 256 channels, lmax 240 -- latitude-sharded FFT, all-to-all
+                 lat<->m over NVLink, order-sharded Legendre, and back.
+    ddp_train:   BASELINE configs[2]: MSFNO fwd + bwd + Adam on the FiLM head, per-rank batch 8, film_layers 1,
+                 DistributedDataParallel over NCCL."""
+    import torch
+    out = {}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_sharded_sht
+        out["sharded_sht"] = bench_sharded_sht.run(dev, rank, world, max_over_ranks, sync_all, steps=max(3, min(args.steps, 10)))
+    except Exception as e:
+        out["sharded_sht"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    try:
+        import bench_train_step
+        out["ddp_train"] = bench_train_step.run(dev, rank, world, max_over_ranks, sync_all, batch=8, film_layers=1,
+                                                steps=max(2, min(args.steps, 5)))
+    except Exception as e:
+        out["ddp_train"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -428,6 +573,8 @@ def main():
                     help="tf32: tensor-core tier (<= 2e-3 rel-L2 vs the reference, tests/test_gpu_tc.py); fp32: exact tier (<= 1e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--one-tier", action="store_true", help="measure only --precision (default: both tiers, reported under `tiers`)")
+    ap.add_argument("--no-multi-gpu-extras", action="store_true", help="N > 1: skip the sharded-SHT and DDP-training legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

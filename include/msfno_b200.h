@@ -209,6 +209,17 @@ int msfno_gelu_bwd_mul(const float* g, const float* h, float* out, long long n, 
 int msfno_plane_affine(const float* x, const float* A, const float* S, float* y, int planes, long HW,
                        void* stream);
 
+/* ---- 8(f) N3: latitude-weighted squared-error reductions of the spherical losses ----------------------------
+ * replaces: L2Sphere / L2Sphere_noSine / CosineMSELoss.forward (MSFNO/Models/losses.py:6-37,80-155) and their autograd:
+ *   out[plane] = ( sum_{h,w} wlat[h] (prd - tar)^2 ,  sum_{h,w} wlat[h] tar^2 )      (fp64, overwritten)
+ * prd, tar: [planes][H][W]; wlat: [H] device vector (the reference rebuilds it on the host every call, :90,129). */
+int msfno_weighted_sq_sums(const float* prd, const float* tar, const float* wlat, double* out, int planes, int H,
+                           int W, void* stream);
+/* gprd[plane][h][w] = coef[plane] * wlat[h] * (prd - tar): the adjoint of the reduction with the chain-rule factors of
+ * the caller (2, 1/norm, 1/(2 sqrt(.)), upstream gradient) folded into coef. */
+int msfno_weighted_diff(const float* prd, const float* tar, const float* wlat, const float* coef, float* gprd,
+                        int planes, int H, int W, void* stream);
+
 /* ---- 8(f) N2: 1x1 convolution (NCHW) with fused epilogue ------------------------------------------------
  * replaces: nn.Conv2d(cin, cout, 1) + bias + nn.GELU + residual/pos_embed add + torch.cat of the big skip
  *           (MSFNO/Models/sfno/layers.py:161-168; sfnonet.py:184-185,232,249,671,682-684).

@@ -18,12 +18,15 @@ from .layers import MLP, ComplexReLU, DropPath, SpectralAttentionS2, SpectralCon
 from .sfnonet import (FeedForward, FiLM, Film_wrapper, FourierNeuralOperatorBlock, FourierNeuralOperatorBlock_Filmed,
                       FourierNeuralOperatorNet, FourierNeuralOperatorNet_Filmed, SpectralFilterLayer)
 from . import harmonics
+from . import losses
+from .losses import CosineMSELoss, L2Sphere, L2Sphere_noSine
 from .pipeline import HostPipeline
 from .graph import GraphedForward
+from .trainer import Trainer, TrainerConfig, freeze_backbone
 
 __all__ = [
     "RealSHT", "InverseRealSHT", "quadrature", "legendre", "harmonics", "set_precision", "get_precision", "set_fp32_engine", "get_fp32_engine", "invalidate_caches",
     "SpectralConvS2", "SpectralAttentionS2", "ComplexReLU", "MLP", "DropPath", "trunc_normal_",
     "SpectralFilterLayer", "FiLM", "FourierNeuralOperatorBlock", "FourierNeuralOperatorBlock_Filmed",
-    "FourierNeuralOperatorNet", "FourierNeuralOperatorNet_Filmed", "Film_wrapper", "FeedForward", "HostPipeline", "GraphedForward",
+    "FourierNeuralOperatorNet", "FourierNeuralOperatorNet_Filmed", "Film_wrapper", "FeedForward", "HostPipeline", "GraphedForward", "Trainer", "TrainerConfig", "freeze_backbone", "losses", "L2Sphere", "L2Sphere_noSine", "CosineMSELoss",
 ]

@@ -6,7 +6,7 @@ OUT=../libmsfno_b200.so
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v ${MSFNO_EXTRA_FLAGS:-}"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 mkdir -p build
-SRCS="fft fft2d plan gemm_ffma specconv specattn sht elementwise gemm_tc conv_tc conv1x1 mlp_tc dft_tc"
+SRCS="fft fft2d plan gemm_ffma specconv specattn sht elementwise gemm_tc conv_tc conv1x1 mlp_tc dft_tc losses"
 pids=()
 for f in $SRCS; do
   rm -f build/$f.o

@@ -176,18 +176,27 @@ class DistributedSHT:
         st = self.stages
         B, C = x_loc.shape[0], x_loc.shape[1]
         Xt_loc = st.fft_fwd(x_loc.contiguous())                       # [B, mlim, 2C, pad(nlat_loc)]
-        ins, outs = [], []
-        for s in range(self.world):
-            lo, hi = self.m_bounds[s], self.m_bounds[s + 1]
-            ins.append(Xt_loc[:, lo:hi, :, :self.nlat_loc].contiguous())
-            n_s = self.lat_bounds[s + 1] - self.lat_bounds[s]
-            outs.append(torch.empty((B, self.m_hi - self.m_lo, 2 * C, n_s), dtype=x_loc.dtype, device=x_loc.device))
-        exchange(outs, ins, self.group)
-        Xt = torch.zeros((B, self.m_hi - self.m_lo, 2 * C, st.pad(self.nlat)), dtype=x_loc.dtype, device=x_loc.device)
-        for s in range(self.world):
-            Xt[..., self.lat_bounds[s]:self.lat_bounds[s + 1]] = outs[s]
+        mloc = self.m_hi - self.m_lo
+        if self.world == 1:
+            Xt = Xt_loc                                               # the stage's own padded layout: nothing to move
+        else:
+            # send side: a destination's orders are one contiguous run of the m-major intermediate (for B = 1 the slices
+            # below are views -- no copy), sent with their padded latitude pitch; receive side: one strided scatter per
+            # source into the full-latitude operand of the Legendre stage
+            ins, outs = [], []
+            for s in range(self.world):
+                lo, hi = self.m_bounds[s], self.m_bounds[s + 1]
+                ins.append(Xt_loc[:, lo:hi].contiguous())
+                pw = st.pad(self.lat_bounds[s + 1] - self.lat_bounds[s])     # the SENDER's padded pitch
+                outs.append(torch.empty((B, mloc, 2 * C, pw), dtype=x_loc.dtype, device=x_loc.device))
+            exchange(outs, ins, self.group)
+            Xt = torch.empty((B, mloc, 2 * C, st.pad(self.nlat)), dtype=x_loc.dtype, device=x_loc.device)
+            Xt[..., self.nlat:] = 0
+            for s in range(self.world):
+                n_s = self.lat_bounds[s + 1] - self.lat_bounds[s]
+                Xt[..., self.lat_bounds[s]:self.lat_bounds[s + 1]] = outs[s][..., :n_s]
         p0, p1 = self.pos_range()
-        if self.m_hi == self.m_lo:
+        if mloc == 0:
             return torch.zeros((B, 0, 2 * C), dtype=x_loc.dtype, device=x_loc.device)
         return st.legendre_fwd(Xt, self.m_lo, self.m_hi, p1 - p0)
 
@@ -199,15 +208,29 @@ class DistributedSHT:
             Yt = st.legendre_inv(cm_loc.contiguous(), self.m_lo, self.m_hi)  # [B, mloc, 2C, pad(nlat)]
         else:
             Yt = torch.zeros((B, 0, 2 * C, st.pad(self.nlat)), dtype=cm_loc.dtype, device=cm_loc.device)
+        if self.world == 1:
+            return st.fft_inv(Yt, B, C)
+        # send side: one strided gather per destination, written with the destination's padded latitude pitch; receive
+        # side: a source's orders are one contiguous run of the local m-major operand -- for B = 1 the receive buffers ARE
+        # views of it (no assembly copy)
+        padl = st.pad(self.nlat_loc)
+        Yt_loc = torch.empty((B, self.mlim, 2 * C, padl), dtype=cm_loc.dtype, device=cm_loc.device)
+        direct = B == 1
         ins, outs = [], []
         for s in range(self.world):
-            ins.append(Yt[..., self.lat_bounds[s]:self.lat_bounds[s + 1]].contiguous())
-            ms = self.m_bounds[s + 1] - self.m_bounds[s]
-            outs.append(torch.empty((B, ms, 2 * C, self.nlat_loc), dtype=cm_loc.dtype, device=cm_loc.device))
+            n_s = self.lat_bounds[s + 1] - self.lat_bounds[s]
+            pw = st.pad(n_s)
+            blk = torch.empty((B, mloc, 2 * C, pw), dtype=cm_loc.dtype, device=cm_loc.device)
+            blk[..., :n_s] = Yt[..., self.lat_bounds[s]:self.lat_bounds[s + 1]]
+            if pw > n_s:
+                blk[..., n_s:] = 0
+            ins.append(blk)
+            view = Yt_loc[:, self.m_bounds[s]:self.m_bounds[s + 1]]
+            outs.append(view if direct else torch.empty_like(view))
         exchange(outs, ins, self.group)
-        Yt_loc = torch.zeros((B, self.mlim, 2 * C, st.pad(self.nlat_loc)), dtype=cm_loc.dtype, device=cm_loc.device)
-        for s in range(self.world):
-            Yt_loc[:, self.m_bounds[s]:self.m_bounds[s + 1], :, :self.nlat_loc] = outs[s]
+        if not direct:
+            for s in range(self.world):
+                Yt_loc[:, self.m_bounds[s]:self.m_bounds[s + 1]] = outs[s]
         return st.fft_inv(Yt_loc, B, C)
 
     # -- helpers for tests / the public boundary ---------------------------------------------------

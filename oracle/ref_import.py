@@ -2,8 +2,9 @@
 /root/reference so the restatement in sfno_oracle.py / th_shim.py can be checked against
 the real thing and golden vectors can be generated (oracle/gen_golden.py).
 
-/root/reference does not exist on the GPU box: nothing under tests -m gpu, smoke() or
-bench.py calls this.  The reference needs a handful of absent third-party modules purely at
+/root/reference does not exist on the GPU box: there the byte-identical copy staged by
+oracle/build_ref.sh under the git-ignored oracle/_ref/ is imported instead (bench.py --impl reference,
+tests/test_gpu_dropin.py).  The reference needs a handful of absent third-party modules purely at
 import time; they are stubbed in sys.modules.  torch_harmonics
 is replaced by oracle/th_shim.py (un-vendored dependency, conda_environment.yml:62).
 """
@@ -13,11 +14,24 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("MSFNO_REFERENCE_ROOT", "/root/reference")
+# the mounted reference tree (build container), else the byte-identical copy staged by oracle/build_ref.sh in the
+# git-ignored oracle/_ref/ (which travels to the GPU box with the snapshot)
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+_MOUNT = os.environ.get("MSFNO_REFERENCE_ROOT", "/root/reference")
+REFERENCE_ROOT = _MOUNT if os.path.isdir(os.path.join(_MOUNT, "MSFNO", "Models", "sfno")) else _STAGED
 
 
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "MSFNO", "Models", "sfno"))
+
+
+def use_harmonics(mod):
+    """Point the reference's `import torch_harmonics as harmonics` at `mod` (oracle.th_shim on the CPU legs,
+    msfno_b200.harmonics for the drop-in tests): the reference looks the classes up at construction time."""
+    st = sys.modules["torch_harmonics"]
+    st.RealSHT, st.InverseRealSHT, st.quadrature = mod.RealSHT, mod.InverseRealSHT, mod.quadrature
+    if hasattr(mod, "legendre"):
+        st.legendre = mod.legendre
 
 
 def _stub(name, **attrs):
@@ -58,8 +72,9 @@ def load():
           quadrature=th_shim.quadrature, legendre=th_shim.legendre)
 
     from MSFNO.Models.sfno import sfnonet, layers, contractions, activations
+    from MSFNO.Models import losses
     from MSFNO.utils import Attributes
 
     _loaded = types.SimpleNamespace(sfnonet=sfnonet, layers=layers, contractions=contractions,
-                                    activations=activations, Attributes=Attributes)
+                                    activations=activations, losses=losses, Attributes=Attributes, th_shim=th_shim)
     return _loaded

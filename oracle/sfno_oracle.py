@@ -168,6 +168,30 @@ def film_head(cond, sd, prefix="film_gen.film_head.net."):
 
 
 # --------------------------------------------------------------------------- random init
+def l2_sphere(prd, tar, relative=True, squared=False, sine=True):
+    """L2Sphere (sine=True) / L2Sphere_noSine, reduction "sum" or "mean" (/root/reference MSFNO/Models/losses.py:80-155)."""
+    H = prd.shape[2]
+    w = torch.tensor(th_shim.legendre_gauss_weights(H, -1, 1)[1], dtype=prd.dtype)
+    if sine:
+        w = torch.abs(w * torch.cos(torch.linspace(-math.pi / 2, math.pi / 2, H, dtype=prd.dtype)))
+    w = w[None, None, :, None]
+    loss = (w * (prd - tar) ** 2).sum(dim=(-1, -2))
+    if relative:
+        loss = loss / (w * tar ** 2).sum(dim=(-1, -2))
+    if not squared:
+        loss = torch.sqrt(loss)
+    return loss.sum()
+
+
+def cosine_mse(x, y, reduction="mean", eps=1e-4):
+    """CosineMSELoss (/root/reference MSFNO/Models/losses.py:6-37)."""
+    H, W = x.shape[2], x.shape[3]
+    w = torch.clamp(torch.cos(torch.linspace(-math.pi / 2, math.pi / 2, H, dtype=x.dtype)), min=0.0) + eps
+    w = (w / w.sum(dim=-1, keepdim=True))[None, None, :, None]
+    loss = (x - y) ** 2 * w
+    return loss.mean() if reduction == "mean" else loss.sum() / W
+
+
 def trunc_normal_(t, std=0.02, gen=None):
     """trunc_normal_(std=0.02) clipped to [-2,2] absolute (layers.py:29-84)."""
     with torch.no_grad():

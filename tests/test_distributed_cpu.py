@@ -74,14 +74,14 @@ class TorchStages:
         return out
 
 
-def _worker(rank, world, port, nlat, nlon, L, M, grid, q):
+def _worker(rank, world, port, nlat, nlon, L, M, grid, q, B=2):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.manual_seed(0)
         o_s = th_shim.RealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid)
         o_i = th_shim.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid=grid)
-        B, C = 2, 3
+        C = 3
         x = torch.randn(B, C, nlat, nlon, dtype=torch.float64)
         dsht = D.DistributedSHT(nlat, nlon, L, M, lambda nloc: TorchStages(nlat, nloc, nlon, L, M, o_s.weights, o_i.pct))
         pm_loc = dsht.forward_packed(x[:, :, dsht.lat_lo:dsht.lat_hi])
@@ -119,13 +119,14 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,nlat,nlon,L,M,grid", [(2, 24, 48, 12, 13, "equiangular"), (3, 25, 48, 10, 13, "equiangular"),
-                                                      (2, 16, 32, 16, 9, "legendre-gauss")])
-def test_spatially_sharded_sht_gloo(world, nlat, nlon, L, M, grid):
+@pytest.mark.parametrize("world,nlat,nlon,L,M,grid,B", [(2, 24, 48, 12, 13, "equiangular", 2), (3, 25, 48, 10, 13, "equiangular", 2),
+                                                        (2, 16, 32, 16, 9, "legendre-gauss", 2),
+                                                        (3, 25, 48, 10, 13, "equiangular", 1)])   # B = 1: receive straight into views
+def test_spatially_sharded_sht_gloo(world, nlat, nlon, L, M, grid, B):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, nlat, nlon, L, M, grid, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nlat, nlon, L, M, grid, q, B)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:

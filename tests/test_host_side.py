@@ -199,3 +199,26 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
     assert "plan_create" in _lib.last_error()
     with pytest.raises(RuntimeError, match="fold_affine: bad argument"):
         _lib.check(lib.msfno_fold_affine(None, None, None, None, None, None, 1, 1, 1, 1, 0, None), "fold_affine")
+
+
+def test_staged_reference_copy_is_unmodified():
+    """oracle/_ref/ (git-ignored, staged by oracle/build_ref.sh) must be byte-identical to the reference it was copied
+    from: the recorded SHA-256 sums are checked, and against the mounted tree where there is one."""
+    import hashlib
+    import os
+    staged = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    sums = os.path.join(staged, "SHA256SUMS")
+    if not os.path.exists(sums):
+        import pytest
+        pytest.skip("oracle/_ref not staged (run oracle/build_ref.sh where /root/reference is mounted)")
+    n = 0
+    for line in open(sums):
+        digest, rel = line.split()
+        with open(os.path.join(staged, rel), "rb") as f:
+            assert hashlib.sha256(f.read()).hexdigest() == digest, rel
+        mounted = os.path.join("/root/reference", rel)
+        if os.path.exists(mounted):
+            with open(mounted, "rb") as f:
+                assert hashlib.sha256(f.read()).hexdigest() == digest, "staged copy differs from " + mounted
+        n += 1
+    assert n >= 9

@@ -95,3 +95,21 @@ def test_film_and_transform_goldens():
         isht = th_shim.InverseRealSHT(d["nlat"], d["nlon"], lmax=d["lmax"], mmax=d["mmax"], grid=d["grid"]).float()
         assert rel_l2(torch.view_as_real(sht(d["x"])), torch.view_as_real(d["coeffs"])) < 1e-6
         assert rel_l2(isht(d["cin"]), d["y"]) < 1e-6
+
+
+def test_loss_oracle_matches_reference_losses():
+    """oracle.sfno_oracle.l2_sphere / cosine_mse vs the UNMODIFIED reference losses.py (mounted tree or its staged copy)."""
+    import pytest
+    import torch
+    from oracle import ref_import, sfno_oracle
+    if not ref_import.available():
+        pytest.skip("no copy of the reference")
+    ref = ref_import.load()
+    ref_import.use_harmonics(ref.th_shim)
+    g = torch.Generator().manual_seed(1)
+    a, b = torch.randn(2, 4, 24, 48, generator=g), torch.randn(2, 4, 24, 48, generator=g)
+    for rel, sq in ((True, False), (False, True), (True, True)):
+        assert abs(float(sfno_oracle.l2_sphere(a, b, rel, sq, True)) - float(ref.losses.L2Sphere(rel, sq)(a, b))) < 1e-6
+        assert abs(float(sfno_oracle.l2_sphere(a, b, rel, sq, False)) - float(ref.losses.L2Sphere_noSine(rel, sq)(a, b))) < 1e-6
+    for red in ("mean", "sum"):
+        assert abs(float(sfno_oracle.cosine_mse(a, b, red)) - float(ref.losses.CosineMSELoss(red)(a, b))) < 1e-6

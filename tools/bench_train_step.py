@@ -16,6 +16,46 @@ class Cfg:
     film_gen_type, cls, embed_dim, mlp_dim, dropout, scale_weight, repeat_film = "mae", "x", 512, 1024, 0.0, 1, False
 
 
+def run(dev, rank, world, max_over_ranks, sync_all, batch=8, film_layers=1, steps=5, warmup=2, precision="tf32"):
+    """One data-parallel MSFNO training step through msfno_b200.Trainer (the reference's loop structure, train.py:201-298):
+    frozen backbone, DistributedDataParallel over the FiLM head when world > 1.  Returns the result dict (all ranks)."""
+    msfno_b200.set_precision(precision)
+    try:
+        torch.manual_seed(0)
+        cfg = Cfg()
+        cfg.film_layers, cfg.batch_size = film_layers, batch
+        net = msfno_b200.FourierNeuralOperatorNet_Filmed(dev, cfg, advanced_logging=False, film_layers=film_layers, model_depth=6).to(dev)
+        tcfg = msfno_b200.TrainerConfig(ddp=world > 1, rank=rank, world_size=world, model_version="film")
+        trainer = msfno_b200.Trainer(net, tcfg, loss_fn=torch.nn.MSELoss(), device=dev)
+        trainer.ready_model()
+        g = torch.Generator().manual_seed(rank)
+        x = torch.randn(batch, 73, 721, 1440, generator=g).to(dev)
+        y = torch.randn(batch, 73, 721, 1440, generator=g).to(dev)
+        cond = torch.randn(batch, 512, generator=g).to(dev)
+        data = [(x, cond), (y, cond)]
+
+        def loader(n):
+            for _ in range(n):
+                yield data
+
+        with msfno_b200.precision.library_scope():
+            trainer.train_epoch(loader(warmup))
+            sync_all()
+            torch.cuda.reset_peak_memory_stats()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            losses = trainer.train_epoch(loader(steps))
+            e1.record()
+            sync_all()
+        ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+        return {"config": "configs[2]: MSFNO fwd+bwd+Adam on the FiLM head, film_layers=%d, DDP" % film_layers, "n_gpus": world,
+                "batch_per_gpu": batch, "precision": precision, "ms_per_step": ms, "samples_per_sec": world * batch / ms * 1e3,
+                "loss": float(losses[-1]), "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
+                "trainable_params": sum(p.numel() for p in net.parameters() if p.requires_grad)}
+    finally:
+        msfno_b200.set_precision("fp32")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
@@ -29,54 +69,22 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    msfno_b200.set_precision(a.precision)
-    torch.manual_seed(0)
-    cfg = Cfg()
-    cfg.film_layers, cfg.batch_size = a.film_layers, a.batch
-    net = msfno_b200.FourierNeuralOperatorNet_Filmed(dev, cfg, advanced_logging=False, film_layers=a.film_layers, model_depth=6).to(dev)
-    for n, p in net.named_parameters():
-        p.requires_grad_(n.startswith("film_gen"))
-    model = net
-    if world > 1:
-        model = torch.nn.parallel.DistributedDataParallel(net, device_ids=[local], broadcast_buffers=False)
-    opt = torch.optim.Adam([p for p in net.parameters() if p.requires_grad], lr=1e-4)
-    g = torch.Generator().manual_seed(rank)
-    x = torch.randn(a.batch, 73, 721, 1440, generator=g).to(dev)
-    y = torch.randn(a.batch, 73, 721, 1440, generator=g).to(dev)
-    cond = torch.randn(a.batch, 512, generator=g).to(dev)
-    lossf = torch.nn.MSELoss()
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        with msfno_b200.precision.library_scope():
-            out = model(x, cond, 1.0)
-            loss = lossf(out, y)
-            loss.backward()
-        opt.step()
-        return loss
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        loss = step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(a.steps):
-        loss = step()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / a.steps], device=dev, dtype=torch.float64)
-    if world > 1:
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    res = run(dev, rank, world, max_over_ranks, sync_all, a.batch, a.film_layers, a.steps, a.warmup, a.precision)
     if rank == 0:
-        gn = sum(float(p.grad.norm()) for p in net.parameters() if p.grad is not None)
-        print(json.dumps({"config": "3: MSFNO fwd+bwd+Adam, film_layers=%d" % a.film_layers, "n_gpus": world,
-                          "batch_per_gpu": a.batch, "precision": a.precision, "ms_per_step": float(t),
-                          "samples_per_sec": world * a.batch / float(t) * 1e3, "loss": float(loss), "grad_norm_sum": gn,
-                          "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9}))
+        print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 
