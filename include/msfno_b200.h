@@ -243,12 +243,13 @@ int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const float* w, l
  * MSFNO_ERR_UNSUPPORTED for shapes outside Chid % 32 == 0 (Chid <= 256, or a multiple of 256 up to 1024: processed
  * in 256-channel chunks), Cout <= 256, HW % 4 == 0 (callers then
  * use two msfno_conv1x1_fwd calls).  w1: [Chid][ldw1] (per-sample stride w1_bstride, 0 = shared), w1b: [Chid][ldw1b],
- * w2: [Cout][ldw2], b1: [Chid] (stride b1_bstride), b2: [Cout] or NULL, add: [B or 1][Cout][HW] or NULL.
+ * w2: [Cout][ldw2], b1: [Chid] (stride b1_bstride), b2: [Cout] (per-sample stride b2_bstride, 0 = shared) or NULL,
+ * add: [B or 1][Cout][HW] or NULL.
  * stats: NULL, or [B][Cout][2] doubles that receive the plane (sum, sum of squares) of y -- the InstanceNorm statistics
  * the next block needs (msfno_plane_stats of y) without another pass over y.  flags bit 1: round y to TF32. */
 int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const float* w1, long ldw1, long w1_bstride,
                      const float* x2, long x2_bstride, int Cin2, const float* w1b, long ldw1b, const float* b1,
-                     long b1_bstride, int Chid, const float* w2, long ldw2, const float* b2, const float* add,
+                     long b1_bstride, int Chid, const float* w2, long ldw2, const float* b2, long b2_bstride, const float* add,
                      long add_bstride, float* y, double* stats, int B, int Cout, long HW, int flags, void* stream);
 
 /* ---- generic K-major batched GEMM used by the Legendre and MLP stages ---------------------

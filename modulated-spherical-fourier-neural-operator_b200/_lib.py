@@ -83,7 +83,7 @@ _SIGS = {
     "msfno_conv1x1_fwd": (c_int, [_P, c_long, c_int, _P, c_long, c_long, _P, c_long, c_int, _P, c_long, _P, c_long, _P, c_long, _P,
                           c_int, c_int, c_long, c_int, c_int, _P]),
     "msfno_mlp1x1_fwd": (c_int, [_P, c_long, c_int, _P, c_long, c_long, _P, c_long, c_int, _P, c_long, _P, c_long, c_int, _P, c_long,
-                                 _P, _P, c_long, _P, _P, c_int, c_int, c_long, c_int, _P]),
+                                 _P, c_long, _P, c_long, _P, _P, c_int, c_int, c_long, c_int, _P]),
     "msfno_weighted_sq_sums": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "msfno_weighted_diff": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),
     "msfno_gemm_nt": (c_int, [_P, c_long, _P, c_long, _P, c_long, c_int, c_int, c_int, c_int, c_int, _P]),

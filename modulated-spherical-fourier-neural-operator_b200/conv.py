@@ -85,7 +85,7 @@ def mlp1x1_supported(chid, cout, HW):
 
 @_lib.on_input_device
 def mlp1x1(x, w1, cin, b1, w2, b2=None, add=None, x2=None, w1b=None, cin2=0, per_sample_w1=False, per_sample_b1=False,
-           final=False, w1_rounded=False, stats=None, out=None):
+           final=False, w1_rounded=False, stats=None, out=None, per_sample_b2=False):
     """y = conv1x1(gelu(conv1x1(x, w1) [+ conv1x1(x2, w1b)] + b1), w2) + b2 + add in ONE kernel; the hidden activation
     never reaches HBM.  w1: [Chid, ld] (or [B, Chid, ld]), w1b: [Chid, ld2], w2: [Cout, ld3] zero-padded rows.
     stats: optional [B*Cout, 2] float64 tensor that receives the plane sums / sums of squares of y.
@@ -109,6 +109,6 @@ def mlp1x1(x, w1, cin, b1, w2, b2=None, add=None, x2=None, w1b=None, cin2=0, per
     check(lib.msfno_mlp1x1_fwd(ptr(x), x.shape[1] * HW, cin, ptr(w1), w1.shape[-1], (chid * w1.shape[-1]) if per_sample_w1 else 0,
                                ptr(x2), (x2.shape[1] * HW) if x2 is not None else 0, cin2, ptr(w1b),
                                w1b.shape[-1] if w1b is not None else 0, ptr(b1), chid if per_sample_b1 else 0, chid, ptr(w2),
-                               w2.shape[-1], ptr(b2), ptr(add), add_bs, ptr(y), ptr(stats), B, cout, HW, 0 if final else 2,
+                               w2.shape[-1], ptr(b2), cout if per_sample_b2 else 0, ptr(add), add_bs, ptr(y), ptr(stats), B, cout, HW, 0 if final else 2,
                                torch.cuda.current_stream().cuda_stream), "mlp1x1_fwd")
     return y

@@ -47,7 +47,8 @@ struct MlpTcParams {
   float* D;
   long long ldd, sd;               // output plane stride (= HW) and sample stride
   const float* b1; long long sb1;  // hidden bias [Chid], per-sample stride
-  const float* b2;                 // output bias [Cout] or null
+  const float* b2;                 // output bias [Cout] (+ b * sb2: per-sample bias) or null
+  long long sb2;
   const float* add; long long ldadd, sadd;
   long long x_rows_per_sample, x2_rows_per_sample, w1_rows_per_sample;   // row offsets (tensor-map rows) per sample
   int HW, K1a, K1b, Chid, Cout, N2pad;
@@ -181,7 +182,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   if (threadIdx.x >= 64 && threadIdx.x < 64 + 256) {
     const int c = (int)threadIdx.x - 64;
     for (int h = c; h < ML_MAX_HID; h += 256) b1_s[h] = (p.b1 && h < p.Chid) ? p.b1[(long long)b * p.sb1 + h] : 0.0f;
-    b2_s[c] = (p.b2 && c < p.Cout) ? p.b2[c] : 0.0f;
+    b2_s[c] = (p.b2 && c < p.Cout) ? p.b2[(long long)b * p.sb2 + c] : 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) stat_s[j * 256 + c] = 0.0f;
   }
@@ -417,7 +418,7 @@ using namespace msfno;
 
 extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const float* w1, long ldw1, long w1_bstride,
                                 const float* x2, long x2_bstride, int Cin2, const float* w1b, long ldw1b, const float* b1,
-                                long b1_bstride, int Chid, const float* w2, long ldw2, const float* b2, const float* add,
+                                long b1_bstride, int Chid, const float* w2, long ldw2, const float* b2, long b2_bstride, const float* add,
                                 long add_bstride, float* y, double* stats, int B, int Cout, long HW, int flags, void* stream) {
   if (!x || !w1 || !w2 || !y || B < 1 || Cin < 1 || Chid < 1 || Cout < 1 || HW < 1 || ldw1 < Cin || ldw2 < Chid ||
       (x2 && (!w1b || Cin2 < 1 || ldw1b < Cin2)))
@@ -462,7 +463,7 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
   MSFNO_CUDA_OK(attr_err);
   MlpTcParams p{};
   p.D = y; p.ldd = HW; p.sd = (long long)Cout * HW;
-  p.b1 = b1; p.sb1 = b1_bstride; p.b2 = b2;
+  p.b1 = b1; p.sb1 = b1_bstride; p.b2 = b2; p.sb2 = b2_bstride;
   p.add = add; p.ldadd = HW; p.sadd = add_bstride;
   p.x_rows_per_sample = x_bstride / HW; p.x2_rows_per_sample = x2 ? x2_bstride / HW : 0; p.w1_rows_per_sample = w1_bstride / ldw1;
   p.HW = (int)HW; p.K1a = Cin; p.K1b = x2 ? Cin2 : 0; p.Chid = Chid; p.Cout = Cout; p.N2pad = N2pad;

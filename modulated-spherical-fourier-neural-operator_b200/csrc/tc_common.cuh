@@ -137,6 +137,15 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 inline EncodeTiledFn get_encode() {
+  // cuTensorMapEncodeTiled is a DRIVER call: it fails on a thread that has no current context yet.  PyTorch's autograd
+  // worker threads only bind the primary context at their first runtime call, and a backward pass may reach a
+  // tensor-map encode before any (measured: the first full-size backward of a fresh process).  One cudaFree(0) per
+  // thread binds it.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   static EncodeTiledFn fn = nullptr;
   static std::once_flag once;
   std::call_once(once, [] {

@@ -12,6 +12,9 @@ import contextlib
 import torch
 
 _TIER = "fp32"
+# (the default tier is applied to the PyTorch library flags at import, see set_precision)
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
 
 
 def set_precision(tier):
@@ -19,6 +22,11 @@ def set_precision(tier):
     if tier not in ("fp32", "tf32"):
         raise ValueError("precision tier must be 'fp32' or 'tf32'")
     _TIER = tier
+    # the PyTorch library ops either side of the path (cuDNN / cuBLAS 1x1 convolutions of layers that need weight
+    # gradients, and every autograd backward of them, which runs outside any forward-time scope) follow the tier:
+    # PyTorch allows TF32 in cuDNN convolutions by default, which alone puts ~1e-3 on full-size gradients
+    torch.backends.cudnn.allow_tf32 = tier == "tf32"
+    torch.backends.cuda.matmul.allow_tf32 = tier == "tf32"
 
 
 def set_fp32_engine(engine):

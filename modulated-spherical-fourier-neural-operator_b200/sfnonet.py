@@ -289,59 +289,90 @@ class FourierNeuralOperatorBlock(nn.Module):
                 x = x + self.outer_skip(residual)
         return x
 
-    def _fused(self, x, gamma=None, beta=None, scale=1.0, defer_affine=False, in_stats=None, want_stats=False, prefilm=False):
+    def _fused(self, x, gamma=None, beta=None, scale=1.0, defer_affine=False, in_stats=None, want_stats=False, prefilm=False,
+               mu=None, want_mu=False):
         """Inference path with the normalisations / skip / activation / FiLM folded into the transforms and the
         channel MLP run as two fused 1x1-conv GEMMs (msfno_conv1x1_fwd).  With defer_affine=True (a block without
         MLP, i.e. the last one) the un-normalised output and the pending per-plane affine (A, S) are returned so the
         caller can fold them into the next 1x1 conv instead of spending a full-tensor pass.
         in_stats: plane (sum, sum of squares) of x when the producer already accumulated them (fused MLP epilogue);
         want_stats=True returns (out, stats of out or None) so the next block can skip its statistics pass."""
-        residual = x
+        # Mean-carrying residual stream (tensor-core tier): the tensor handed from block to block is X = x - mu with a
+        # per-plane scalar mu [B, C] carried beside it.  Every producer rounds what it stores to TF32, i.e. relative to
+        # |x| INCLUDING the plane mean, while everything downstream only uses x - mean (InstanceNorm) -- with planes whose
+        # mean is a multiple of their standard deviation the re-rounding of the residual stream at every block was the
+        # largest error term of the tier.  InstanceNorm is shift-invariant, so norm0 / the SHT see X unchanged; the inner
+        # skip conv gets W mu added to its (per-sample) bias; the residual add of the fused MLP subtracts the plane mean
+        # of X through a per-sample output bias, so the stored stream stays centred: mu' = mu + mean(X).
         x = x.contiguous().float()
         B, C = x.shape[0], x.shape[1]
-        A0, S0 = norm_film_coeffs(in_stats if in_stats is not None else plane_stats(x), self.norm0, B, C, x[0, 0].numel())
-        skip = None
-        if hasattr(self, "inner_skip"):
-            if isinstance(self.inner_skip, nn.Conv2d):
-                skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
-            else:
-                skip = self.inner_skip(residual)
-        stats1 = torch.empty((B * C, 2), dtype=torch.float64, device=x.device)
-        y = self.filter_layer(x, in_scale=A0, in_shift=S0, skip_add=skip, act_gelu=hasattr(self, "act_layer"), stats=stats1)
+        HW = x[0, 0].numel()
         mlp = getattr(self, "mlp", None)
         fused_mlp = (not prefilm and mlp is not None and len(mlp.fwd) == 3 and isinstance(mlp.fwd[0], nn.Conv2d)
                      and isinstance(mlp.fwd[1], nn.GELU) and getattr(mlp.fwd[1], "approximate", "none") == "none"
                      and isinstance(mlp.fwd[2], nn.Conv2d))
+        no_drop = isinstance(self.drop_path, nn.Identity) or not self.training
+        fuse_res = no_drop and not self.concat_skip and isinstance(getattr(self, "outer_skip", None), nn.Identity)
+        carry = (want_mu and fused_mlp and fuse_res and _precision.get_precision() == "tf32"
+                 and mlp1x1_supported(mlp.fwd[0].out_channels, mlp.fwd[2].out_channels, HW)
+                 and isinstance(getattr(self, "inner_skip", None), nn.Conv2d))
+        if mu is not None and not (carry or (want_mu and not hasattr(self, "inner_skip") and not hasattr(self, "outer_skip"))):
+            x = x + mu[:, :, None, None]       # a path that cannot carry the offset: materialise x
+            mu, in_stats = None, None
+        residual = x
+        stats0 = in_stats if in_stats is not None else plane_stats(x)
+        A0, S0 = norm_film_coeffs(stats0, self.norm0, B, C, HW)
+        skip = None
+        if hasattr(self, "inner_skip"):
+            if isinstance(self.inner_skip, nn.Conv2d):
+                if mu is not None:
+                    sb = torch.addmm(self.inner_skip.bias.float()[None, :], mu, self.inner_skip.weight.view(C, C).float().t())
+                    skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=sb.contiguous(), per_sample_bias=True)
+                else:
+                    skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
+            else:
+                skip = self.inner_skip(residual)
+        stats1 = torch.empty((B * C, 2), dtype=torch.float64, device=x.device)
+        y = self.filter_layer(x, in_scale=A0, in_shift=S0, skip_add=skip, act_gelu=hasattr(self, "act_layer"), stats=stats1)
         if not fused_mlp:
             A1, S1 = norm_film_coeffs(stats1, self.norm1, B, C, y[0, 0].numel(), gamma, beta, scale)
         if prefilm:   # training: the caller applies norm1's affine, then FiLM / MLP / skip under autograd
             return y, A1, S1
-        no_drop = isinstance(self.drop_path, nn.Identity) or not self.training
         if mlp is None and defer_affine and not hasattr(self, "outer_skip"):
             return y, A1, S1
         if fused_mlp:
             fc1, fc2 = mlp.fwd[0], mlp.fwd[2]
             # norm1 o FiLM folded into fc1; the coefficients are computed inside the folding kernel
             Wb, bias_b = fold_norm_affine(padded_weight(fc1.weight), stats1, self.norm1, y[0, 0].numel(), fc1.bias, gamma, beta, scale)
-            fuse_res = no_drop and not self.concat_skip and isinstance(getattr(self, "outer_skip", None), nn.Identity)
             if mlp1x1_supported(fc1.out_channels, fc2.out_channels, y.shape[2] * y.shape[3]):
                 # fc1 -> GELU -> fc2 (+ residual) in one kernel; the 512-channel hidden tile never leaves tensor memory
                 ostats = (torch.empty((B * fc2.out_channels, 2), dtype=torch.float64, device=x.device)
                           if (want_stats and fuse_res) else None)
-                out = mlp1x1(y, Wb, C, bias_b.contiguous(), padded_weight(fc2.weight), fc2.bias,
+                b2, mu_out = fc2.bias, None
+                if carry:
+                    mean_x = (stats0.view(B, C, 2)[:, :, 0] / HW).float()     # plane means of the stored input X
+                    b2 = (fc2.bias.float()[None, :] - mean_x if fc2.bias is not None else -mean_x).contiguous()
+                    mu_out = mean_x if mu is None else mu + mean_x
+                out = mlp1x1(y, Wb, C, bias_b.contiguous(), padded_weight(fc2.weight), b2,
                              add=residual.contiguous().float() if fuse_res else None, per_sample_w1=True, per_sample_b1=True,
-                             w1_rounded=True, stats=ostats)
+                             w1_rounded=True, stats=ostats, per_sample_b2=carry)
                 out = out if fuse_res else self._tail(out, residual)
+                if want_mu:
+                    return out, ostats, mu_out
                 return (out, ostats) if want_stats else out
             h = conv1x1(y, Wb, C, bias=bias_b.contiguous(), act_gelu=True, per_sample_w=True, per_sample_bias=True, w_rounded=True)
             out = conv1x1(h, padded_weight(fc2.weight), fc2.in_channels, bias=fc2.bias,
                           add=residual.contiguous().float() if fuse_res else None)
             out = out if fuse_res else self._tail(out, residual)
+            if want_mu:
+                return out, None, None
             return (out, None) if want_stats else out
         y = plane_affine(y, A1, S1)
         if mlp is not None:
             y = mlp(y)
         out = self._tail(y, residual)
+        if want_mu:
+            return out, None, None
         return (out, None) if want_stats else out
 
     def _unfused(self, x, gamma=None, beta=None, scale=1.0, film=None):
@@ -602,6 +633,7 @@ class FourierNeuralOperatorNet(nn.Module):
         """film: None or (gamma [B, film_layers, C], beta, scale, first_filmed_block_index)."""
         residual = x
         x, stats = self._encode_fused(x)     # stats: plane sums of x accumulated by the producing kernel (or None)
+        mu = None                            # per-plane offset carried beside the stored stream (tensor-core tier, see _fused)
         last = len(self.blocks) - 1
         for i, blk in enumerate(self.blocks):
             g = b = None
@@ -609,9 +641,9 @@ class FourierNeuralOperatorNet(nn.Module):
             if film is not None and i >= film[3]:
                 g, b, sc = film[0][:, i - film[3]], film[1][:, i - film[3]], film[2]
             if i == last:
-                y, A, S = blk._fused(x, g, b, sc, defer_affine=True, in_stats=stats)
+                y, A, S = blk._fused(x, g, b, sc, defer_affine=True, in_stats=stats, mu=mu, want_mu=True)
             else:
-                x, stats = blk._fused(x, g, b, sc, in_stats=stats, want_stats=True)
+                x, stats, mu = blk._fused(x, g, b, sc, in_stats=stats, want_stats=True, mu=mu, want_mu=True)
         return self._decode_fused(y, A, S, residual)
 
     @_lib.on_input_device

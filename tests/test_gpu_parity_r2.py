@@ -33,27 +33,50 @@ def _load(net, sd):
 
 
 # ------------------------------------------------------------------------------------------------ (a)
+def _oracle_filmed(sd32, train, x, cond, gy, film_layers, scale, dtype):
+    sd = {k: (v.detach().to(dtype) if v.is_floating_point() else v) for k, v in sd32.items()}
+    for k in train:
+        sd[k].requires_grad_(True)
+    tr = sfno_oracle.Transforms()
+    if dtype == torch.float64:
+        for t in (tr.trans_down, tr.trans):
+            t.weights = t.weights.double()
+        for t in (tr.itrans_up, tr.itrans):
+            t.pct = t.pct.double()
+    B = x.shape[0]
+    fm = sfno_oracle.film_head(cond.to(dtype), sd).reshape(B, 2, film_layers, 256)
+    y = sfno_oracle.sfno_forward(x.to(dtype), sd, tr, "non-linear", 12, film_mod=fm, film_layers=film_layers, scale=scale)
+    y.backward(gy.to(dtype))
+    return y.detach(), {k: sd[k].grad.clone() for k in train}
+
+
 @pytest.mark.parametrize("film_layers", [1, 12])
 def test_filmed_net_full_size_forward_backward_vs_oracle(film_layers):
+    """film_layers = 1 (the shipped configuration): the gradient reaches the FiLM head through decoder and
+    FiLM only -- smooth, compared at 1e-5.  film_layers = 12: it crosses 36 ComplexReLU layers.  A ReLU kink makes
+    d(loss)/d(theta) discontinuous in the pre-activation: two CORRECT fp32 evaluations whose forward activations differ
+    by 1e-6 flip the mask of a few of the 7.6 M real parts per layer, and every flip moves the gradient by that element's
+    whole contribution (tools/diag_relu_kink_gradients.py: the CUDA-core and the tensor-core engine BOTH sit at 6e-4 from
+    the oracle at 256 channels, 2e-6 at 64 channels where no mask happens to flip).  The reference's own fp32 path has
+    the same floor against its fp64 evaluation; the test measures that floor and requires the CUDA path to be no
+    further from the fp64 gradient than twice the oracle's own fp32 evaluation is -- and the forward at 1e-5."""
     B, scale = 2, 0.8
     torch.set_num_threads(os.cpu_count() or 1)
     sd = sfno_oracle.make_state_dict(filter_type="non-linear", seed=5, film_layers=film_layers)
     head = [k for k in sd if k.startswith("film_gen.") and sd[k].is_floating_point()]
     wkey = "blocks.11.filter_layer.filter.w.0"
     train = head + ([wkey] if film_layers == 12 else [])
-    for k in train:
-        sd[k].requires_grad_(True)
     g = torch.Generator().manual_seed(8)
     x = torch.randn(B, 73, NLAT, NLON, generator=g)
     cond = torch.randn(B, 512, generator=g)
     gy = torch.randn(B, 73, NLAT, NLON, generator=g)
-    tr = sfno_oracle.Transforms()
-    fm = sfno_oracle.film_head(cond, sd).reshape(B, 2, film_layers, 256)
-    want = sfno_oracle.sfno_forward(x, sd, tr, "non-linear", 12, film_mod=fm, film_layers=film_layers, scale=scale)
-    want.backward(gy)
-    want_grads = {k: sd[k].grad.clone() for k in train}
-    want = want.detach()
-    del fm
+    want, g32 = _oracle_filmed(sd, train, x, cond, gy, film_layers, scale, torch.float32)
+    floor = {k: 0.0 for k in train}
+    gref = g32
+    if film_layers == 12:
+        _, g64 = _oracle_filmed(sd, train, x, cond, gy, film_layers, scale, torch.float64)
+        floor = {k: rel_l2(g32[k], g64[k]) for k in train}
+        gref = g64
 
     cfg = _Cfg()
     cfg.film_layers, cfg.batch_size = film_layers, B
@@ -65,10 +88,15 @@ def test_filmed_net_full_size_forward_backward_vs_oracle(film_layers):
     got = net(x.cuda(), cond.cuda(), scale)
     got.backward(gy.cuda())
     assert rel_l2(got, want) < TOL_FP32, rel_l2(got, want)
-    errs = {k: rel_l2(dict(net.named_parameters())[k].grad, want_grads[k]) for k in train}
-    print("film_layers=%d gradient rel-L2:" % film_layers, errs)
-    bad = {k: v for k, v in errs.items() if not v < TOL_FP32}
+    params = dict(net.named_parameters())
+    errs = {k: rel_l2(params[k].grad, gref[k]) for k in train}
+    print("film_layers=%d gradient rel-L2 vs oracle:" % film_layers, errs)
+    print("film_layers=%d oracle fp32-vs-fp64 floor:" % film_layers, floor)
+    bad = {k: (v, floor[k]) for k, v in errs.items() if not v < max(TOL_FP32, 2.0 * floor[k])}
     assert not bad, bad
+    for k in train:   # direction: a flipped mask perturbs, it never rotates
+        a, b = params[k].grad.double().cpu().flatten(), gref[k].double().flatten()
+        assert float(torch.dot(a, b) / (a.norm() * b.norm())) > 1.0 - 1e-5
 
 
 # ------------------------------------------------------------------------------------------------ (b)
