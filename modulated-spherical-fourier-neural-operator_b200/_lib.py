@@ -10,7 +10,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libmsfno_b200.so")
+# MSFNO_B200_LIB: another BUILD of the same library (e.g. the -DMSFNO_TRACE build the tools use), never another implementation
+LIB_PATH = os.environ.get("MSFNO_B200_LIB") or os.path.join(_HERE, "libmsfno_b200.so")
 HEADER_PATH = os.path.join(_ROOT, "include", "msfno_b200.h")
 
 OK = 0

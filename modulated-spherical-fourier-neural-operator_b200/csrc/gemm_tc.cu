@@ -191,41 +191,49 @@ template <bool A_MN, bool B_MN>
 __device__ __forceinline__ void tc_producer(const TcParams& p, const GemmGroup& grp, const CUtensorMap& tmA, const CUtensorMap& tmB,
                                             const CUtensorMap& tmA2, const CUtensorMap& tmB2, uint8_t* tiles, int stage_bytes,
                                             int nstages, uint64_t* full, uint64_t* empty, int m0, int n0, int nkb1, int nkb) {
+  // (row, column) of the operands' first elements, computed ONCE: the 64-bit divisions cost the issuing thread ~500 clk
+  // each, and four of them per k-block made this single thread the slowest stage of the whole pipeline (measured: 1490 clk
+  // per k-block with every consumer starved, 8 CTAs on an idle GPU as much as 472)
   const long long a_off2 = blockIdx.y * p.sa2, b_off2 = blockIdx.y * p.sb2;
+  const int ac1 = (int)(grp.a_off % p.lda), ar1 = (int)(grp.a_off / p.lda);
+  const int bc1 = (int)(grp.b_off % p.ldb);
+  const long long br1 = grp.b_off / p.ldb;
+  const int ac2 = nkb > nkb1 ? (int)(a_off2 % p.lda2) : 0, ar2 = nkb > nkb1 ? (int)(a_off2 / p.lda2) : 0;
+  const int bc2 = nkb > nkb1 ? (int)(b_off2 % p.ldb2) : 0, br2 = nkb > nkb1 ? (int)(b_off2 / p.ldb2) : 0;
+  const bool b3d = p.b_group_rows > 0;
+  const int tab = b3d ? (int)(br1 / p.b_group_rows) : 0;
+  const int br1_in = b3d ? (int)(br1 % p.b_group_rows) : (int)br1;
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb % nstages;
     const uint32_t ph = (uint32_t)((kb / nstages) & 1);
     const bool second = kb >= nkb1;
     const int kk = (second ? kb - nkb1 : kb) * TC_BK;
-    const long long aoff = second ? a_off2 : grp.a_off, boff = second ? b_off2 : grp.b_off;
-    const long long lda = second ? p.lda2 : p.lda, ldb = second ? p.ldb2 : p.ldb;
+    const int ac = second ? ac2 : ac1, ar = second ? ar2 : ar1, bc = second ? bc2 : bc1, br = second ? br2 : br1_in;
     const CUtensorMap* ma = second ? &tmA2 : &tmA;
     const CUtensorMap* mb = second ? &tmB2 : &tmB;
     mbar_wait_bounded(&empty[s], ph ^ 1u);
+#ifdef MSFNO_TRACE
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && kb >= 8 && kb < 12) p.trace[16 + kb - 8] = clock64();   // TMA issue
+#endif
     mbar_arrive_expect_tx(&full[s], TC_HI_BYTES);
     uint8_t* sa = tiles + s * stage_bytes;
     if (!A_MN) {
-      tma_load_2d(sa, ma, &full[s], (int)(aoff % lda) + kk, (int)(aoff / lda) + m0);
+      tma_load_2d(sa, ma, &full[s], ac + kk, ar + m0);
     } else {
       // [K][M] operand: four boxes of 32 (m) x 32 (k); box j holds m in [m0 + 32 j, +32)
-      const int mcol = (int)(aoff % lda) + m0, krow = (int)(aoff / lda) + kk;
 #pragma unroll
-      for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d(sa + j * (TC_BK * 128), ma, &full[s], mcol + 32 * j, krow);
+      for (int j = 0; j < TC_BM / 32; ++j) tma_load_2d(sa + j * (TC_BK * 128), ma, &full[s], ac + m0 + 32 * j, ar + kk);
     }
     if (!B_MN) {
-      tma_load_2d(sa + TC_A_BYTES, mb, &full[s], (int)(boff % ldb) + kk, (int)(boff / ldb) + n0);
+      tma_load_2d(sa + TC_A_BYTES, mb, &full[s], bc + kk, br + n0);
     } else {
       // [K][N] operand: four boxes of 32 (n) x 32 (k); box j holds n in [n0 + 32 j, +32)
-      const int ncol = (int)(boff % ldb) + n0;
-      const long long brow = boff / ldb;
-      if (p.b_group_rows > 0 && !second) {
-        const int tab = (int)(brow / p.b_group_rows), krow = (int)(brow % p.b_group_rows) + kk;
+      if (b3d && !second) {
 #pragma unroll
-        for (int j = 0; j < TC_BN / 32; ++j) tma_load_3d(sa + TC_A_BYTES + j * (TC_BK * 128), mb, &full[s], ncol + 32 * j, krow, tab);
+        for (int j = 0; j < TC_BN / 32; ++j) tma_load_3d(sa + TC_A_BYTES + j * (TC_BK * 128), mb, &full[s], bc + n0 + 32 * j, br + kk, tab);
       } else {
-        const int krow = (int)brow + kk;
 #pragma unroll
-        for (int j = 0; j < TC_BN / 32; ++j) tma_load_2d(sa + TC_A_BYTES + j * (TC_BK * 128), mb, &full[s], ncol + 32 * j, krow);
+        for (int j = 0; j < TC_BN / 32; ++j) tma_load_2d(sa + TC_A_BYTES + j * (TC_BK * 128), mb, &full[s], bc + n0 + 32 * j, br + kk);
       }
     }
   }
@@ -335,9 +343,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // The tensor core adds into its TMEM accumulator with truncation, not round-to-nearest: measured on B200, the relative
 // error of a K = 1024 product accumulated in TMEM is 7.6e-6 (biased towards zero, growing with K) against 5.8e-7 for
 // FFMA.  So every 32-wide k-block is multiplied into a FRESH accumulator (accumulate = 0 on its first MMA; two TMEM
-// buffers alternate) -- the eight small-term MMAs first, then the four hi*hi ones -- and eight accumulator warps drain
-// it with tcgen05.ld into fp32 registers, adding with round-to-nearest while the tensor core works on the next k-block.
-// 16 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4-7 = converters, 8-15 = accumulators / epilogue.
+// buffers alternate) and eight accumulator warps drain it with tcgen05.ld into fp32 registers, adding with
+// round-to-nearest while the tensor core works on the next one.  Draining is the expensive part (tensor memory reads at
+// 64 B/clk: 64 KB per 128 x 128 buffer = 1 024 clk, more than the 768 clk of a k-block's twelve MMAs), so
+//   * the small terms lo(a) hi(b) + hi(a) lo(b) -- 2^-11 of the result, their truncation error is irrelevant -- go to a
+//     third accumulator S that stays in tensor memory for the whole K loop and is drained once, and
+//   * only the hi(a) hi(b) products go to the alternating buffers, TC3_GROUP k-blocks (16 MMAs = 16 truncating adds, about
+//     3e-7) per drain.
+// 16 warps: 0 = TMA producer, 1 and 3 = MMA issuers, 2 = TMEM allocator, 4-7 = converters, 8-15 = accumulators / epilogue.
 //
 // Converters (thread = tile row): a K-major A tile is read once from shared memory (one swizzled 16-byte chunk per lane
 // and access: conflict-free), split and written to TENSOR MEMORY as the A operand (hi and lo, 32 columns each per
@@ -349,8 +362,10 @@ template <bool A_MN> struct Tc3Cfg {
   static constexpr int STAGE_BYTES = TC_HI_BYTES + TC_B_BYTES + (A_TMEM ? 0 : TC_A_BYTES);   // A, B, lo(B) [, lo(A)]
   static constexpr int STAGES = A_TMEM ? 4 : 3;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = A_TMEM ? 512 : 256;    // 2 accumulators of 128 [+ 4 stages x (32 hi + 32 lo) of A]
+  static constexpr int NH = A_TMEM ? 1 : 2;   // hi * hi accumulators (K-major A: tensor memory holds the A operand instead)
+  static constexpr int TMEM_COLS = 512;       // H, S + 4 stages x (32 hi + 32 lo) columns of A   or   H0, H1, S
 };
+static constexpr int TC3_GROUP = 4;        // k-blocks of hi * hi products per drain of an H buffer
 static constexpr int TC3_THREADS = 512;
 
 #define MSFNO_TC_ST32(taddr, r)                                                                                          \
@@ -411,16 +426,18 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   uint64_t* conv = bars + 2 * NST;       // the lo() tiles (and the TMEM copy of A) of the stage are written
   uint64_t* acc_full = bars + 3 * NST;   // [2] the k-block product in TMEM buffer b is complete
   uint64_t* acc_empty = acc_full + 2;    // [2] the accumulator warps have read TMEM buffer b
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* s_full = acc_empty + 2;      // the small-term accumulator S is complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(s_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb1 = (grp.K + TC_BK - 1) / TC_BK;
   const int nkb = nkb1 + (p.K2 + TC_BK - 1) / TC_BK;
 
   if (warp == 0 && lane == 0) {
+    mbar_init(s_full, 1);
     for (int s = 0; s < NST; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], 2);   // one commit per issuing thread
       mbar_init(&conv[s], 12);   // one arrival per A-converter warp (4) and per accumulator warp (8, they make lo(B))
     }
     for (int b = 0; b < 2; ++b) {
@@ -437,7 +454,9 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_a = tmem_base + 256u;   // A operand: stage s at columns 256 + 64 s (hi) and + 32 (lo)
+  constexpr int NH = Cfg::NH;
+  const uint32_t tmem_s = tmem_base + (uint32_t)(NH * TC_BN);   // S: the small terms of the whole K loop
+  const uint32_t tmem_a = tmem_base + 256u;   // K-major A: stage s at columns 256 + 64 s (hi) and + 32 (lo)
   pdl_wait();
 
   float acc[64];   // accumulator warps: rows q*32 + lane, columns chalf*64 .. +64 of the tile
@@ -447,73 +466,106 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (nkb > 0) {
     if (warp == 0 && lane == 0) {
       tc_producer<A_MN, B_MN>(p, grp, tmA, tmB, tmA2, tmB2, tiles, STAGE, NST, full, empty, m0, n0, nkb1, nkb);
-    } else if (warp == 1 && lane == 0) {
-      // ---------------- MMA issuer ----------------
+    } else if ((warp == 1 || warp == 3) && lane == 0) {
+      // ---------------- MMA issuers ----------------
+      // TWO issuing threads with disjoint accumulators: warp 1 issues the hi * hi products (into H[b]), warp 3 the small
+      // terms (into S).  A single issuer is nearly synchronous with the tensor pipe (its twelve MMAs of a k-block return
+      // after ~880 clk, when they have all but completed) and every mbarrier wait costs it 100-200 clk even when the phase
+      // completed long ago -- three waits per k-block left the pipe idle 40 % of the time (per-k-block timeline,
+      // profiles/r02_x3_timeline_*.txt).  Now each thread waits once per k-block (conv[s] implies full[s]), and the
+      // other thread's MMAs run under that wait.  Both commit on empty[s] (count 2).
+      const bool issue_h = warp == 1;
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 #ifdef MSFNO_TRACE
-      long long tr_full = 0, tr_conv = 0, tr_acc = 0, tr_first = 0, tr_last = 0, tr_issue = 0;
+      long long tr_conv = 0, tr_acc = 0, tr_first = 0, tr_last = 0, tr_issue = 0;
 #endif
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % NST, b = kb & 1;
+        const int s = kb % NST, g = kb / TC3_GROUP, b = g % NH;
+        const bool first = kb % TC3_GROUP == 0, last = kb % TC3_GROUP == TC3_GROUP - 1 || kb == nkb - 1;
 #ifdef MSFNO_TRACE
         const long long w0 = clock64();
 #endif
-        mbar_wait_bounded(&full[s], (uint32_t)((kb / NST) & 1));
-#ifdef MSFNO_TRACE
-        const long long w1 = clock64();
-#endif
-        mbar_wait_bounded(&conv[s], (uint32_t)((kb / NST) & 1));
+        mbar_wait_bounded(&conv[s], (uint32_t)((kb / NST) & 1));   // every converter saw full[s] before it arrived here
 #ifdef MSFNO_TRACE
         const long long w2 = clock64();
 #endif
-        mbar_wait_bounded(&acc_empty[b], (uint32_t)(((kb >> 1) & 1) ^ 1));
+        if (issue_h && first) mbar_wait_bounded(&acc_empty[b], (uint32_t)(((g / NH) & 1) ^ 1));
 #ifdef MSFNO_TRACE
         const long long w3 = clock64();
-        tr_full += w1 - w0; tr_conv += w2 - w1; tr_acc += w3 - w2;
+        tr_conv += w2 - w0; tr_acc += w3 - w2;
         if (kb == 0) tr_first = w3;
         tr_last = w3;
 #endif
         tc_fence_after();
         const uint32_t sa = base + s * STAGE, sb = sa + TC_A_BYTES;
-        const uint32_t d = tmem_base + (uint32_t)(b * TC_BN);
         const uint32_t ta = tmem_a + (uint32_t)(s * 64);
-        // small terms first (they add up among themselves at 2^-11 of the magnitude), then hi * hi
+        if (issue_h) {
+          const uint32_t d = tmem_base + (uint32_t)(b * TC_BN);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          if (A_TMEM) tc_mma_tf32_ts(d, ta + 32u + 8u * k, tc_desc<B_MN>(sb, k), idesc, k ? 1u : 0u);          // lo(a) hi(b)
-          else tc_mma_tf32(d, tc_desc<A_MN>(sa + LO_A, k), tc_desc<B_MN>(sb, k), idesc, k ? 1u : 0u);
-        }
+          for (int k = 0; k < TC_BK / 8; ++k) {   // hi(a) hi(b): the tensor core truncates the raw fp32 operands itself
+            if (A_TMEM) tc_mma_tf32_ts(d, ta + 8u * k, tc_desc<B_MN>(sb, k), idesc, (first && k == 0) ? 0u : 1u);
+            else tc_mma_tf32(d, tc_desc<A_MN>(sa, k), tc_desc<B_MN>(sb, k), idesc, (first && k == 0) ? 0u : 1u);
+          }
+          tc_commit(&empty[s]);                 // (with the other issuer's commit) the stage may be refilled
+          if (last) tc_commit(&acc_full[b]);    // the group's hi * hi product is complete
+        } else {
+          // small terms: they add up among themselves at 2^-11 of the magnitude, S stays in tensor memory for the whole K loop
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          if (A_TMEM) tc_mma_tf32_ts(d, ta + 8u * k, tc_desc<B_MN>(sa + LO_B, k), idesc, 1u);                  // hi(a) lo(b)
-          else tc_mma_tf32(d, tc_desc<A_MN>(sa, k), tc_desc<B_MN>(sa + LO_B, k), idesc, 1u);
-        }
+          for (int k = 0; k < TC_BK / 8; ++k) {   // lo(a) hi(b): lo(A) from tensor memory (K-major A) or shared memory
+            if (A_TMEM) tc_mma_tf32_ts(tmem_s, ta + 32u + 8u * k, tc_desc<B_MN>(sb, k), idesc, (kb | k) ? 1u : 0u);
+            else tc_mma_tf32(tmem_s, tc_desc<A_MN>(sa + LO_A, k), tc_desc<B_MN>(sb, k), idesc, (kb | k) ? 1u : 0u);
+          }
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          if (A_TMEM) tc_mma_tf32_ts(d, ta + 8u * k, tc_desc<B_MN>(sb, k), idesc, 1u);                         // hi(a) hi(b)
-          else tc_mma_tf32(d, tc_desc<A_MN>(sa, k), tc_desc<B_MN>(sb, k), idesc, 1u);
+          for (int k = 0; k < TC_BK / 8; ++k) {   // hi(a) lo(b)
+            if (A_TMEM) tc_mma_tf32_ts(tmem_s, ta + 8u * k, tc_desc<B_MN>(sa + LO_B, k), idesc, 1u);
+            else tc_mma_tf32(tmem_s, tc_desc<A_MN>(sa, k), tc_desc<B_MN>(sa + LO_B, k), idesc, 1u);
+          }
+          tc_commit(&empty[s]);
+          if (kb == nkb - 1) tc_commit(s_full);   // S is complete
         }
-        tc_commit(&empty[s]);       // the stage (and its TMEM copy of A) may be refilled
-        tc_commit(&acc_full[b]);    // the k-block product is complete
 #ifdef MSFNO_TRACE
-        tr_issue += clock64() - w3;
+        const long long w4 = clock64();
+        tr_issue += w4 - w3;
+        if (issue_h && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && kb >= 8 && kb < 12) {
+          long long* e = p.trace + 32 + (kb - 8) * 12;
+          e[0] = w0; e[1] = w0; e[2] = w2; e[3] = w3; e[4] = w4;
+        }
+        if (!issue_h && p.trace && blockIdx.x == 0 && blockIdx.y == 0 && kb >= 8 && kb < 12) {
+          long long* e = p.trace + 32 + (kb - 8) * 12;
+          e[10] = w0; e[11] = w4;
+        }
 #endif
       }
 #ifdef MSFNO_TRACE
-      if (p.trace && blockIdx.x == 0 && blockIdx.y == 0) {
-        p.trace[0] = tr_full; p.trace[1] = tr_conv; p.trace[2] = tr_acc; p.trace[3] = tr_first; p.trace[4] = tr_last; p.trace[8] = tr_issue;
+      if (issue_h && p.trace && blockIdx.x == 0 && blockIdx.y == 0) {
+        p.trace[0] = 0; p.trace[1] = tr_conv; p.trace[2] = tr_acc; p.trace[3] = tr_first; p.trace[4] = tr_last; p.trace[8] = tr_issue;
       }
 #endif
     } else if (warp >= 4 && warp < 8) {
       // ---------------- A converters (thread = tile row of A = TMEM lane: warp 4 + q owns lane quarter q) ----------------
       const int t = threadIdx.x - 128;
+#ifdef MSFNO_TRACE
+      long long cv_full = 0, cv_slot = 0, cv_work = 0;
+#endif
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % NST;
+#ifdef MSFNO_TRACE
+        const long long c0 = clock64();
+#endif
         mbar_wait_bounded(&full[s], (uint32_t)((kb / NST) & 1));
+#ifdef MSFNO_TRACE
+        const long long c1 = clock64();
+        cv_full += c1 - c0;
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128 && kb >= 8 && kb < 12) p.trace[20 + kb - 8] = c1;   // landed
+#endif
         uint8_t* st = tiles + s * STAGE;
         if (A_TMEM) {
-          // row t of the K-major A tile: 128 bytes, its 16-byte chunk c stored at chunk position c ^ (t % 8)
+          // row t of the K-major A tile: 128 bytes, its 16-byte chunk c stored at chunk position c ^ (t % 8).  Both halves go
+          // to tensor memory (slot = stage: free whenever the stage is), so every MMA reads only B from shared memory: with
+          // 4-byte operands an MMA with both operands in shared memory reads 8 KB in its 64 clk -- all of the 128 B/clk
+          // port (measured: 1 300 clk per k-block with hi(A) left in shared memory, and writing lo(A) back to shared memory
+          // costs the converter ~1 100 clk per k-block, half of it the generic -> async proxy fence).
           uint32_t hi[32], lo[32];
           const uint8_t* rowp = st + t * 128;
 #pragma unroll
@@ -535,32 +587,58 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv[s]);
+#ifdef MSFNO_TRACE
+        const long long c3 = clock64();
+        cv_work += c3 - c1;
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128 && kb >= 8 && kb < 12) {
+          long long* e = p.trace + 32 + (kb - 8) * 12;
+          e[5] = c1; e[6] = c3;
+        }
+#endif
       }
+#ifdef MSFNO_TRACE
+      if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 128) { p.trace[9] = cv_full; p.trace[10] = cv_slot; p.trace[11] = cv_work; }
+#endif
     } else if (warp >= 8) {
       // ---------------- accumulators: acc += TMEM buffer (round-to-nearest adds on the CUDA cores) ----------------
-      // They also make lo(B) in shared memory, two k-blocks ahead of the product they drain: the A converters alone
+      // They also make lo(B) in shared memory, AHEAD k-blocks ahead of the product they drain: the A converters alone
       // (one warp per scheduler, a serial chain of shared loads, ALU, tensor-memory stores and fences per k-block) were
       // the slowest stage of the pipeline.
       const int q = warp & 3, chalf = (warp - 8) >> 2;
       const int t = threadIdx.x - 256;
       const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+#ifdef MSFNO_TRACE
+      long long ac_full = 0, ac_conv = 0, ac_wait = 0, ac_drain = 0;
+#endif
       auto convert_b = [&](int kb) {
         const int s = kb % NST;
+#ifdef MSFNO_TRACE
+        const long long q0 = clock64();
+#endif
         mbar_wait_bounded(&full[s], (uint32_t)((kb / NST) & 1));
+#ifdef MSFNO_TRACE
+        const long long q1 = clock64();
+        ac_full += q1 - q0;
+#endif
         uint8_t* st = tiles + s * STAGE;
         convert_stage_lo(st + TC_A_BYTES, st + LO_B, TC_B_BYTES, t, 256);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv[s]);
+#ifdef MSFNO_TRACE
+        const long long q4 = clock64();
+        ac_conv += q4 - q1;
+        if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 256 && kb >= 8 && kb < 12) {
+          long long* e = p.trace + 32 + (kb - 8) * 12;
+          e[7] = q0; e[8] = q1; e[9] = q4;
+        }
+#endif
       };
-      convert_b(0);
-      if (nkb > 1) convert_b(1);
-      for (int kb = 0; kb < nkb; ++kb) {
-        if (kb + 2 < nkb) convert_b(kb + 2);
-        const int b = kb & 1;
-        mbar_wait_bounded(&acc_full[b], (uint32_t)((kb >> 1) & 1));
-        tc_fence_after();
-        const uint32_t src = tmem_base + lane_off + (uint32_t)(b * TC_BN + chalf * 64);
+      constexpr int AHEAD = NST - 1;   // lo(B) is made as soon as its stage lands: AHEAD k-blocks before its product is needed
+#pragma unroll
+      for (int j = 0; j < AHEAD; ++j)
+        if (j < nkb) convert_b(j);
+      auto drain = [&](uint32_t src, uint64_t* release) {
         uint32_t r[32];
         MSFNO_TC_LD32(r, src);
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
@@ -569,10 +647,40 @@ gemm_tc3_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         MSFNO_TC_LD32(r, src + 32u);
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
         tc_fence_before();
-        if (lane == 0) mbar_arrive(&acc_empty[b]);   // the tensor core may overwrite the buffer
+        if (release && lane == 0) mbar_arrive(release);   // the tensor core may overwrite the buffer
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[32 + j] += __uint_as_float(r[j]);
+      };
+      for (int kb = 0; kb < nkb; ++kb) {
+        if (kb % TC3_GROUP != TC3_GROUP - 1 && kb != nkb - 1) {
+          if (kb + AHEAD < nkb) convert_b(kb + AHEAD);
+          continue;
+        }
+        // group end: the drain first -- the hi * hi issuer waits for it, and the stage of k-block kb + AHEAD can only
+        // be refilled once the MMAs of k-block kb - 1 have completed, so that conversion would block here for a TMA
+        // round trip (measured: acc_empty 1 850 clk late)
+        const int g = kb / TC3_GROUP, b = g % NH;
+#ifdef MSFNO_TRACE
+        const long long q2 = clock64();
+#endif
+        mbar_wait_bounded(&acc_full[b], (uint32_t)((g / NH) & 1));
+#ifdef MSFNO_TRACE
+        const long long q3 = clock64();
+        ac_wait += q3 - q2;
+#endif
+        tc_fence_after();
+        drain(tmem_base + lane_off + (uint32_t)(b * TC_BN + chalf * 64), &acc_empty[b]);
+#ifdef MSFNO_TRACE
+        ac_drain += clock64() - q3;
+#endif
+        if (kb + AHEAD < nkb) convert_b(kb + AHEAD);
       }
+#ifdef MSFNO_TRACE
+      if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 256) { p.trace[12] = ac_full; p.trace[13] = ac_conv; p.trace[14] = ac_wait; p.trace[15] = ac_drain; }
+#endif
+      mbar_wait_bounded(s_full, 0u);
+      tc_fence_after();
+      drain(tmem_s + lane_off + (uint32_t)(chalf * 64), nullptr);
     }
   }
 
@@ -703,6 +811,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (nkb > 0) {
     if (warp == 0 && lane == 0) {
       // ---------------- TMA producer (both CTAs) ----------------
+      const int ac = (int)(grp.a_off % p.lda), ar = (int)(grp.a_off / p.lda) + m0;
+      const int bc = (int)(grp.b_off % p.ldb), br = (int)(grp.b_off / p.ldb) + n0 + (int)rank * TC_BM;
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % TC_STAGES;
         const uint32_t ph = (uint32_t)((kb / TC_STAGES) & 1);
@@ -710,9 +820,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait_bounded(&empty[s], ph ^ 1u);
         if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * TC2_STAGE_BYTES);   // bytes of both CTAs
         uint8_t* sa = tiles + s * TC2_STAGE_BYTES;
-        tma_load_2d_pair(sa, &tmA, &full[s], (int)(grp.a_off % p.lda) + kk, (int)(grp.a_off / p.lda) + m0);
-        tma_load_2d_pair(sa + TC_A_BYTES, &tmB, &full[s], (int)(grp.b_off % p.ldb) + kk,
-                         (int)(grp.b_off / p.ldb) + n0 + (int)rank * TC_BM);
+        tma_load_2d_pair(sa, &tmA, &full[s], ac + kk, ar);
+        tma_load_2d_pair(sa + TC_A_BYTES, &tmB, &full[s], bc + kk, br);
       }
     } else if (warp == 1 && lane == 0 && rank == 0) {
       // ---------------- MMA issuer (leader CTA only) ----------------
@@ -836,8 +945,8 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     dim3 grid(p.tilesM * p.tilesN, g.ngroups);
 #ifdef MSFNO_TRACE
     static long long* d_trace = nullptr;
-    if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 16 * sizeof(long long)));
-    MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 16 * sizeof(long long), st));
+    if (!d_trace) MSFNO_CUDA_OK(cudaMalloc(&d_trace, 96 * sizeof(long long)));
+    MSFNO_CUDA_OK(cudaMemsetAsync(d_trace, 0, 96 * sizeof(long long), st));
     p.trace = d_trace;
 #endif
     if (amn && bmn) MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<true, true>, grid, dim3(TC3_THREADS), Tc3Cfg<true>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
@@ -846,12 +955,19 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     else MSFNO_CUDA_OK(launch_pdl(gemm_tc3_kernel<false, false>, grid, dim3(TC3_THREADS), Tc3Cfg<false>::SMEM_BYTES, st, tmA, tmB, tmA2, tmB2, p));
 #ifdef MSFNO_TRACE
     {
-      long long h[16];
+      long long h[96];
       MSFNO_CUDA_OK(cudaStreamSynchronize(st));
       MSFNO_CUDA_OK(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
       fprintf(stderr, "gemm_tc3 trace CTA(0,0) maxM=%d maxN=%d: issuer waits full %lld conv %lld acc_empty %lld | first MMA at %lld, last issue at %lld, "
-                      "mainloop done %lld, cta done %lld (clk since CTA start); issue blocks %lld\n", g.maxM, g.maxN, h[0], h[1], h[2], h[3] - h[7], h[4] - h[7],
-              h[5] - h[7], h[6] - h[7], h[8]);
+                      "mainloop done %lld, cta done %lld (clk since CTA start); issue blocks %lld | A converter: waits full %lld slot %lld, busy %lld | accumulators: "
+                      "waits full %lld, lo(B) %lld, waits product %lld, drains %lld | TMA issue -> landed, k-blocks 8..11: %lld %lld %lld %lld clk, issued at %lld %lld %lld %lld\n", g.maxM, g.maxN, h[0], h[1], h[2], h[3] - h[7], h[4] - h[7],
+              h[5] - h[7], h[6] - h[7], h[8], h[9], h[10], h[11], h[12], h[13], h[14], h[15], h[20] - h[16], h[21] - h[17], h[22] - h[18], h[23] - h[19], h[16] - h[7], h[17] - h[7], h[18] - h[7], h[19] - h[7]);
+      for (int j = 0; j < 4; ++j) {
+        const long long* e = h + 32 + 12 * j;
+        fprintf(stderr, "  k-block %d: TMA issued %lld | issuer arrives %lld, full %lld, conv %lld, acc %lld, issued %lld | S issuer arrives %lld issued %lld | A conv: landed %lld done %lld | lo(B) (warp 8): "
+                        "starts waiting %lld landed %lld done %lld\n", 8 + j, h[16 + j] - h[7], e[0] - h[7], e[1] - h[7], e[2] - h[7], e[3] - h[7], e[4] - h[7], e[10] - h[7], e[11] - h[7], e[5] - h[7],
+                e[6] - h[7], e[7] - h[7], e[8] - h[7], e[9] - h[7]);
+      }
     }
 #endif
     count_launch();

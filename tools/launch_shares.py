@@ -1,7 +1,9 @@
 """Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv`) of bench.py: per-kernel share of ONE forward step.
 
 The step boundary is found from the launch list itself: the (kernel name, grid) sequence of a forward repeats, so the
-smallest period L with rows[-L:] == rows[-2L:-L] is one step -- whatever the precision tier or workload launches.
+smallest period L with rows[-L:] == rows[-2L:-L] whose window holds EVERY distinct launch of the list's second half is
+one step -- whatever the precision tier or workload launches (the ten identical inner blocks of a net repeat with a
+shorter period, but their window lacks the full-grid launches of blocks 0 / 11 and of the encoder / decoder).
 usage: python tools/launch_shares.py profiles/<launch list>.csv [--json]"""
 import collections
 import csv
@@ -27,8 +29,9 @@ def short(name):
 
 def period(keys, lo=8):
     n = len(keys)
+    everything = set(keys[n // 2:])
     for L in range(lo, n // 2 + 1):
-        if keys[n - L:] == keys[n - 2 * L:n - L]:
+        if keys[n - L:] == keys[n - 2 * L:n - L] and set(keys[n - L:]) == everything:
             return L
     return None
 
