@@ -1,5 +1,5 @@
 // Four-step longitude FFT kernels (forward truncated r2c, inverse zero-padded c2r) for the production sizes:
-//   nlon = 1440 (H = 720 = 24 x 30), nlon = 240 (H = 120 = 15 x 8, 4 rows per warp), nlon = 2880 (H = 1440 = 36 x 40).
+//   nlon = 1440 (H = 720 = 24 x 30), nlon = 240 (H = 120 = 15 x 8, 4 rows per warp), nlon = 2880 (H = 1440 = 48 x 30).
 // Same interface, data layout and fused prologue/epilogue as the generic Stockham kernels in fft.cu (which remain
 // the fallback for every other size); the difference is the arithmetic core: two rounds of fully unrolled
 // in-register DFTs (fft_reg.cuh) with compile-time twiddles, one shared-memory exchange in between, no integer
@@ -13,12 +13,15 @@
 
 namespace msfno {
 
-static constexpr int ROWS_PER_TILE2 = 32;
-static constexpr int OST2 = 33;
+// RT rows (latitudes) per CTA tile: 32 (one 128-byte segment of the lat-contiguous intermediate per order and re/im) for
+// the production grids.  The 2880-point rows of the 0.125 degree grid need 23 KB of shared memory per warp and a
+// [2 mlim][RT + 1] staging tile: with RT = 32, twiddles in shared memory and a double-buffered row only TWO warps fit in
+// an SM (measured: 9.6 ms per 1441 x 2880 x 256 transform, 0.5 TB/s) -- RT = 16, TWG (the w_H twiddles read through L1
+// instead of a shared copy) and a single row buffer per warp that also holds the compact spectrum (!DB) let eight warps in.
 
 // NZ2 > 0: mlim <= NZ2 * P1, so only output columns k2 in [0, NZ2) and [P2 - NZ2, P2) of the second step are ever
 // needed by the real split -- a compile-time set: the other outputs of the in-register DFT are dead code.
-template <int P1, int P2, int RW, int NZ2>
+template <int P1, int P2, int RW, int NZ2, int RT, bool TWG, bool DB>
 __global__ void __launch_bounds__(256, 1)
 rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __restrict__ g_tw,
               const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ in_scale,
@@ -29,26 +32,31 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bc = blockIdx.y;
   const int b = bc / C, c = bc - b * C;
-  const int k0 = blockIdx.x * ROWS_PER_TILE2;
+  constexpr int OST2 = RT + 1;
+  const int k0 = blockIdx.x * RT;
   constexpr int KEEP_STATIC = NZ2 * P1;                 // bins [0, KEEP) and [H - KEEP, H) are stored
   const int keep = (NZ2 > 0) ? KEEP_STATIC : mlim;
   const int XS = xs_size(H, keep);
 
-  cf* tw = reinterpret_cast<cf*>(smem_raw);
-  cf* tw2 = tw + H;
+  cf* tw_s = reinterpret_cast<cf*>(smem_raw);
+  const cf* tw = TWG ? g_tw : tw_s;
+  cf* tw2 = tw_s + (TWG ? 0 : H);
   float* ostage = reinterpret_cast<float*>(tw2 + (mlim + 1));
   size_t off = (size_t)(reinterpret_cast<unsigned char*>(ostage + 2 * mlim * OST2) - smem_raw);
   off = (off + 15) & ~(size_t)15;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + off);
   off += sizeof(uint64_t) * 2 * nw;
   off = (off + 127) & ~(size_t)127;
-  const size_t per_warp = sizeof(cf) * ((size_t)2 * RW * H + (size_t)RW * P1 * WP + (size_t)RW * XS);
+  constexpr int NRAW = DB ? 2 : 1;
+  // !DB: the compact spectrum store xs re-uses the row buffer (dead once step 1 has read it; XS <= H)
+  const size_t per_warp = sizeof(cf) * ((size_t)NRAW * RW * H + (size_t)RW * P1 * WP + (DB ? (size_t)RW * XS : 0));
   unsigned char* wbase = smem_raw + off + (size_t)warp * ((per_warp + 127) & ~(size_t)127);
-  cf* raw[2] = {reinterpret_cast<cf*>(wbase), reinterpret_cast<cf*>(wbase) + RW * H};
-  cf* work = raw[1] + RW * H;
-  cf* xs = work + RW * P1 * WP;
+  cf* raw[2] = {reinterpret_cast<cf*>(wbase), reinterpret_cast<cf*>(wbase) + (DB ? RW * H : 0)};
+  cf* work = reinterpret_cast<cf*>(wbase) + NRAW * RW * H;
+  cf* xs = DB ? work + RW * P1 * WP : raw[0];
 
-  for (int i = threadIdx.x; i < H; i += blockDim.x) tw[i] = g_tw[i];
+  if (!TWG)
+    for (int i = threadIdx.x; i < H; i += blockDim.x) tw_s[i] = g_tw[i];
   for (int i = threadIdx.x; i <= mlim; i += blockDim.x) tw2[i] = g_tw2[i];
   if (lane == 0) {
     mbar_init(&bars[2 * warp + 0], 1);
@@ -60,7 +68,7 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
   const float sc_in = in_scale ? in_scale[bc] : 1.0f;
   const float sh_in = in_shift ? in_shift[bc] : 0.0f;
   const float* xbase = x + ((size_t)bc * nlat) * NLON;
-  constexpr int NGROUPS = ROWS_PER_TILE2 / RW;
+  constexpr int NGROUPS = RT / RW;
   const int iters = (NGROUPS + nw - 1) / nw;
 
   auto rows_valid = [&](int it) -> int {  // valid rows of the row group this warp handles in iteration `it`
@@ -84,7 +92,7 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
   for (int it = 0; it < iters; ++it) {
     if (nv <= 0) break;  // warp-uniform; groups are ascending so later ones are invalid too
     const int nv_next = (it + 1 < iters) ? rows_valid(it + 1) : 0;
-    if (nv_next > 0) issue_load(it + 1, nv_next);
+    if (DB && nv_next > 0) issue_load(it + 1, nv_next);
     mbar_wait(&bars[2 * warp + (it & 1)], (uint32_t)((it >> 1) & 1));
     const cf* in = raw[it & 1];
     const int g = warp + it * nw;
@@ -131,13 +139,15 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
     }
     fence_proxy_async();
     __syncwarp();
+    if (!DB && nv_next > 0) issue_load(it + 1, nv_next);   // single row buffer (also the spectrum store): free only now
     nv = nv_next;
   }
   __syncthreads();
 
-  const int nvalid = min(ROWS_PER_TILE2, nlat - k0);
+  const int nvalid = min(RT, nlat - k0);
   for (int seg = warp; seg < 2 * mlim; seg += nw) {
     const int m = seg >> 1, ri = seg & 1;
+    if (lane >= RT) continue;   // (RT < 32: half-segment stores)
     float v = (lane < nvalid) ? ostage[seg * OST2 + lane] : 0.0f;
     if (round_tf32) { uint32_t rr; asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(rr) : "f"(v)); v = __uint_as_float(rr); }
     Xt[(((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane] = v;
@@ -145,7 +155,7 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
 }
 
 // NZ > 0: only the first and last NZ rows of the P1 x P2 spectrum matrix can be non-zero (mlim <= NZ * P2).
-template <int P1, int P2, int RW, int NZ>
+template <int P1, int P2, int RW, int NZ, int RT, bool TWG>
 __global__ void __launch_bounds__(256, 1)
 irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __restrict__ g_tw,
                const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ skip,
@@ -157,10 +167,12 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bc = blockIdx.y;
   const int b = bc / C, c = bc - b * C;
-  const int k0 = blockIdx.x * ROWS_PER_TILE2;
+  constexpr int OST2 = RT + 1;
+  const int k0 = blockIdx.x * RT;
 
-  cf* tw = reinterpret_cast<cf*>(smem_raw);
-  cf* tw2 = tw + H;
+  cf* tw_s = reinterpret_cast<cf*>(smem_raw);
+  const cf* tw = TWG ? g_tw : tw_s;
+  cf* tw2 = tw_s + (TWG ? 0 : H);
   float* istage = reinterpret_cast<float*>(tw2 + (mlim + 1));
   size_t off = (size_t)(reinterpret_cast<unsigned char*>(istage + 2 * mlim * OST2) - smem_raw);
   off = (off + 15) & ~(size_t)15;
@@ -174,14 +186,16 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
   cf* work = reinterpret_cast<cf*>(wbase);
   cf* outb = work + RW * P1 * WP;
 
-  for (int i = threadIdx.x; i < H; i += blockDim.x) tw[i] = g_tw[i];
+  if (!TWG)
+    for (int i = threadIdx.x; i < H; i += blockDim.x) tw_s[i] = g_tw[i];
   for (int i = threadIdx.x; i <= mlim; i += blockDim.x) tw2[i] = g_tw2[i];
-  const int nvalid = min(ROWS_PER_TILE2, nlat - k0);
+  const int nvalid = min(RT, nlat - k0);
   // staging fill: every 128-byte segment is fetched with fire-and-forget cp.async (LDGSTS), so all ~2*mlim/nw loads
   // of a lane are in flight at once instead of one DRAM round trip per batch (the profile showed half of the kernel's
   // stall samples on the first use of these loads); the per-order scale is applied when the spectrum is read
   for (int seg = warp; seg < 2 * mlim; seg += nw) {
     const int m = seg >> 1, ri = seg & 1;
+    if (lane >= RT) continue;
     if (lane < nvalid) {
       const float* src = Yt + (((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane;
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(istage + seg * OST2 + lane)), "l"(src) : "memory");
@@ -195,7 +209,7 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
 
   const float osc = out_scale ? out_scale[bc] : 1.0f;
   float lsum = 0.0f, lsq = 0.0f;
-  constexpr int NGROUPS = ROWS_PER_TILE2 / RW;
+  constexpr int NGROUPS = RT / RW;
   const int iters = (NGROUPS + nw - 1) / nw;
   for (int it = 0; it < iters; ++it) {
     const int g = warp + it * nw;
@@ -296,19 +310,19 @@ static bool pick_warps2(size_t fixed, size_t per_warp, int max_groups, int* nwar
   return false;
 }
 
-template <int P1, int P2, int RW, int NZ2 = 0>
+template <int P1, int P2, int RW, int NZ2 = 0, int RT = 32, bool TWG = false, bool DB = true>
 static int launch_fwd(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
                       const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st) {
   constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
   const int XS = xs_size(H, NZ2 > 0 ? NZ2 * P1 : p->mlim);
-  const size_t fixed = sizeof(cf) * (H + p->mlim + 1) + sizeof(float) * 2 * p->mlim * OST2;
-  const size_t per_warp = sizeof(cf) * ((size_t)2 * RW * H + (size_t)RW * P1 * WP + (size_t)RW * XS);
+  const size_t fixed = sizeof(cf) * ((TWG ? 0 : H) + p->mlim + 1) + sizeof(float) * 2 * p->mlim * (RT + 1);
+  const size_t per_warp = sizeof(cf) * ((size_t)(DB ? 2 : 1) * RW * H + (size_t)RW * P1 * WP + (DB ? (size_t)RW * XS : 0));
   int nw; size_t smem;
-  if (!pick_warps2(fixed, per_warp, ROWS_PER_TILE2 / RW, &nw, &smem))
+  if (!pick_warps2(fixed, per_warp, RT / RW, &nw, &smem))
     return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT does not fit in shared memory");
-  auto kern = rfft2d_kernel<P1, P2, RW, NZ2>;
+  auto kern = rfft2d_kernel<P1, P2, RW, NZ2, RT, TWG, DB>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((p->nlat + ROWS_PER_TILE2 - 1) / ROWS_PER_TILE2, B * C);
+  dim3 grid((p->nlat + RT - 1) / RT, B * C);
   kern<<<grid, nw * 32, smem, st>>>(x, Xt, reinterpret_cast<const cf*>(p->d_tw), reinterpret_cast<const cf*>(p->d_tw2),
                                     mscale, in_scale, in_shift, p->nlat, p->mlim, p->kpad, C, zero_imag,
                                     (p->precision == MSFNO_PREC_TF32 && !zero_imag) ? 1 : 0);
@@ -317,23 +331,23 @@ static int launch_fwd(const msfno_plan* p, const float* x, float* Xt, const floa
   return MSFNO_OK;
 }
 
-template <int P1, int P2, int RW, int NZ = 0>
+template <int P1, int P2, int RW, int NZ = 0, int RT = 32, bool TWG = false>
 static int launch_inv(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
                       const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st) {
   constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
-  const size_t fixed = sizeof(cf) * (H + p->mlim + 1) + sizeof(float) * 2 * p->mlim * OST2 + 16 * 8 + sizeof(float) * p->mlim + 128;
+  const size_t fixed = sizeof(cf) * ((TWG ? 0 : H) + p->mlim + 1) + sizeof(float) * 2 * p->mlim * (RT + 1) + 16 * 8 + sizeof(float) * p->mlim + 128;
   const size_t per_warp = sizeof(cf) * ((size_t)RW * P1 * WP + (size_t)RW * H);
   int nw; size_t smem;
-  if (!pick_warps2(fixed, per_warp, ROWS_PER_TILE2 / RW, &nw, &smem))
+  if (!pick_warps2(fixed, per_warp, RT / RW, &nw, &smem))
     return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT does not fit in shared memory");
   // prefer two resident CTAs per SM (one CTA's staging fill overlaps another's FFT phase) when 4 warps allow it
   if (nw == 8) {
     const size_t t4 = fixed + 512 + 4 * (((per_warp + 127) & ~(size_t)127) + 32);
     if (t4 <= 112 * 1024 && RW == 1) { nw = 4; smem = t4; }   // (measured: helps the 1440-point rows, hurts RW = 4)
   }
-  auto kern = irfft2d_kernel<P1, P2, RW, NZ>;
+  auto kern = irfft2d_kernel<P1, P2, RW, NZ, RT, TWG>;
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((p->nlat + ROWS_PER_TILE2 - 1) / ROWS_PER_TILE2, B * C);
+  dim3 grid((p->nlat + RT - 1) / RT, B * C);
   kern<<<grid, nw * 32, smem, st>>>(Yt, y, reinterpret_cast<const cf*>(p->d_tw), reinterpret_cast<const cf*>(p->d_tw2),
                                     mscale, skip, out_scale, stats, p->nlat, p->mlim, p->kpad, C, act_gelu);
   count_launch();
@@ -350,7 +364,11 @@ int launch_rfft2d(const msfno_plan* p, const float* x, float* Xt, const float* m
       if (p->mlim <= 5 * 24) return launch_fwd<24, 30, 1, 5>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
       return launch_fwd<24, 30, 1>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
     case 240: return launch_fwd<15, 8, 4>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
-    case 2880: return launch_fwd<36, 40, 1>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
+    case 2880:   // 0.125 degree grid: eight warps per SM (see RT above); second-step outputs pruned to the kept orders
+      // H = 1440 = 48 x 30: step 1 is ONE pass of 30 lane tasks (36 x 40 needs two passes of 40 and of 36 tasks, the
+      // second with 8 / 4 active lanes)
+      if (p->mlim <= 5 * 48) return launch_fwd<48, 30, 1, 5, 16, true, false>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
+      return launch_fwd<48, 30, 1, 0, 16, true, false>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
     default: return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT: unsupported nlon");
   }
 }
@@ -362,7 +380,9 @@ int launch_irfft2d(const msfno_plan* p, const float* Yt, float* y, const float* 
       if (p->mlim <= 4 * 30) return launch_inv<24, 30, 1, 4>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
       return launch_inv<24, 30, 1>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
     case 240: return launch_inv<15, 8, 4>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
-    case 2880: return launch_inv<36, 40, 1>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
+    case 2880:
+      if (p->mlim <= 8 * 30) return launch_inv<48, 30, 1, 8, 16, true>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
+      return launch_inv<48, 30, 1, 0, 16, true>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
     default: return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT: unsupported nlon");
   }
 }

@@ -60,7 +60,7 @@ int main() {
   switch (N / 2) {
     case 720: return (M <= 120) ? run<24, 30, 4>(mode, N, M) : run<24, 30>(mode, N, M);
     case 120: return run<15, 8>(mode, N, M);
-    case 1440: return run<36, 40>(mode, N, M);
+    case 1440: return (M <= 240) ? run<48, 30, 8>(mode, N, M) : run<48, 30>(mode, N, M);
     case 24: return run<4, 6>(mode, N, M);
     case 36: return run<6, 6>(mode, N, M);
     default: printf("ERR size\n"); return 2;
