@@ -381,6 +381,9 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     import msfno_b200
     from msfno_b200 import _lib
+    from msfno_b200.pipeline import bind_host_to_device
+    # before any pinned allocation: this rank's CPUs (and first-touch pages) = the NUMA node of its GPU
+    cpu_binding = bind_host_to_device(dev) if world > 1 else None
     pk = peaks()
 
     def sync_all():
@@ -514,7 +517,7 @@ def run_ours(args):
                 # host-link floor of one step; e2e cannot beat it
                 "copy_ceiling_ms_per_step": ceiling_ms,
                 "copy_ceiling_GBps": world * (primary["h2d"] + primary["d2h"]) / (ceiling_ms * 1e-3) / 1e9,
-                "frac_of_copy_ceiling": ceiling_ms / e2e_ms},
+                "frac_of_copy_ceiling": ceiling_ms / e2e_ms, "rank0_cpu_binding": cpu_binding},
         "tiers": tiers,
         "gpu_launches": primary["launches"],
         "clocks": primary["clocks"],
@@ -536,7 +539,9 @@ def multi_gpu_extras(args, dev, rank, world, max_over_ranks, sync_all):
     sharded_sht: BASELINE configs[4] (A): 1441 x 2880, 256 channels, lmax 240 -- latitude-sharded FFT, all-to-all
                  lat<->m over NVLink, order-sharded Legendre, and back.
     ddp_train:   BASELINE configs[2]: MSFNO fwd + bwd + Adam on the FiLM head, per-rank batch 8, film_layers 1,
-                 DistributedDataParallel over NCCL."""
+                 DistributedDataParallel over NCCL.
+    ensemble_rollout: BASELINE configs[3]: 28-day (112-step) autoregressive rollout, 8 members per GPU (64 on 8 GPUs),
+                 members sharded across ranks, no data-path collective."""
     import torch
     out = {}
     try:
@@ -552,6 +557,12 @@ def multi_gpu_extras(args, dev, rank, world, max_over_ranks, sync_all):
                                                 steps=max(2, min(args.steps, 5)))
     except Exception as e:
         out["ddp_train"] = {"error": repr(e)}
+    torch.cuda.empty_cache()
+    try:
+        import bench_rollout
+        out["ensemble_rollout"] = bench_rollout.run(dev, rank, world, max_over_ranks, sync_all, members=8, batch=1, steps=112)
+    except Exception as e:
+        out["ensemble_rollout"] = {"error": repr(e)}
     torch.cuda.empty_cache()
     return out
 

@@ -203,6 +203,14 @@ int msfno_fold_affine(const float* W, const float* A, const float* S, const floa
 int msfno_fold_norm_affine(const float* W, const double* stats, const float* nw, const float* nb, const float* gamma,
                            const float* beta, float scale, float eps, long HW, const float* bias, float* Wb,
                            float* bb, int B, int O, int C, int ld, int round_tf32, void* stream);
+/* Mean-carrying residual stream of the tensor-core tier (the stream stored between blocks is X = x - mu, mu [B][C] carried
+ * beside it; InstanceNorm, sfnonet.py:221-251, is shift-invariant): from the plane sums `stats` [B C][2] of X (may be
+ * NULL with b2 = mu_out = NULL) and the incoming offset mu (may be NULL = 0):
+ *   b2[b][o] = bias2[o] - mean(X[b][o]);  mu_out[b][c] = mu[b][c] + mean(X[b][c]);
+ *   sb[b][o] = skip_bias[o] + sum_c Wskip[o][c] mu[b][c]   (sb may be NULL; needs mu and Wskip [C][ldw]).
+ * One launch instead of six library element-wise / gemv launches per block. */
+int msfno_mean_carry(const double* stats, long HW, const float* mu, const float* bias2, const float* Wskip, long ldw,
+                     const float* skip_bias, float* b2, float* mu_out, float* sb, int B, int C, void* stream);
 /* out = g * gelu'(h), exact (erf) GELU: activation adjoint of the frozen-weight channel-MLP backward (a14) */
 int msfno_gelu_bwd_mul(const float* g, const float* h, float* out, long long n, void* stream);
 /* y[plane][:] = A[plane]*x[plane][:] + S[plane] */

@@ -76,6 +76,7 @@ _SIGS = {
     "msfno_film_affine_bwd": (c_int, [_P, _P, _P, c_float, _P, _P, _P, c_int, c_int, c_long, _P]),
     "msfno_plane_stats": (c_int, [_P, _P, c_int, c_long, _P]),
     "msfno_norm_film_coeffs": (c_int, [_P, _P, _P, _P, _P, c_float, c_float, _P, _P, c_int, c_int, c_long, _P]),
+    "msfno_mean_carry": (c_int, [_P, c_long, _P, _P, _P, c_long, _P, _P, _P, _P, c_int, c_int, _P]),
     "msfno_fold_affine": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "msfno_fold_norm_affine": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_float, c_long, _P, _P, _P, c_int, c_int, c_int, c_int,
                                        c_int, _P]),

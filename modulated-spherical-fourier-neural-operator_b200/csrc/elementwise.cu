@@ -220,6 +220,43 @@ __global__ void norm_film_coeffs_kernel(const double* __restrict__ stats, const 
   S[i] = s;
 }
 
+// Mean-carrying residual stream (tensor-core tier, sfnonet.py: _fused): everything a block needs from the plane sums of the
+// stored stream X = x - mu and the carried offset mu, in one launch (it replaced six PyTorch element-wise / gemv launches
+// per block, each of which also broke the programmatic-dependent-launch chain of the step):
+//   mean[b][c]   = stats[b C + c][0] / HW
+//   b2[b][o]     = bias2[o] - mean[b][o]                        (per-sample bias of the fused MLP's second conv)
+//   mu_out[b][c] = mu[b][c] + mean[b][c]                        (offset of the stream the block stores)
+//   sb[b][o]     = skip_bias[o] + sum_c Wskip[o][c] mu[b][c]    (per-sample bias of the inner skip conv; only with mu)
+// grid = B, block = 256: warps walk the rows of Wskip with lanes along c (coalesced), fixed-order shuffle reduction.
+__global__ void mean_carry_kernel(const double* __restrict__ stats, double inv_hw, const float* __restrict__ mu,
+                                  const float* __restrict__ bias2, const float* __restrict__ Wskip, long long ldw,
+                                  const float* __restrict__ skip_bias, float* __restrict__ b2, float* __restrict__ mu_out,
+                                  float* __restrict__ sb, int C) {
+  extern __shared__ float mu_s[];
+  pdl_trigger();
+  pdl_wait();
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float m = mu ? mu[(size_t)b * C + c] : 0.0f;
+    mu_s[c] = m;
+    if (stats) {
+      const float mean = (float)(stats[2 * ((size_t)b * C + c)] * inv_hw);
+      if (b2) b2[(size_t)b * C + c] = (bias2 ? bias2[c] : 0.0f) - mean;
+      if (mu_out) mu_out[(size_t)b * C + c] = m + mean;
+    }
+  }
+  if (!sb) return;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int o = warp; o < C; o += nw) {
+    const float* wr = Wskip + (size_t)o * ldw;
+    float acc = 0.0f;
+    for (int c = lane; c < C; c += 32) acc = fmaf(wr[c], mu_s[c], acc);
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) sb[(size_t)b * C + o] = (skip_bias ? skip_bias[o] : 0.0f) + acc;
+  }
+}
+
 // one CTA per plane: gx = (1 + gamma*scale) * gy, ggamma = scale * sum(gy*x), gbeta = scale * sum(gy)
 __global__ void film_bwd_kernel(const float* __restrict__ gy, const float* __restrict__ x, const float* __restrict__ gamma,
                                 float scale, float* __restrict__ gx, float* __restrict__ ggamma,
@@ -331,6 +368,17 @@ int msfno_fold_norm_affine(const float* W, const double* stats, const float* nw,
     return record_error(MSFNO_ERR_BAD_SHAPE, "fold_norm_affine: bad argument");
   MSFNO_CUDA_OK(launch_pdl(fold_norm_affine_kernel, dim3(O, B), dim3(128), 0, (cudaStream_t)stream, W, stats, nw, nb, gamma, beta,
                            scale, eps, 1.0 / (double)HW, bias, Wb, bb, O, C, ld, round_tf32));
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
+}
+
+int msfno_mean_carry(const double* stats, long HW, const float* mu, const float* bias2, const float* Wskip, long ldw,
+                     const float* skip_bias, float* b2, float* mu_out, float* sb, int B, int C, void* stream) {
+  if (B < 1 || C < 1 || (stats && HW < 1) || (!stats && (b2 || mu_out)) || (sb && (!mu || !Wskip || ldw < C)) || (!b2 && !mu_out && !sb))
+    return record_error(MSFNO_ERR_BAD_SHAPE, "mean_carry: bad argument");
+  MSFNO_CUDA_OK(launch_pdl(mean_carry_kernel, dim3(B), dim3(256), sizeof(float) * (size_t)C, (cudaStream_t)stream, stats,
+                           stats ? 1.0 / (double)HW : 0.0, mu, bias2, Wskip, (long long)ldw, skip_bias, b2, mu_out, sb, C));
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

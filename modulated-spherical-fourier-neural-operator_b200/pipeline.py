@@ -6,7 +6,48 @@ The reference's inference loop copies every step's fields device->host synchrono
 member i on separate CUDA streams (double-buffered device staging), so throughput is bounded by
 max(compute, PCIe) instead of their sum.
 """
+import os
+
 import torch
+
+
+def bind_host_to_device(device):
+    """Pin this process (and so its later pinned-memory allocations, by first touch) to the CPUs of the NUMA node the GPU
+    hangs off: with one rank per GPU on an 8-GPU box every rank otherwise allocates its staging buffers wherever the kernel
+    puts them, and half of the ranks' 600 MB per step cross the socket interconnect.  Reads
+    /sys/bus/pci/devices/<bdf>/local_cpulist; returns the CPU list it bound to, or None when the topology is not exposed
+    (containers without sysfs PCI entries) -- never raises."""
+    try:
+        idx = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+        bdf = torch.cuda.get_device_properties(idx).pci_bus_id if hasattr(torch.cuda.get_device_properties(idx), "pci_bus_id") else None
+        if bdf is None:
+            import ctypes
+            buf = ctypes.create_string_buffer(32)
+            rt = ctypes.CDLL("libcudart.so.12")
+            if rt.cudaDeviceGetPCIBusId(buf, 32, idx) != 0:
+                return None
+            bdf = buf.value.decode()
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:      # cudart prints an 8-digit domain, sysfs uses 4
+            bdf = bdf[4:]
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bdf
+        with open(path) as f:
+            spec = f.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return spec
+    except Exception:
+        return None
 
 
 class HostPipeline:

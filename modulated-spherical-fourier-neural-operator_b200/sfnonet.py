@@ -322,12 +322,25 @@ class FourierNeuralOperatorBlock(nn.Module):
         residual = x
         stats0 = in_stats if in_stats is not None else plane_stats(x)
         A0, S0 = norm_film_coeffs(stats0, self.norm0, B, C, HW)
+        b2c = mu_out = sb = None
+        skip_conv = isinstance(getattr(self, "inner_skip", None), nn.Conv2d)
+        if carry or (mu is not None and skip_conv):
+            # one launch: per-sample fc2 bias (fc2.bias - plane mean of X), the outgoing offset, the skip conv's bias + W mu
+            if carry:
+                b2c = torch.empty((B, C), dtype=torch.float32, device=x.device)
+                mu_out = torch.empty((B, C), dtype=torch.float32, device=x.device)
+            if mu is not None and skip_conv:
+                sb = torch.empty((B, C), dtype=torch.float32, device=x.device)
+                wsk = self.inner_skip.weight.view(C, C)
+            fc2b = mlp.fwd[2].bias if carry else None
+            check(lib.msfno_mean_carry(ptr(stats0) if carry else None, HW, ptr(mu), ptr(fc2b), ptr(wsk) if sb is not None else None, C,
+                                       ptr(self.inner_skip.bias) if sb is not None else None, ptr(b2c), ptr(mu_out), ptr(sb), B, C,
+                                       _stream()), "mean_carry")
         skip = None
         if hasattr(self, "inner_skip"):
             if isinstance(self.inner_skip, nn.Conv2d):
                 if mu is not None:
-                    sb = torch.addmm(self.inner_skip.bias.float()[None, :], mu, self.inner_skip.weight.view(C, C).float().t())
-                    skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=sb.contiguous(), per_sample_bias=True)
+                    skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=sb, per_sample_bias=True)
                 else:
                     skip = conv1x1(x, padded_weight(self.inner_skip.weight), C, bias=self.inner_skip.bias)
             else:
@@ -350,9 +363,7 @@ class FourierNeuralOperatorBlock(nn.Module):
                           if (want_stats and fuse_res) else None)
                 b2, mu_out = fc2.bias, None
                 if carry:
-                    mean_x = (stats0.view(B, C, 2)[:, :, 0] / HW).float()     # plane means of the stored input X
-                    b2 = (fc2.bias.float()[None, :] - mean_x if fc2.bias is not None else -mean_x).contiguous()
-                    mu_out = mean_x if mu is None else mu + mean_x
+                    b2 = b2c     # fc2.bias - plane means of the stored input X; mu_out = mu + those means (msfno_mean_carry)
                 out = mlp1x1(y, Wb, C, bias_b.contiguous(), padded_weight(fc2.weight), b2,
                              add=residual.contiguous().float() if fuse_res else None, per_sample_w1=True, per_sample_b1=True,
                              w1_rounded=True, stats=ostats, per_sample_b2=carry)

@@ -8,6 +8,7 @@ tests/test_gpu_dropin.py).  The reference needs a handful of absent third-party 
 import time; they are stubbed in sys.modules.  torch_harmonics
 is replaced by oracle/th_shim.py (un-vendored dependency, conda_environment.yml:62).
 """
+import importlib.machinery
 import os
 import sys
 import types
@@ -36,6 +37,9 @@ def use_harmonics(mod):
 
 def _stub(name, **attrs):
     m = types.ModuleType(name)
+    # a real spec: importlib.util.find_spec() raises ValueError on a sys.modules entry whose __spec__ is None, and
+    # torch._dynamo calls it for "xarray" & co. when it is first imported (e.g. by torch.optim.Adam) later in the process
+    m.__spec__ = importlib.machinery.ModuleSpec(name, None)
     m.__dict__.update(attrs)
     sys.modules[name] = m
     return m

@@ -15,6 +15,42 @@ import msfno_b200
 from msfno_b200.graph import GraphedForward
 
 
+def run(dev, rank, world, max_over_ranks, sync_all, members=8, batch=1, steps=112, precision="tf32"):
+    """Rolls out this rank's `members` members for `steps` 6 h steps on an initialised process group (world may be 1);
+    returns the result dict on every rank (device time: CUDA events, max over ranks)."""
+    assert members % batch == 0, "members must be a multiple of batch"
+    msfno_b200.set_precision(precision)
+    try:
+        torch.manual_seed(0)
+        net = msfno_b200.FourierNeuralOperatorNet(dev, None, filter_type="non-linear").to(dev).eval()
+        g = torch.Generator().manual_seed(1000 + rank)
+        ens = torch.randn(members, 73, 721, 1440, generator=g).to(dev)
+        final = torch.empty_like(ens)
+        with msfno_b200.precision.library_scope():
+            gf = GraphedForward(net, ens[:batch])
+            gf.rollout(ens[:batch], 2)  # warm-up replays
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(0, members, batch):
+            final[i:i + batch].copy_(gf.rollout(ens[i:i + batch], steps), non_blocking=True)
+        e1.record()
+        sync_all()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        finite = bool(torch.isfinite(final).all())
+        total = world * members * steps
+        return {"metric": "sfno_rollout_member_steps_per_sec_721x1440x73", "value": total / (ms * 1e-3), "unit": "member-steps/s",
+                "n_gpus": world, "members_per_gpu": members, "members_total": world * members, "batch": batch,
+                "steps_per_member": steps, "ms_per_member_step": ms / (members * steps),
+                "rollout_seconds_per_member": ms * 1e-3 / members, "wall_ms": ms, "scaling": "weak", "dtype": precision,
+                "data": "synthetic (random-init weights: the iterated map is not a forecast, only its cost is meaningful)",
+                "output_finite_this_rank": finite,
+                "config": {"workload": "configs[3]: 112-step autoregressive rollout, ensemble members sharded across GPUs, "
+                                       "no inter-GPU traffic", "filter_type": "non-linear", "cuda_graph": True}}
+    finally:
+        msfno_b200.set_precision("fp32")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--members", type=int, default=8, help="ensemble members per GPU (config 4: 64 members over 8 GPUs)")
@@ -22,46 +58,27 @@ def main():
     ap.add_argument("--steps", type=int, default=112, help="6 h steps per member (28 days = 112)")
     ap.add_argument("--precision", default="tf32")
     a = ap.parse_args()
-    assert a.members % a.batch == 0, "--members must be a multiple of --batch"
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    msfno_b200.set_precision(a.precision)
-    torch.manual_seed(0)
-    net = msfno_b200.FourierNeuralOperatorNet(dev, None, filter_type="non-linear").to(dev).eval()
-    g = torch.Generator().manual_seed(1000 + rank)
-    members = torch.randn(a.members, 73, 721, 1440, generator=g).to(dev)
-    final = torch.empty_like(members)
-    with msfno_b200.precision.library_scope():
-        gf = GraphedForward(net, members[: a.batch])
-        gf.rollout(members[: a.batch], 2)  # warm-up replays
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(0, a.members, a.batch):
-        final[i : i + a.batch].copy_(gf.rollout(members[i : i + a.batch], a.steps), non_blocking=True)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    finite = torch.tensor([float(torch.isfinite(final).all())], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(finite, op=dist.ReduceOp.MIN)
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t)
+
+    res = run(dev, rank, world, max_over_ranks, sync_all, a.members, a.batch, a.steps, a.precision)
     if rank == 0:
-        total = world * a.members * a.steps
-        print(json.dumps({
-            "metric": "sfno_rollout_member_steps_per_sec_721x1440x73", "value": total / (ms.item() * 1e-3), "unit": "member-steps/s",
-            "n_gpus": world, "members_per_gpu": a.members, "batch": a.batch, "steps_per_member": a.steps,
-            "ms_per_member_step": ms.item() / (a.members * a.steps), "rollout_seconds_per_member": ms.item() * 1e-3 / a.members,
-            "wall_ms": ms.item(), "scaling": "weak", "dtype": a.precision, "data": "synthetic (random-init weights: the "
-            "iterated map is not a forecast, only its cost is meaningful)", "output_finite": bool(finite.item()),
-            "config": {"workload": "configs[3]: 112-step autoregressive rollout, ensemble members sharded across GPUs, "
-                                   "no inter-GPU traffic", "filter_type": "non-linear", "cuda_graph": True}}))
+        print(json.dumps(res))
     if world > 1:
         dist.destroy_process_group()
 
