@@ -130,6 +130,43 @@ int msfno_fft_stage(msfno_plan* plan, int inverse, int adjoint, const float* src
                     void* stream);
 int msfno_legendre_stage(msfno_plan* plan, int kind, const float* src, float* dst, int m_lo, int m_hi, int B,
                          int C, void* stream);
+/* The two ends of the lat<->m all-to-all, one launch each (they replaced one strided PyTorch copy per peer).
+ * `flat`: the buffer all_to_all_single moves -- for every peer s a block [rows][pad32(seg_n[s])], rows = local orders x 2C,
+ * seg_n[s] = the peer's latitude count (the pitch is the peer's own lat-contiguous pitch), blocks back to back;
+ * `full`: the Legendre stage's operand [rows][pad_full] holding all nlat latitudes, peer s at columns seg_lo[s].
+ * gather != 0: blocks -> full (columns >= nlat zeroed);  gather == 0: full -> blocks (pitch tails zeroed).
+ * seg_lo / seg_n are HOST arrays of nseg <= MSFNO_MAX_LAT_SEGMENTS entries. */
+#define MSFNO_MAX_LAT_SEGMENTS 16
+int msfno_lat_segments(int gather, float* flat, float* full, long rows, int pad_full, int nlat, int nseg,
+                       const int* seg_lo, const int* seg_n, void* stream);
+
+/* ---- lat<->m exchange over NVLink peer memory (one process per GPU, CUDA IPC) -----------------------------------
+ * msfno_peer_alloc: cudaMalloc'ed, zero-filled buffer plus its 64-byte IPC handle (ship the handle to the other ranks by
+ * any means, e.g. torch.distributed.all_gather_object); msfno_peer_open maps a peer's buffer into this process
+ * (msfno_peer_close unmaps it, msfno_peer_free releases an own buffer).
+ * msfno_peer_block_copy: ONE launch that copies, for every block i, rows x cols floats from
+ * src[(src_row0 + r) * src_pitch + src_col0 + j] to dst[(dst_row0 + r) * dst_pitch + dst_col0 + j] and zero-fills the
+ * zero_tail columns behind them; dst is typically a peer mapping, so the transpose between the latitude-sharded longitude
+ * stage and the order-sharded Legendre stage is a direct NVLink store into the consumer's operand buffer.
+ * msfno_peer_barrier: all `world` ranks call it with the same increasing `epoch`; flags[r] is (this rank's mapping of)
+ * rank r's flag array of `world` unsigned ints, zero at start.  Returns when every rank has arrived AND the peer stores
+ * issued before the barrier on each rank are visible; *timed_out (device int) is set instead of hanging if a peer never
+ * arrives.  `blocks` and `flags` are HOST arrays. */
+#define MSFNO_MAX_PEERS 16
+typedef struct msfno_peer_block {
+  float* dst;
+  long long rows;
+  int cols, zero_tail;
+  long long src_row0, src_col0, src_pitch;
+  long long dst_row0, dst_col0, dst_pitch;
+} msfno_peer_block;
+int msfno_peer_alloc(size_t bytes, void** ptr, void* handle64);
+int msfno_peer_free(void* ptr);
+int msfno_peer_open(const void* handle64, void** ptr);
+int msfno_peer_close(void* ptr);
+int msfno_peer_block_copy(const float* src, int nblocks, const msfno_peer_block* blocks, void* stream);
+int msfno_peer_barrier(unsigned int* const* flags, int rank, int world, unsigned int epoch, int* timed_out,
+                       void* stream);
 
 /* ---- coefficient layout changes (public boundary of RealSHT / InverseRealSHT) ------------
  * replaces: the zeros()+slice-assign in RealSHT.forward, view_as_real/complex shuffles and the

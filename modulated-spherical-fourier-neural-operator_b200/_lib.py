@@ -63,6 +63,13 @@ _SIGS = {
     "msfno_isht_bwd": (c_int, [_P, _P, _P, _P, c_int, c_int, _P]),
     "msfno_fft_stage": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P]),
     "msfno_legendre_stage": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "msfno_lat_segments": (c_int, [c_int, _P, _P, c_long, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), _P]),
+    "msfno_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), _P]),
+    "msfno_peer_free": (c_int, [_P]),
+    "msfno_peer_open": (c_int, [_P, ctypes.POINTER(c_void_p)]),
+    "msfno_peer_close": (c_int, [_P]),
+    "msfno_peer_block_copy": (c_int, [_P, c_int, _P, _P]),
+    "msfno_peer_barrier": (c_int, [_P, c_int, c_int, ctypes.c_uint, _P, _P]),
     "msfno_coef_relayout": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     "msfno_specconv_ws_floats": (ctypes.c_size_t, [_P, c_int, c_int, c_int]),
     "msfno_specconv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),

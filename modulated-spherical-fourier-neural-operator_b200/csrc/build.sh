@@ -7,7 +7,7 @@ OBJ=${MSFNO_OBJ:-build}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Xptxas -v ${MSFNO_EXTRA_FLAGS:-}"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 mkdir -p $OBJ
-SRCS="fft fft2d plan gemm_ffma specconv specattn sht elementwise gemm_tc conv_tc conv1x1 mlp_tc dft_tc losses"
+SRCS="fft fft2d plan gemm_ffma specconv specattn sht elementwise gemm_tc conv_tc conv1x1 mlp_tc dft_tc losses peer"
 pids=()
 for f in $SRCS; do
   rm -f $OBJ/$f.o

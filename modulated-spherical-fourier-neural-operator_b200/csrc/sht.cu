@@ -51,6 +51,39 @@ static int legendre_gemm(msfno_plan* p, int kind, const float* A, long long lda,
   return launch_gemm_ffma(g, st);
 }
 
+// ---- lat <-> m exchange buffers of the spatially sharded transform (one launch per direction) -----------------------
+// `flat` is what NCCL all_to_all_single moves: for every peer s a block [rows][pad32(n_s)] (rows = local orders x 2C, n_s =
+// the peer's latitude count, zero-padded pitch = the peer's own lat-contiguous pitch); `full` is the Legendre stage's
+// operand [rows][pad_full] with all nlat latitudes.  gather: blocks -> full (columns [nlat, pad_full) zeroed);
+// scatter: full -> blocks (pitch tails zeroed).
+struct LatSegs {
+  int n;
+  int lo[MSFNO_MAX_LAT_SEGMENTS];        // first latitude of peer s
+  int cnt[MSFNO_MAX_LAT_SEGMENTS];       // its latitude count
+  long long base[MSFNO_MAX_LAT_SEGMENTS];  // float offset of its block in `flat`
+};
+
+__global__ void lat_segments_kernel(int gather, float* __restrict__ flat, float* __restrict__ full, long long rows, int pad_full,
+                                    int nlat, LatSegs sg) {
+  const int s = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (long long r = (long long)blockIdx.x * nw + warp; r < rows; r += (long long)gridDim.x * nw) {
+    float* frow = full + r * pad_full;
+    if (s == sg.n) {   // pseudo-segment: the zero tail of `full`
+      if (gather)
+        for (int j = nlat + lane; j < pad_full; j += 32) frow[j] = 0.0f;
+      continue;
+    }
+    const int n = sg.cnt[s], pitch = (n + 31) & ~31;
+    float* brow = flat + sg.base[s] + r * pitch;
+    if (gather) {
+      for (int j = lane; j < n; j += 32) frow[sg.lo[s] + j] = brow[j];
+    } else {
+      for (int j = lane; j < pitch; j += 32) brow[j] = j < n ? frow[sg.lo[s] + j] : 0.0f;
+    }
+  }
+}
+
 extern "C" {
 
 size_t msfno_sht_ws_floats(const msfno_plan* p, int B, int C) {
@@ -151,6 +184,27 @@ int msfno_legendre_stage(msfno_plan* p, int kind, const float* src, float* dst, 
     default:
       return record_error(MSFNO_ERR_BAD_SHAPE, "legendre_stage: bad kind");
   }
+}
+
+int msfno_lat_segments(int gather, float* flat, float* full, long rows, int pad_full, int nlat, int nseg, const int* seg_lo,
+                       const int* seg_n, void* stream) {
+  if (!flat || !full || rows < 1 || nlat < 1 || pad_full < nlat || nseg < 1 || nseg > MSFNO_MAX_LAT_SEGMENTS || !seg_lo || !seg_n)
+    return record_error(MSFNO_ERR_BAD_SHAPE, "lat_segments: bad argument");
+  LatSegs sg{};
+  sg.n = nseg;
+  long long base = 0;
+  for (int s = 0; s < nseg; ++s) {
+    if (seg_n[s] < 0 || seg_lo[s] < 0 || seg_lo[s] + seg_n[s] > nlat) return record_error(MSFNO_ERR_BAD_SHAPE, "lat_segments: bad segment");
+    sg.lo[s] = seg_lo[s]; sg.cnt[s] = seg_n[s]; sg.base[s] = base;
+    base += (long long)rows * ((seg_n[s] + 31) & ~31);
+  }
+  long long blocks = (rows + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  lat_segments_kernel<<<dim3((unsigned)blocks, nseg + (gather ? 1 : 0)), 256, 0, (cudaStream_t)stream>>>(gather, flat, full, rows, pad_full,
+                                                                                                       nlat, sg);
+  count_launch();
+  MSFNO_CUDA_OK(cudaGetLastError());
+  return MSFNO_OK;
 }
 
 }  // extern "C"

@@ -136,12 +136,138 @@ class CudaStages:
                    "legendre_stage")
         return pm
 
+    def lat_segments(self, gather, flat, full, lat_bounds):
+        """One launch for either end of the lat<->m exchange (msfno_lat_segments): `flat` = the peers' blocks back to back,
+        each [rows][pad(n_s)]; `full` = [..., pad(nlat)] with every latitude."""
+        n = len(lat_bounds) - 1
+        lo = (ctypes.c_int * n)(*lat_bounds[:-1])
+        cnt = (ctypes.c_int * n)(*[lat_bounds[i + 1] - lat_bounds[i] for i in range(n)])
+        rows = full.numel() // full.shape[-1]
+        _lib.check(_lib.lib.msfno_lat_segments(1 if gather else 0, flat.data_ptr(), full.data_ptr(), rows, full.shape[-1], self.nlat, n,
+                                               lo, cnt, self._st()), "lat_segments")
+
     def legendre_inv(self, cm, m_lo, m_hi):
         B, C = cm.shape[0], cm.shape[1] // 2
         Yt = torch.empty((B, m_hi - m_lo, 2 * C, self.pad(self.nlat)), dtype=torch.float32, device=cm.device)
         _lib.check(_lib.lib.msfno_legendre_stage(self.leg_s.h, 2, cm.data_ptr(), Yt.data_ptr(), m_lo, m_hi, B, C, self._st()),
                    "legendre_stage")
         return Yt
+
+
+class _DevArray:
+    """__cuda_array_interface__ view of raw device memory (own cudaMalloc or a peer mapping) for torch.as_tensor."""
+
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class _PeerBlock(ctypes.Structure):      # mirrors msfno_peer_block (include/msfno_b200.h)
+    _fields_ = [("dst", ctypes.c_void_p), ("rows", ctypes.c_longlong), ("cols", ctypes.c_int), ("zero_tail", ctypes.c_int),
+                ("src_row0", ctypes.c_longlong), ("src_col0", ctypes.c_longlong), ("src_pitch", ctypes.c_longlong),
+                ("dst_row0", ctypes.c_longlong), ("dst_col0", ctypes.c_longlong), ("dst_pitch", ctypes.c_longlong)]
+
+
+class PeerExchange:
+    """The lat<->m transpose as direct NVLink stores into the consumers' operand buffers (csrc/peer.cu): every rank owns
+         A [mloc][2C][pad(nlat)]     operand of ITS Legendre analysis -- filled by all ranks' longitude stages
+         Bf [mlim][2C][pad(nlat_loc)] operand of ITS inverse longitude stage -- filled by all ranks' Legendre syntheses
+    both cudaMalloc'ed, exported through CUDA IPC and mapped by every peer (one process per GPU, one node).  A direction
+    is barrier -> ONE block-copy launch -> barrier on the caller's stream; no library collective, no staging copy."""
+
+    def __init__(self, dsht, C, device, pad):
+        self.d, self.C, self.device, self.group = dsht, C, device, dsht.group
+        self.world, self.rank = dsht.world, dsht.rank
+        if self.world > 16:
+            raise ValueError("PeerExchange supports up to 16 ranks (MSFNO_MAX_PEERS)")
+        lib, check = _lib.lib, _lib.check
+        d = dsht
+        self.padN = pad(d.nlat)
+        self.pads = [pad(d.lat_bounds[s + 1] - d.lat_bounds[s]) for s in range(self.world)]
+        mloc = d.m_hi - d.m_lo
+        self.nA = max(mloc, 1) * 2 * C * self.padN
+        self.nB = d.mlim * 2 * C * self.pads[self.rank]
+        own, handles = [], []
+        with torch.cuda.device(device):
+            for nbytes in (4 * self.nA, 4 * self.nB, 4 * 64):
+                p, h = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+                check(lib.msfno_peer_alloc(nbytes, ctypes.byref(p), h), "peer_alloc")
+                own.append(p.value)
+                handles.append(h.raw)
+        self.own = own
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, handles, group=self.group)
+        self.maps = []          # maps[r] = [A, Bf, flags] pointers of rank r as seen from this process
+        with torch.cuda.device(device):
+            for r in range(self.world):
+                if r == self.rank:
+                    self.maps.append(list(own))
+                    continue
+                ptrs = []
+                for raw in gathered[r]:
+                    q = ctypes.c_void_p()
+                    check(lib.msfno_peer_open(ctypes.create_string_buffer(raw, 64), ctypes.byref(q)), "peer_open")
+                    ptrs.append(q.value)
+                self.maps.append(ptrs)
+        self.A = torch.as_tensor(_DevArray(own[0], self.nA), device=device)
+        self.Bf = torch.as_tensor(_DevArray(own[1], self.nB), device=device)
+        self.flag_ptrs = (ctypes.c_void_p * self.world)(*[m[2] for m in self.maps])
+        self.timed_out = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epoch = 0
+        dist.barrier(group=self.group)      # every mapping exists before anyone stores through one
+
+    def _barrier(self):
+        self.epoch += 1
+        _lib.check(_lib.lib.msfno_peer_barrier(self.flag_ptrs, self.rank, self.world, self.epoch, self.timed_out.data_ptr(),
+                                               torch.cuda.current_stream().cuda_stream), "peer_barrier")
+
+    def _copy(self, src, blocks):
+        arr = (_PeerBlock * len(blocks))(*blocks)
+        _lib.check(_lib.lib.msfno_peer_block_copy(src.data_ptr(), len(blocks), arr, torch.cuda.current_stream().cuda_stream),
+                   "peer_block_copy")
+
+    def forward(self, Xt_loc):
+        """Xt_loc [1][mlim][2C][pad(nlat_loc)] (this rank's latitudes, every order) -> view of A [1][mloc][2C][pad(nlat)]."""
+        d, C2 = self.d, 2 * self.C
+        n_me, padl = d.lat_hi - d.lat_lo, self.pads[self.rank]
+        blocks = [_PeerBlock(self.maps[s][0], (d.m_bounds[s + 1] - d.m_bounds[s]) * C2, n_me, 0, d.m_bounds[s] * C2, 0, padl,
+                             0, d.lat_lo, self.padN) for s in range(self.world)]
+        self._barrier()                      # every peer has finished reading its A of the previous call
+        self._copy(Xt_loc, blocks)
+        self._barrier()                      # every peer's stores into MY A are visible
+        return self.A.view(1, max(d.m_hi - d.m_lo, 1), C2, self.padN)[:, :d.m_hi - d.m_lo]
+
+    def inverse(self, Yt):
+        """Yt [1][mloc][2C][pad(nlat)] (this rank's orders, every latitude) -> view of Bf [1][mlim][2C][pad(nlat_loc)]."""
+        d, C2 = self.d, 2 * self.C
+        mloc = d.m_hi - d.m_lo
+        blocks = []
+        for s in range(self.world):
+            n_s = d.lat_bounds[s + 1] - d.lat_bounds[s]
+            blocks.append(_PeerBlock(self.maps[s][1], mloc * C2, n_s, self.pads[s] - n_s, 0, d.lat_bounds[s], self.padN,
+                                     d.m_lo * C2, 0, self.pads[s]))
+        self._barrier()
+        if mloc > 0:
+            self._copy(Yt, blocks)
+        self._barrier()
+        return self.Bf.view(1, d.mlim, C2, self.pads[self.rank])
+
+    def check(self):
+        """Synchronises; raises if a barrier gave up waiting for a peer."""
+        if int(self.timed_out.item()) != 0:
+            raise RuntimeError("PeerExchange: a rank never arrived at a peer barrier")
+
+    def close(self):
+        lib = _lib.lib
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=self.group)       # nobody unmaps while a peer may still store
+        for r, ptrs in enumerate(self.maps):
+            if r != self.rank:
+                for p in ptrs:
+                    lib.msfno_peer_close(p)
+        self.A = self.Bf = None
+        for p in self.own:
+            lib.msfno_peer_free(p)
+        self.maps, self.own = [], []
 
 
 class DistributedSHT:
@@ -151,8 +277,11 @@ class DistributedSHT:
     inverse_packed(cm_loc [B,2C,Ploc])         -> y_loc [B,C,nlat_loc,nlon]
     """
 
-    def __init__(self, nlat, nlon, lmax, mmax, stages_factory, group=None):
+    def __init__(self, nlat, nlon, lmax, mmax, stages_factory, group=None, peer_exchange=False):
+        """peer_exchange=True (NCCL process group on one node, B = 1): the lat<->m transpose runs as direct NVLink stores
+        into the peers' operand buffers (PeerExchange) instead of all_to_all_single + pack / unpack launches."""
         self.group = group
+        self.use_peer, self.peer = bool(peer_exchange), None
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.nlat, self.nlon, self.lmax, self.mmax = nlat, nlon, lmax, mmax
@@ -164,6 +293,19 @@ class DistributedSHT:
         self.m_lo, self.m_hi = self.m_bounds[self.rank], self.m_bounds[self.rank + 1]
         self.nlat_loc = self.lat_hi - self.lat_lo
         self.stages = stages_factory(self.nlat_loc)
+
+    def _peer(self, B, C, st):
+        if not self.use_peer or B != 1 or not hasattr(st, "lat_segments") or dist.get_backend(self.group) != "nccl":
+            return None
+        if self.peer is None or self.peer.C != C:
+            if self.peer is not None:
+                self.peer.close()
+            self.peer = PeerExchange(self, C, st.device, st.pad)
+        return self.peer
+
+    def _single_exchange(self, B, st):
+        """all_to_all_single + one pack / unpack launch (NCCL, B = 1, stages that provide lat_segments)."""
+        return (B == 1 and hasattr(st, "lat_segments") and self.world <= 16 and dist.get_backend(self.group) == "nccl")
 
     def pos_range(self, r=None):
         r = self.rank if r is None else r
@@ -179,6 +321,20 @@ class DistributedSHT:
         mloc = self.m_hi - self.m_lo
         if self.world == 1:
             Xt = Xt_loc                                               # the stage's own padded layout: nothing to move
+        elif self._peer(B, C, st) is not None:
+            Xt = self.peer.forward(Xt_loc)
+        elif self._single_exchange(B, st):
+            # B = 1 on the CUDA stages: a destination's orders are ONE contiguous run of the m-major intermediate, so
+            # all_to_all_single sends straight out of the FFT stage's output (no send-side copy) and one gather launch
+            # assembles the full-latitude operand of the Legendre stage from the received blocks
+            padl = Xt_loc.shape[-1]
+            in_splits = [(self.m_bounds[s + 1] - self.m_bounds[s]) * 2 * C * padl for s in range(self.world)]
+            out_splits = [mloc * 2 * C * st.pad(self.lat_bounds[s + 1] - self.lat_bounds[s]) for s in range(self.world)]
+            recv = torch.empty(max(sum(out_splits), 1), dtype=x_loc.dtype, device=x_loc.device)
+            dist.all_to_all_single(recv[:sum(out_splits)], Xt_loc.view(-1), out_splits, in_splits, group=self.group)
+            Xt = torch.empty((B, mloc, 2 * C, st.pad(self.nlat)), dtype=x_loc.dtype, device=x_loc.device)
+            if mloc > 0:
+                st.lat_segments(True, recv, Xt, self.lat_bounds)
         else:
             # send side: a destination's orders are one contiguous run of the m-major intermediate (for B = 1 the slices
             # below are views -- no copy), sent with their padded latitude pitch; receive side: one strided scatter per
@@ -210,6 +366,20 @@ class DistributedSHT:
             Yt = torch.zeros((B, 0, 2 * C, st.pad(self.nlat)), dtype=cm_loc.dtype, device=cm_loc.device)
         if self.world == 1:
             return st.fft_inv(Yt, B, C)
+        if self._peer(B, C, st) is not None:
+            return st.fft_inv(self.peer.inverse(Yt), B, C)
+        if self._single_exchange(B, st):
+            # one scatter launch writes every destination's block with that destination's padded pitch; the received
+            # orders land directly in the FFT stage's m-major operand (a source's orders are one contiguous run of it)
+            padl = st.pad(self.nlat_loc)
+            in_splits = [mloc * 2 * C * st.pad(self.lat_bounds[s + 1] - self.lat_bounds[s]) for s in range(self.world)]
+            out_splits = [(self.m_bounds[s + 1] - self.m_bounds[s]) * 2 * C * padl for s in range(self.world)]
+            send = torch.empty(max(sum(in_splits), 1), dtype=cm_loc.dtype, device=cm_loc.device)
+            if mloc > 0:
+                st.lat_segments(False, send, Yt, self.lat_bounds)
+            Yt_loc = torch.empty((B, self.mlim, 2 * C, padl), dtype=cm_loc.dtype, device=cm_loc.device)
+            dist.all_to_all_single(Yt_loc.view(-1), send[:sum(in_splits)], out_splits, in_splits, group=self.group)
+            return st.fft_inv(Yt_loc, B, C)
         # send side: one strided gather per destination, written with the destination's padded latitude pitch; receive
         # side: a source's orders are one contiguous run of the local m-major operand -- for B = 1 the receive buffers ARE
         # views of it (no assembly copy)

@@ -195,3 +195,33 @@ def test_fold_norm_affine_is_the_two_launch_result(tier, film):
         assert rel_l2(got, want) < (1e-5 if tier == "fp32" else 2e-3)
     finally:
         msfno_b200.set_precision("fp32")
+
+
+def test_mean_carry_matches_algebra():
+    """msfno_mean_carry: the per-block coefficients of the mean-carrying stream (tensor-core tier) against fp64 algebra --
+    b2 = bias2 - mean(X), mu_out = mu + mean(X), sb = skip_bias + Wskip mu -- with and without an incoming offset."""
+    from msfno_b200._lib import check, lib, ptr
+    from msfno_b200.sfnonet import plane_stats
+    g = torch.Generator().manual_seed(5)
+    B, C, H, W = 3, 256, 9, 16
+    X = (torch.randn(B, C, H, W, generator=g) + torch.randn(B, C, 1, 1, generator=g) * 3).cuda()
+    st = plane_stats(X)
+    mu = torch.randn(B, C, generator=g).cuda()
+    bias2, sbias = torch.randn(C, generator=g).cuda(), torch.randn(C, generator=g).cuda()
+    Wsk = torch.randn(C, C, generator=g).cuda()
+    stream = torch.cuda.current_stream().cuda_stream
+    mean = X.double().mean(dim=(2, 3))
+    for use_mu in (True, False):
+        b2 = torch.full((B, C), float("nan"), device="cuda")
+        mo = torch.full((B, C), float("nan"), device="cuda")
+        sb = torch.full((B, C), float("nan"), device="cuda") if use_mu else None
+        check(lib.msfno_mean_carry(ptr(st), H * W, ptr(mu) if use_mu else None, ptr(bias2), ptr(Wsk) if use_mu else None, C,
+                                   ptr(sbias) if use_mu else None, ptr(b2), ptr(mo), ptr(sb), B, C, stream), "mean_carry")
+        assert rel_l2(b2, bias2.double()[None, :] - mean) < 1e-6
+        assert rel_l2(mo, (mu.double() if use_mu else 0) + mean) < 1e-6
+        if use_mu:
+            assert rel_l2(sb, sbias.double()[None, :] + mu.double() @ Wsk.double().T) < 1e-6
+    # skip-bias only (a block that receives an offset but cannot carry it on): stats may be NULL
+    sb = torch.empty((B, C), device="cuda")
+    check(lib.msfno_mean_carry(None, 0, ptr(mu), None, ptr(Wsk), C, ptr(sbias), None, None, ptr(sb), B, C, stream), "mean_carry")
+    assert rel_l2(sb, sbias.double()[None, :] + mu.double() @ Wsk.double().T) < 1e-6

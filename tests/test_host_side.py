@@ -189,6 +189,7 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
                                                                1, 1, 1, 1, 0, None),
         "norm_film_coeffs": lambda: lib.msfno_norm_film_coeffs(None, None, None, None, None, 1.0, 1e-6, None, None, 1, 1, 10, None),
         "gelu_bwd_mul": lambda: lib.msfno_gelu_bwd_mul(None, None, None, 0, None),
+        "mean_carry": lambda: lib.msfno_mean_carry(None, 0, None, None, None, 0, None, None, None, None, 1, 1, None),
         "plane_affine": lambda: lib.msfno_plane_affine(None, None, None, None, 0, 0, None),
     }
     for name, call in cases.items():
@@ -222,3 +223,34 @@ def test_staged_reference_copy_is_unmodified():
                 assert hashlib.sha256(f.read()).hexdigest() == digest, "staged copy differs from " + mounted
         n += 1
     assert n >= 9
+
+
+def test_launch_shares_reads_every_committed_launch_list():
+    """tools/launch_shares.py (the "share of the step" evidence in DESIGN.md) must find the step boundary of every launch
+    list committed under profiles/ -- whatever tier or round produced it -- and the shares must add up."""
+    import glob
+    import os
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import launch_shares
+    lists = sorted(glob.glob(os.path.join(root, "profiles", "r0*_launches_bench_*.csv")))
+    assert lists, "no launch list committed under profiles/"
+    for path in lists:
+        res = launch_shares.shares(path)
+        assert res["launches_per_step"] >= 100, path          # a 12-block forward, not one block
+        assert abs(sum(v["share"] for v in res["by_kernel"].values()) - 1.0) < 1e-9, path
+
+
+def test_bind_host_to_device_never_raises():
+    """pipeline.bind_host_to_device: returns the CPU list it bound to or None (no GPU / no sysfs topology); never raises and
+    never leaves the process with an empty affinity mask."""
+    import os
+    from msfno_b200.pipeline import bind_host_to_device
+    before = os.sched_getaffinity(0)
+    try:
+        got = bind_host_to_device("cuda:0")
+        assert got is None or isinstance(got, str)
+        assert len(os.sched_getaffinity(0)) >= 1
+    finally:
+        os.sched_setaffinity(0, before)

@@ -17,28 +17,51 @@ def run(dev, rank, world, max_over_ranks, sync_all, steps=10, nlat=1441, nlon=28
     """SHT + ISHT round trip on an initialised process group (world may be 1); returns the result dict (all ranks)."""
     sht = msfno_b200.RealSHT(nlat, nlon, lmax=L, mmax=M, grid="equiangular").float().to(dev)
     isht = msfno_b200.InverseRealSHT(nlat, nlon, lmax=L, mmax=M, grid="equiangular").float().to(dev)
-    dsht = D.DistributedSHT(nlat, nlon, L, M, lambda nloc: D.CudaStages(nlat, nloc, nlon, L, M, sht.weights, isht.pct, dev))
+    def stages(nloc):
+        return D.CudaStages(nlat, nloc, nlon, L, M, sht.weights, isht.pct, dev)
+
+    def roundtrips(dsht, n):
+        for _ in range(n):
+            pm = dsht.forward_packed(x)
+            y = dsht.inverse_packed(pm.transpose(1, 2).contiguous())
+        return y
+
+    def timed(dsht):
+        with torch.no_grad():
+            roundtrips(dsht, 3)
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            y = roundtrips(dsht, steps)
+            e1.record()
+            sync_all()
+        return max_over_ranks(e0.elapsed_time(e1) / steps), y
+
+    # exchange engines: "peer" = direct NVLink stores into the peers' operand buffers (csrc/peer.cu, the default here),
+    # "nccl" = all_to_all_single + one pack / unpack launch per direction
+    dsht = D.DistributedSHT(nlat, nlon, L, M, stages, peer_exchange=False)
     x = torch.randn(B, C, dsht.nlat_loc, nlon, device=dev)
-    with torch.no_grad():
-        for _ in range(3):
-            pm = dsht.forward_packed(x)
-            y = dsht.inverse_packed(pm.transpose(1, 2).contiguous())
-        sync_all()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            pm = dsht.forward_packed(x)
-            y = dsht.inverse_packed(pm.transpose(1, 2).contiguous())
-        e1.record()
-        sync_all()
-    ms = max_over_ranks(e0.elapsed_time(e1) / steps)
+    ms_nccl, y = timed(dsht)
+    ms, engine, peer_err = ms_nccl, "nccl", None
+    if world > 1 and B == 1:
+        try:
+            dp = D.DistributedSHT(nlat, nlon, L, M, stages, peer_exchange=True)
+            ms_peer, y2 = timed(dp)
+            dp.peer.check()
+            same = bool(torch.equal(y, y2))
+            dp.peer.close()
+            ms, engine = ms_peer, "peer"
+        except Exception as e:   # no IPC / no P2P between the ranks: the NCCL engine is the result
+            peer_err = repr(e)
     gb = 2 * (4 * B * C * nlat * nlon + 8 * B * C * L * M + 4 * M * L * nlat) / 1e9
     # all-to-all payload of one direction: the truncated spectrum [B][mlim][2C][nlat] fp32; (world - 1) / world of it
     # crosses NVLink
     payload = 4.0 * B * min(L, M) * 2 * C * nlat
     wire = payload * (world - 1) / world
     return {"config": "configs[4] (A): sharded SHT + ISHT round trip, %d x %d, C = %d, lmax = %d" % (nlat, nlon, C, L), "n_gpus": world,
-            "ms_per_roundtrip": ms, "algorithmic_GB": gb, "aggregate_GBps": gb / ms * 1e3,
+            "exchange": engine, "ms_per_roundtrip": ms, "ms_per_roundtrip_nccl_exchange": ms_nccl,
+            "peer_result_bit_identical_to_nccl": same if engine == "peer" else None, "peer_exchange_error": peer_err,
+            "algorithmic_GB": gb, "aggregate_GBps": gb / ms * 1e3,
             "all_to_all_payload_MB_per_direction": payload / 1e6, "nvlink_MB_per_direction": wire / 1e6,
             "finite": bool(torch.isfinite(y).all())}
 
