@@ -148,10 +148,11 @@ int msfno_lat_segments(int gather, float* flat, float* full, long rows, int pad_
  * src[(src_row0 + r) * src_pitch + src_col0 + j] to dst[(dst_row0 + r) * dst_pitch + dst_col0 + j] and zero-fills the
  * zero_tail columns behind them; dst is typically a peer mapping, so the transpose between the latitude-sharded longitude
  * stage and the order-sharded Legendre stage is a direct NVLink store into the consumer's operand buffer.
- * msfno_peer_barrier: all `world` ranks call it with the same increasing `epoch`; flags[r] is (this rank's mapping of)
- * rank r's flag array of `world` unsigned ints, zero at start.  Returns when every rank has arrived AND the peer stores
- * issued before the barrier on each rank are visible; *timed_out (device int) is set instead of hanging if a peer never
- * arrives.  `blocks` and `flags` are HOST arrays. */
+ * msfno_peer_barrier: all `world` ranks call it the same number of times; flags[r] is (this rank's mapping of) rank r's
+ * flag array of `world` unsigned ints, zero at start; `state` is this rank's own device array of two unsigned ints, zero
+ * at start: state[1] counts the barriers (the epoch is kept on the device, so a captured CUDA graph replays correctly),
+ * state[0] is set if a peer never arrived (bounded spin instead of a hung GPU).  Completes when every rank has arrived
+ * AND the peer stores issued before the barrier on each rank are visible.  `blocks` and `flags` are HOST arrays. */
 #define MSFNO_MAX_PEERS 16
 typedef struct msfno_peer_block {
   float* dst;
@@ -165,8 +166,7 @@ int msfno_peer_free(void* ptr);
 int msfno_peer_open(const void* handle64, void** ptr);
 int msfno_peer_close(void* ptr);
 int msfno_peer_block_copy(const float* src, int nblocks, const msfno_peer_block* blocks, void* stream);
-int msfno_peer_barrier(unsigned int* const* flags, int rank, int world, unsigned int epoch, int* timed_out,
-                       void* stream);
+int msfno_peer_barrier(unsigned int* const* flags, int rank, int world, unsigned int* state, void* stream);
 
 /* ---- coefficient layout changes (public boundary of RealSHT / InverseRealSHT) ------------
  * replaces: the zeros()+slice-assign in RealSHT.forward, view_as_real/complex shuffles and the

@@ -69,7 +69,7 @@ _SIGS = {
     "msfno_peer_open": (c_int, [_P, ctypes.POINTER(c_void_p)]),
     "msfno_peer_close": (c_int, [_P]),
     "msfno_peer_block_copy": (c_int, [_P, c_int, _P, _P]),
-    "msfno_peer_barrier": (c_int, [_P, c_int, c_int, ctypes.c_uint, _P, _P]),
+    "msfno_peer_barrier": (c_int, [_P, c_int, c_int, _P, _P]),
     "msfno_coef_relayout": (c_int, [_P, _P, c_int, _P, c_int, c_int, c_int, _P]),
     "msfno_specconv_ws_floats": (ctypes.c_size_t, [_P, c_int, c_int, c_int]),
     "msfno_specconv_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, _P]),

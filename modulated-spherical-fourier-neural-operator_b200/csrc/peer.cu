@@ -26,7 +26,10 @@ struct BlockSet {
   msfno_peer_block b[MSFNO_MAX_PEERS];
 };
 
-// grid = (row chunks, blocks): warp per row, lanes along the latitude-contiguous columns
+// grid = (row chunks, blocks): warp per row, lanes along the latitude-contiguous columns.  VEC: every offset, pitch and
+// count is a multiple of four floats and both bases are 16-byte aligned (the latitude split of DistributedSHT is aligned
+// to four rows for this) -- 16-byte loads and NVLink stores.
+template <bool VEC>
 __global__ void peer_block_copy_kernel(const float* __restrict__ src, BlockSet bs) {
   const msfno_peer_block& k = bs.b[blockIdx.y];
   if (!k.dst || k.rows <= 0) return;
@@ -35,7 +38,13 @@ __global__ void peer_block_copy_kernel(const float* __restrict__ src, BlockSet b
   for (long long r = (long long)blockIdx.x * nw + warp; r < k.rows; r += (long long)gridDim.x * nw) {
     const float* s = src + (k.src_row0 + r) * k.src_pitch + k.src_col0;
     float* d = k.dst + (k.dst_row0 + r) * k.dst_pitch + k.dst_col0;
-    for (int j = lane; j < nfill; j += 32) d[j] = j < ncopy ? s[j] : 0.0f;
+    if (VEC) {
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      float4* d4 = reinterpret_cast<float4*>(d);
+      for (int j = lane; j < (nfill >> 2); j += 32) d4[j] = (4 * j < ncopy) ? s4[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      for (int j = lane; j < nfill; j += 32) d[j] = j < ncopy ? s[j] : 0.0f;
+    }
   }
 }
 
@@ -43,7 +52,14 @@ __global__ void peer_block_copy_kernel(const float* __restrict__ src, BlockSet b
 // GPU wrote before -- including the stores of earlier kernels in the stream -- is visible to a peer that has seen the
 // flag), then wait until that peer has published the same epoch here.  The spin is bounded: a peer that never arrives
 // (crashed process) raises an error flag instead of hanging the GPU.
-__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int world, unsigned int epoch, int* timed_out) {
+// The epoch lives in device memory (state[1], incremented here): the launch carries no per-call host value, so a
+// captured CUDA graph of the exchange replays correctly.
+__global__ void peer_barrier_kernel(PeerFlags pf, int rank, int world, unsigned int* state) {
+  __shared__ unsigned int epoch_s;
+  if (threadIdx.x == 0) epoch_s = ++state[1];
+  __syncthreads();
+  const unsigned int epoch = epoch_s;
+  int* timed_out = reinterpret_cast<int*>(state);
   const int r = threadIdx.x;
   if (r >= world) return;
   __threadfence_system();
@@ -105,6 +121,7 @@ int msfno_peer_block_copy(const float* src, int nblocks, const msfno_peer_block*
   BlockSet bs{};
   bs.n = nblocks;
   long long maxrows = 0;
+  bool vec = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
   for (int i = 0; i < nblocks; ++i) {
     const msfno_peer_block& k = blocks[i];
     if (k.rows < 0 || k.cols < 0 || k.zero_tail < 0 || k.src_pitch < k.src_col0 + k.cols || k.dst_pitch < k.dst_col0 + k.cols + k.zero_tail ||
@@ -112,25 +129,28 @@ int msfno_peer_block_copy(const float* src, int nblocks, const msfno_peer_block*
       return record_error(MSFNO_ERR_BAD_SHAPE, "peer_block_copy: bad block");
     bs.b[i] = k;
     if (k.rows > maxrows) maxrows = k.rows;
+    if (k.rows > 0 && ((reinterpret_cast<uintptr_t>(k.dst) & 15) || ((k.cols | k.zero_tail | k.src_col0 | k.src_pitch | k.dst_col0 | k.dst_pitch) & 3)))
+      vec = false;
   }
   if (maxrows == 0) return MSFNO_OK;
   long long chunks = (maxrows + 7) / 8;
   if (chunks > 148 * 4) chunks = 148 * 4;
-  peer_block_copy_kernel<<<dim3((unsigned)chunks, nblocks), 256, 0, (cudaStream_t)stream>>>(src, bs);
+  if (vec) peer_block_copy_kernel<true><<<dim3((unsigned)chunks, nblocks), 256, 0, (cudaStream_t)stream>>>(src, bs);
+  else peer_block_copy_kernel<false><<<dim3((unsigned)chunks, nblocks), 256, 0, (cudaStream_t)stream>>>(src, bs);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
 }
 
-int msfno_peer_barrier(unsigned int* const* flags, int rank, int world, unsigned int epoch, int* timed_out, void* stream) {
-  if (!flags || !timed_out || world < 1 || world > MSFNO_MAX_PEERS || rank < 0 || rank >= world)
+int msfno_peer_barrier(unsigned int* const* flags, int rank, int world, unsigned int* state, void* stream) {
+  if (!flags || !state || world < 1 || world > MSFNO_MAX_PEERS || rank < 0 || rank >= world)
     return record_error(MSFNO_ERR_BAD_SHAPE, "peer_barrier: bad argument");
   PeerFlags pf{};
   for (int r = 0; r < world; ++r) {
     if (!flags[r]) return record_error(MSFNO_ERR_BAD_SHAPE, "peer_barrier: missing flag buffer");
     pf.flags[r] = flags[r];
   }
-  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, rank, world, epoch, timed_out);
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(pf, rank, world, state);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

@@ -32,12 +32,17 @@ def shard_members(n_members, world_size, rank):
     return slice(lo, lo + base + (1 if rank < rem else 0))
 
 
-def split_even(n, parts):
-    """Boundaries [b_0=0, ..., b_parts=n] of a contiguous split with sizes differing by at most one."""
-    base, rem = divmod(n, parts)
+def split_even(n, parts, align=1):
+    """Boundaries [b_0=0, ..., b_parts=n] of a contiguous split with sizes differing by at most one -- in units of `align`
+    (inner boundaries are multiples of it; the last part takes the remainder)."""
+    if n < align * parts:        # too few rows for aligned shares: nobody may end up empty
+        align = 1
+    units = (n + align - 1) // align
+    base, rem = divmod(units, parts)
     out = [0]
     for r in range(parts):
-        out.append(out[-1] + base + (1 if r < rem else 0))
+        out.append(min(n, out[-1] + align * (base + (1 if r < rem else 0))))
+    out[-1] = n
     return out
 
 
@@ -211,49 +216,45 @@ class PeerExchange:
         self.A = torch.as_tensor(_DevArray(own[0], self.nA), device=device)
         self.Bf = torch.as_tensor(_DevArray(own[1], self.nB), device=device)
         self.flag_ptrs = (ctypes.c_void_p * self.world)(*[m[2] for m in self.maps])
-        self.timed_out = torch.zeros(1, dtype=torch.int32, device=device)
-        self.epoch = 0
+        self.state = torch.zeros(2, dtype=torch.int32, device=device)     # [a barrier timed out, barriers so far]
+        # the block lists are static: built once, so a direction costs three launches and no Python object churn
+        d, C2 = dsht, 2 * C
+        n_me, padl, mloc = d.lat_hi - d.lat_lo, self.pads[self.rank], d.m_hi - d.m_lo
+        fwd = [_PeerBlock(self.maps[s][0], (d.m_bounds[s + 1] - d.m_bounds[s]) * C2, n_me, 0, d.m_bounds[s] * C2, 0, padl,
+                          0, d.lat_lo, self.padN) for s in range(self.world)]
+        inv = [_PeerBlock(self.maps[s][1], mloc * C2, d.lat_bounds[s + 1] - d.lat_bounds[s],
+                          self.pads[s] - (d.lat_bounds[s + 1] - d.lat_bounds[s]), 0, d.lat_bounds[s], self.padN, d.m_lo * C2, 0,
+                          self.pads[s]) for s in range(self.world)]
+        self.blocks_fwd = (_PeerBlock * self.world)(*fwd)
+        self.blocks_inv = (_PeerBlock * self.world)(*inv)
+        self.A_view = self.A.view(1, max(mloc, 1), C2, self.padN)[:, :mloc]
+        self.B_view = self.Bf.view(1, d.mlim, C2, padl)
+        self.mloc = mloc
         dist.barrier(group=self.group)      # every mapping exists before anyone stores through one
 
-    def _barrier(self):
-        self.epoch += 1
-        _lib.check(_lib.lib.msfno_peer_barrier(self.flag_ptrs, self.rank, self.world, self.epoch, self.timed_out.data_ptr(),
-                                               torch.cuda.current_stream().cuda_stream), "peer_barrier")
-
-    def _copy(self, src, blocks):
-        arr = (_PeerBlock * len(blocks))(*blocks)
-        _lib.check(_lib.lib.msfno_peer_block_copy(src.data_ptr(), len(blocks), arr, torch.cuda.current_stream().cuda_stream),
-                   "peer_block_copy")
+    def _barrier(self, st):
+        _lib.check(_lib.lib.msfno_peer_barrier(self.flag_ptrs, self.rank, self.world, self.state.data_ptr(), st), "peer_barrier")
 
     def forward(self, Xt_loc):
         """Xt_loc [1][mlim][2C][pad(nlat_loc)] (this rank's latitudes, every order) -> view of A [1][mloc][2C][pad(nlat)]."""
-        d, C2 = self.d, 2 * self.C
-        n_me, padl = d.lat_hi - d.lat_lo, self.pads[self.rank]
-        blocks = [_PeerBlock(self.maps[s][0], (d.m_bounds[s + 1] - d.m_bounds[s]) * C2, n_me, 0, d.m_bounds[s] * C2, 0, padl,
-                             0, d.lat_lo, self.padN) for s in range(self.world)]
-        self._barrier()                      # every peer has finished reading its A of the previous call
-        self._copy(Xt_loc, blocks)
-        self._barrier()                      # every peer's stores into MY A are visible
-        return self.A.view(1, max(d.m_hi - d.m_lo, 1), C2, self.padN)[:, :d.m_hi - d.m_lo]
+        st = torch.cuda.current_stream().cuda_stream
+        self._barrier(st)                    # every peer has finished reading its A of the previous call
+        _lib.check(_lib.lib.msfno_peer_block_copy(Xt_loc.data_ptr(), self.world, self.blocks_fwd, st), "peer_block_copy")
+        self._barrier(st)                    # every peer's stores into MY A are visible
+        return self.A_view
 
     def inverse(self, Yt):
         """Yt [1][mloc][2C][pad(nlat)] (this rank's orders, every latitude) -> view of Bf [1][mlim][2C][pad(nlat_loc)]."""
-        d, C2 = self.d, 2 * self.C
-        mloc = d.m_hi - d.m_lo
-        blocks = []
-        for s in range(self.world):
-            n_s = d.lat_bounds[s + 1] - d.lat_bounds[s]
-            blocks.append(_PeerBlock(self.maps[s][1], mloc * C2, n_s, self.pads[s] - n_s, 0, d.lat_bounds[s], self.padN,
-                                     d.m_lo * C2, 0, self.pads[s]))
-        self._barrier()
-        if mloc > 0:
-            self._copy(Yt, blocks)
-        self._barrier()
-        return self.Bf.view(1, d.mlim, C2, self.pads[self.rank])
+        st = torch.cuda.current_stream().cuda_stream
+        self._barrier(st)
+        if self.mloc > 0:
+            _lib.check(_lib.lib.msfno_peer_block_copy(Yt.data_ptr(), self.world, self.blocks_inv, st), "peer_block_copy")
+        self._barrier(st)
+        return self.B_view
 
     def check(self):
         """Synchronises; raises if a barrier gave up waiting for a peer."""
-        if int(self.timed_out.item()) != 0:
+        if int(self.state[0].item()) != 0:
             raise RuntimeError("PeerExchange: a rank never arrived at a peer barrier")
 
     def close(self):
@@ -264,7 +265,7 @@ class PeerExchange:
             if r != self.rank:
                 for p in ptrs:
                     lib.msfno_peer_close(p)
-        self.A = self.Bf = None
+        self.A = self.Bf = self.A_view = self.B_view = None
         for p in self.own:
             lib.msfno_peer_free(p)
         self.maps, self.own = [], []
@@ -286,7 +287,8 @@ class DistributedSHT:
         self.world = dist.get_world_size(group)
         self.nlat, self.nlon, self.lmax, self.mmax = nlat, nlon, lmax, mmax
         self.mlim = min(lmax, mmax)
-        self.lat_bounds = split_even(nlat, self.world)
+        # latitude boundaries on multiples of four rows: every block of the lat<->m exchange is then 16-byte aligned
+        self.lat_bounds = split_even(nlat, self.world, align=4)
         self.m_bounds = split_orders(lmax, mmax, self.world)
         self.poff, self.plen4, self.P = packed_offsets(lmax, mmax)
         self.lat_lo, self.lat_hi = self.lat_bounds[self.rank], self.lat_bounds[self.rank + 1]

@@ -42,13 +42,59 @@ def run(dev, rank, world, max_over_ranks, sync_all, steps=10, nlat=1441, nlon=28
     dsht = D.DistributedSHT(nlat, nlon, L, M, stages, peer_exchange=False)
     x = torch.randn(B, C, dsht.nlat_loc, nlon, device=dev)
     ms_nccl, y = timed(dsht)
-    ms, engine, peer_err = ms_nccl, "nccl", None
+    ms, engine, peer_err, ms_graph, graph_same, phases = ms_nccl, "nccl", None, None, None, None
     if world > 1 and B == 1:
         try:
             dp = D.DistributedSHT(nlat, nlon, L, M, stages, peer_exchange=True)
             ms_peer, y2 = timed(dp)
             dp.peer.check()
             same = bool(torch.equal(y, y2))
+            # per-phase device times (events between the six phases of a round trip; max over ranks per phase)
+            try:
+                st_, pe = dp.stages, dp.peer
+                p0_, p1_ = dp.pos_range()
+                names = ["fft_fwd", "exchange_fwd", "legendre_analysis", "pm_to_cm", "legendre_synthesis", "exchange_inv", "fft_inv"]
+                acc = [0.0] * len(names)
+                with torch.no_grad():
+                    for it in range(steps + 1):
+                        ev = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+                        ev[0].record()
+                        Xl = st_.fft_fwd(x); ev[1].record()
+                        Xf = pe.forward(Xl); ev[2].record()
+                        pmx = st_.legendre_fwd(Xf, dp.m_lo, dp.m_hi, p1_ - p0_); ev[3].record()
+                        cmx = pmx.transpose(1, 2).contiguous(); ev[4].record()
+                        Yf = st_.legendre_inv(cmx, dp.m_lo, dp.m_hi); ev[5].record()
+                        Yl = pe.inverse(Yf); ev[6].record()
+                        st_.fft_inv(Yl, B, C); ev[7].record()
+                        torch.cuda.synchronize()
+                        if it > 0:
+                            for i in range(len(names)):
+                                acc[i] += ev[i].elapsed_time(ev[i + 1])
+                phases = {n: max_over_ranks(a_ / steps) for n, a_ in zip(names, acc)}
+            except Exception as e:
+                phases = {"error": repr(e)}
+            # the same round trip as ONE CUDA graph (the barrier epoch lives on the device, so the graph replays): what the
+            # GPUs need without the per-launch host work of 14 small launches per round trip
+            try:
+                with torch.no_grad():
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        yg = roundtrips(dp, 1)
+                    for _ in range(2):
+                        g.replay()
+                    sync_all()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        g.replay()
+                    e1.record()
+                    sync_all()
+                ms_graph = max_over_ranks(e0.elapsed_time(e1) / steps)
+                dp.peer.check()
+                graph_same = bool(torch.equal(y, yg))
+                del g
+            except Exception as e:
+                ms_graph, graph_same = None, repr(e)
             dp.peer.close()
             ms, engine = ms_peer, "peer"
         except Exception as e:   # no IPC / no P2P between the ranks: the NCCL engine is the result
@@ -61,6 +107,8 @@ def run(dev, rank, world, max_over_ranks, sync_all, steps=10, nlat=1441, nlon=28
     return {"config": "configs[4] (A): sharded SHT + ISHT round trip, %d x %d, C = %d, lmax = %d" % (nlat, nlon, C, L), "n_gpus": world,
             "exchange": engine, "ms_per_roundtrip": ms, "ms_per_roundtrip_nccl_exchange": ms_nccl,
             "peer_result_bit_identical_to_nccl": same if engine == "peer" else None, "peer_exchange_error": peer_err,
+            "ms_per_roundtrip_cuda_graph": ms_graph, "graph_result_bit_identical": graph_same,
+            "phases_ms_max_over_ranks": phases,
             "algorithmic_GB": gb, "aggregate_GBps": gb / ms * 1e3,
             "all_to_all_payload_MB_per_direction": payload / 1e6, "nvlink_MB_per_direction": wire / 1e6,
             "finite": bool(torch.isfinite(y).all())}
