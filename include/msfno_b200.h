@@ -248,8 +248,9 @@ int msfno_fold_norm_affine(const float* W, const double* stats, const float* nw,
  * One launch instead of six library element-wise / gemv launches per block. */
 int msfno_mean_carry(const double* stats, long HW, const float* mu, const float* bias2, const float* Wskip, long ldw,
                      const float* skip_bias, float* b2, float* mu_out, float* sb, int B, int C, void* stream);
-/* out = g * gelu'(h), exact (erf) GELU: activation adjoint of the frozen-weight channel-MLP backward (a14) */
-int msfno_gelu_bwd_mul(const float* g, const float* h, float* out, long long n, void* stream);
+/* out = g * gelu'(h), exact (erf) GELU: activation adjoint of the frozen-weight channel-MLP backward (a14);
+ * round_tf32 != 0: rounded to TF32 (nearest) where it is made, as the tensor-core operand of the next GEMM */
+int msfno_gelu_bwd_mul(const float* g, const float* h, float* out, long long n, int round_tf32, void* stream);
 /* y[plane][:] = A[plane]*x[plane][:] + S[plane] */
 int msfno_plane_affine(const float* x, const float* A, const float* S, float* y, int planes, long HW,
                        void* stream);

@@ -87,7 +87,7 @@ _SIGS = {
     "msfno_fold_affine": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "msfno_fold_norm_affine": (c_int, [_P, _P, _P, _P, _P, _P, c_float, c_float, c_long, _P, _P, _P, c_int, c_int, c_int, c_int,
                                        c_int, _P]),
-    "msfno_gelu_bwd_mul": (c_int, [_P, _P, _P, ctypes.c_longlong, _P]),
+    "msfno_gelu_bwd_mul": (c_int, [_P, _P, _P, ctypes.c_longlong, c_int, _P]),
     "msfno_plane_affine": (c_int, [_P, _P, _P, _P, c_int, c_long, _P]),
     "msfno_conv1x1_fwd": (c_int, [_P, c_long, c_int, _P, c_long, c_long, _P, c_long, c_int, _P, c_long, _P, c_long, _P, c_long, _P,
                           c_int, c_int, c_long, c_int, c_int, _P]),

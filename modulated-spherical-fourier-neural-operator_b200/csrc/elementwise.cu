@@ -188,7 +188,15 @@ __global__ void fold_norm_affine_kernel(const float* __restrict__ W, const doubl
   }
 }
 
-// out[i] = g[i] * gelu'(h[i])  (exact erf GELU): the activation's adjoint in the frozen-weight MLP backward
+// out[i] = g[i] * gelu'(h[i])  (exact erf GELU): the activation's adjoint in the frozen-weight MLP backward.  RND: the
+// product is rounded to TF32 (round-to-nearest) where it is made -- it is the tensor-core operand of the next GEMM, and
+// rounding it afterwards cost two more passes over a tensor of 1 GB per sample.
+template <bool RND>
+__device__ __forceinline__ float gelu_bwd_one(float g, float h) {
+  const float v = g * gelu_erf_grad(h);
+  return RND ? rna_tf32_dev(v) : v;
+}
+template <bool RND>
 __global__ void gelu_bwd_mul_kernel(const float* __restrict__ g, const float* __restrict__ h, float* __restrict__ out, long long n) {
   const long long n4 = n >> 2;
   const bool vec = (((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(h) | reinterpret_cast<uintptr_t>(out)) & 15) == 0);
@@ -196,13 +204,13 @@ __global__ void gelu_bwd_mul_kernel(const float* __restrict__ g, const float* __
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
       const float4 a = __ldcs(reinterpret_cast<const float4*>(g) + i), b = __ldcs(reinterpret_cast<const float4*>(h) + i);
       __stcs(reinterpret_cast<float4*>(out) + i,
-             make_float4(a.x * gelu_erf_grad(b.x), a.y * gelu_erf_grad(b.y), a.z * gelu_erf_grad(b.z), a.w * gelu_erf_grad(b.w)));
+             make_float4(gelu_bwd_one<RND>(a.x, b.x), gelu_bwd_one<RND>(a.y, b.y), gelu_bwd_one<RND>(a.z, b.z), gelu_bwd_one<RND>(a.w, b.w)));
     }
     for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-      out[i] = g[i] * gelu_erf_grad(h[i]);
+      out[i] = gelu_bwd_one<RND>(g[i], h[i]);
   } else {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-      out[i] = g[i] * gelu_erf_grad(h[i]);
+      out[i] = gelu_bwd_one<RND>(g[i], h[i]);
   }
 }
 
@@ -384,12 +392,13 @@ int msfno_mean_carry(const double* stats, long HW, const float* mu, const float*
   return MSFNO_OK;
 }
 
-int msfno_gelu_bwd_mul(const float* g, const float* h, float* out, long long n, void* stream) {
+int msfno_gelu_bwd_mul(const float* g, const float* h, float* out, long long n, int round_tf32, void* stream) {
   if (!g || !h || !out || n < 1) return record_error(MSFNO_ERR_BAD_SHAPE, "gelu_bwd_mul: bad argument");
   long long blocks = (n / 4 + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   if (blocks < 1) blocks = 1;
-  gelu_bwd_mul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, h, out, n);
+  if (round_tf32) gelu_bwd_mul_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, h, out, n);
+  else gelu_bwd_mul_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(g, h, out, n);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;

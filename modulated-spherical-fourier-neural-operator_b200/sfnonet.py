@@ -60,6 +60,33 @@ class _FiLMFn(torch.autograd.Function):
         return gx, gg, gb, None
 
 
+class _NormFiLMFn(torch.autograd.Function):
+    """FiLM(A1 y + S1) for a frozen backbone: y is the un-normalised block output, (A1, S1) the pending InstanceNorm affine
+    per plane.  One pass forward ((1 + gamma s) A1 y + (1 + gamma s) S1 + beta s is itself a per-plane affine) instead of a
+    normalisation pass followed by a FiLM pass; the backward returns the gradients of gamma and beta only (nothing
+    before FiLM is trainable) from the plane sums of gy y and gy: one read pass, no gradient tensor written."""
+
+    @staticmethod
+    def forward(ctx, y, A1, S1, gammas, betas, scale):
+        f = 1.0 + gammas * scale
+        out = plane_affine(y, (f * A1).contiguous(), (f * S1 + betas * scale).contiguous())
+        ctx.save_for_backward(y, A1, S1, gammas)
+        ctx.scale = float(scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, gy):
+        y, A1, S1, gammas = ctx.saved_tensors
+        B, C = y.shape[0], y.shape[1]
+        gy = gy.contiguous()
+        gg = torch.empty_like(gammas)
+        gb = torch.empty_like(gammas)
+        check(lib.msfno_film_affine_bwd(ptr(gy), ptr(y), ptr(gammas), ctx.scale, None, ptr(gg), ptr(gb), B, C, y[0, 0].numel(),
+                                        _stream()), "film_bwd")
+        # gg = s sum(gy y), gb = s sum(gy): the normalised activation is A1 y + S1
+        return None, None, None, A1 * gg + S1 * gb, gb, None
+
+
 class FiLM(nn.Module):
     """Feature-wise linear modulation (sfnonet.py:689-697): (1 + gamma*scale) * x + beta*scale."""
 
@@ -157,9 +184,8 @@ class _FrozenMLPFn(torch.autograd.Function):
             W2T = _padded_matrix(w2m.t())                                # [Chid, Cout]
             W1aT = _padded_matrix(w1m.t())                               # [cin, Chid]
             gh = conv1x1(gy, W2T, w2m.shape[0], final=True)              # W2^T g_y
-            check(lib.msfno_gelu_bwd_mul(ptr(gh), ptr(h), ptr(gh), gh.numel(), _stream()), "gelu_bwd_mul")
-            if _precision.get_precision() == "tf32":
-                gh = round_tf32(gh)
+            check(lib.msfno_gelu_bwd_mul(ptr(gh), ptr(h), ptr(gh), gh.numel(), 1 if _precision.get_precision() == "tf32" else 0,
+                                         _stream()), "gelu_bwd_mul")
             gx = conv1x1(gh, W1aT, w1m.shape[0], final=True)
         return gx, None, None, None, None, None, None, None
 
@@ -448,9 +474,11 @@ class FourierNeuralOperatorBlock_Filmed(FourierNeuralOperatorBlock):
                 fusable = self._can_fuse(x)
                 if fusable:
                     y, A1, S1 = self._fused(x, prefilm=True)
-                    xn = plane_affine(y, A1, S1)
             if fusable:
-                xf = self.film(xn, gamma, beta, scale)
+                if type(self.film) is FiLM:
+                    xf = _NormFiLMFn.apply(y, A1, S1, gamma.contiguous().float(), beta.contiguous().float(), scale)
+                else:
+                    xf = self.film(plane_affine(y, A1, S1), gamma, beta, scale)
                 if hasattr(self, "mlp"):
                     xf = self.mlp(xf)
                 return self._tail(xf, x)

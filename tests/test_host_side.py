@@ -188,7 +188,7 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
         "fold_norm_affine": lambda: lib.msfno_fold_norm_affine(None, None, None, None, None, None, 1.0, 1e-6, 10, None, None, None,
                                                                1, 1, 1, 1, 0, None),
         "norm_film_coeffs": lambda: lib.msfno_norm_film_coeffs(None, None, None, None, None, 1.0, 1e-6, None, None, 1, 1, 10, None),
-        "gelu_bwd_mul": lambda: lib.msfno_gelu_bwd_mul(None, None, None, 0, None),
+        "gelu_bwd_mul": lambda: lib.msfno_gelu_bwd_mul(None, None, None, 0, 0, None),
         "mean_carry": lambda: lib.msfno_mean_carry(None, 0, None, None, None, 0, None, None, None, None, 1, 1, None),
         "plane_affine": lambda: lib.msfno_plane_affine(None, None, None, None, 0, 0, None),
     }
