@@ -82,12 +82,12 @@ def test_filmed_net_matches_reference(fl):
     yo.backward(gy)
     got = dict(net.named_parameters())
     for k in ("film_gen.film_head.net.4.weight", "film_gen.film_head.net.1.weight", "decoder.fwd.0.weight"):
-        assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
+        assert rel_l2(got[k].grad, sdo[k].grad) < TOL_FP32, (k, rel_l2(got[k].grad, sdo[k].grad))
     last = cfg["num_layers"] - 1
     k = "blocks.%d.filter_layer.filter.wout" % last
-    assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
+    assert rel_l2(got[k].grad, sdo[k].grad) < TOL_FP32, (k, rel_l2(got[k].grad, sdo[k].grad))
     k = "blocks.%d.filter_layer.filter.w.0" % last
-    assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
+    assert rel_l2(got[k].grad, sdo[k].grad) < TOL_FP32, (k, rel_l2(got[k].grad, sdo[k].grad))
 
 
 def test_filmed_net_frozen_backbone_training_shortcut():
@@ -120,7 +120,7 @@ def test_filmed_net_frozen_backbone_training_shortcut():
     yo.backward(gy)
     got = dict(net.named_parameters())
     for k in ("film_gen.film_head.net.4.weight", "film_gen.film_head.net.1.weight", "film_gen.film_head.net.4.bias"):
-        assert rel_l2(got[k].grad, sdo[k].grad) < 5e-5, k
+        assert rel_l2(got[k].grad, sdo[k].grad) < TOL_FP32, (k, rel_l2(got[k].grad, sdo[k].grad))
     assert got["decoder.fwd.0.weight"].grad is None
 
 
