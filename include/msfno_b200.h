@@ -274,6 +274,8 @@ int msfno_weighted_diff(const float* prd, const float* tar, const float* wlat, c
  * >= Cin zero; w_bstride != 0 selects per-sample weights (InstanceNorm/FiLM affine folded into the conv).
  * x2 / w2 (optional): second input accumulated into the same output (the decoder's concat of x and the big skip).
  * bias (optional, [Cout], bias_bstride 0 or Cout), add (optional, [Cout][HW], add_bstride 0 or Cout*HW).
+ * act_gelu: 0 none, 1 GELU, 2 = activation ADJOINT: y = (conv + bias) * gelu'(add), `add` holding the pre-activation
+ * (the W2^T g (.) gelu'(h) step of the frozen-weight MLP backward without a pass of its own).
  * precision: MSFNO_PREC_FP32 or MSFNO_PREC_TF32, optionally | 2 to round the outputs to TF32 (feeds another MMA). */
 int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const float* w, long ldw, long w_bstride,
                       const float* x2, long x2_bstride, int Cin2, const float* w2, long ldw2, const float* bias,

@@ -52,10 +52,13 @@ def padded_weight(weight, cols=None):
 
 @_lib.on_input_device
 def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, cin2=0, per_sample_w=False,
-            per_sample_bias=False, final=False, w_rounded=False):
+            per_sample_bias=False, final=False, w_rounded=False, gelu_grad_of=None):
     """y = act(conv1x1(x, w) [+ conv1x1(x2, w2)] + bias) + add   for contiguous NCHW fp32 CUDA tensors.
     w: [Cout, ld] (or [B, Cout, ld] with per_sample_w) zero-padded rows; bias [Cout] (or [B, Cout]);
-    add: [B or 1, Cout, H, W]."""
+    add: [B or 1, Cout, H, W].  gelu_grad_of=h [B, Cout, H, W]: y = (conv + bias) * gelu'(h) instead (activation adjoint)."""
+    if gelu_grad_of is not None:
+        assert add is None and not act_gelu
+        add = gelu_grad_of
     B, _, H, W = x.shape
     HW = H * W
     cout = w.shape[-2]
@@ -72,7 +75,7 @@ def conv1x1(x, w, cin, bias=None, act_gelu=False, add=None, x2=None, w2=None, ci
     check(lib.msfno_conv1x1_fwd(ptr(x), x.shape[1] * HW, cin, ptr(w), w.shape[-1], (cout * w.shape[-1]) if per_sample_w else 0,
                                 ptr(x2), (x2.shape[1] * HW) if x2 is not None else 0, cin2, ptr(w2),
                                 w2.shape[-1] if w2 is not None else 0, ptr(bias), cout if per_sample_bias else 0, ptr(add),
-                                add_bs, ptr(y), B, cout, HW, 1 if act_gelu else 0, prec,
+                                add_bs, ptr(y), B, cout, HW, 2 if gelu_grad_of is not None else (1 if act_gelu else 0), prec,
                                 torch.cuda.current_stream().cuda_stream), "conv1x1_fwd")
     return y
 

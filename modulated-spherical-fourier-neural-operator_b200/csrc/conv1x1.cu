@@ -20,7 +20,8 @@ extern "C" int msfno_conv1x1_fwd(const float* x, long x_bstride, int Cin, const 
   // bit 1 of `precision`: round the outputs to TF32 (they feed another tensor-core GEMM)
   const int round_out = (precision >> 1) & 1;
   precision &= 1;
-  if (!x || !w || !y || B < 1 || Cin < 1 || Cout < 1 || HW < 1 || ldw < Cin || (x2 && (!w2 || Cin2 < 1 || ldw2 < Cin2)))
+  if (!x || !w || !y || B < 1 || Cin < 1 || Cout < 1 || HW < 1 || ldw < Cin || (x2 && (!w2 || Cin2 < 1 || ldw2 < Cin2)) ||
+      act_gelu < 0 || act_gelu > 2 || (act_gelu == 2 && !add))
     return record_error(MSFNO_ERR_BAD_SHAPE, "conv1x1_fwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   GemmLaunch g{};

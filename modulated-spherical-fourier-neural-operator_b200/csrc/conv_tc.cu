@@ -196,7 +196,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             v[j + 2] = __uint_as_float(r[jb + j + 2]) + bb.z;
             v[j + 3] = __uint_as_float(r[jb + j + 3]) + bb.w;
           }
-          if (p.act_gelu) {
+          if (p.act_gelu == 1) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = gelu_tanh3(v[j]);
           }
@@ -205,8 +205,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float av[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) av[j] = (j < nv) ? __ldg(ap + (long long)j * p.ldadd) : 0.0f;   // coalesced over lanes
+            if (p.act_gelu == 2) {   // activation adjoint: the operand is the GELU's pre-activation
 #pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += av[j];
+              for (int j = 0; j < 16; ++j) v[j] *= gelu_erf_grad(av[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += av[j];
+            }
           }
           if (p.round_tf32) {
 #pragma unroll

@@ -172,12 +172,12 @@ __global__ void __launch_bounds__(256, 2) gemm_ffma_kernel(GemmLaunch g, int til
         const float bv = g.bias[blockIdx.y * g.sbias + gm];
         v[0] += bv; v[1] += bv; v[2] += bv; v[3] += bv;
       }
-      if (g.act_gelu) { v[0] = gelu_erf(v[0]); v[1] = gelu_erf(v[1]); v[2] = gelu_erf(v[2]); v[3] = gelu_erf(v[3]); }
+      if (g.act_gelu == 1) { v[0] = gelu_erf(v[0]); v[1] = gelu_erf(v[1]); v[2] = gelu_erf(v[2]); v[3] = gelu_erf(v[3]); }
       if (g.add) {
         const float* ap = g.add + blockIdx.y * g.sadd + (long long)gm * g.ldadd + gn;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
-          if (gn + j < N) v[j] += ap[j];
+          if (gn + j < N) v[j] = (g.act_gelu == 2) ? v[j] * gelu_erf_grad(ap[j]) : v[j] + ap[j];   // 2: activation adjoint
       }
       if (g.relu_even) {
         v[0] = fmaxf(v[0], 0.f);

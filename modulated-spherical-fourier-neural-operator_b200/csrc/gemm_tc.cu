@@ -109,16 +109,22 @@ __device__ __forceinline__ void tc_epilogue_chunk(const TcParams& p, const GemmG
   const bool vec = (((grp.d_off | p.ldd) & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.D) & 15) == 0);
   const bool row_ok = row < grp.M;
   const bool full_vec = vec && gn + 31 < grp.N;         // warp-uniform
-  if (p.bias || p.act_gelu) {
+  if (p.bias || p.act_gelu == 1) {
     const float bv = (p.bias && row_ok) ? p.bias[blockIdx.y * p.sbias + row] : 0.0f;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
       float t = v[j] + bv;
-      if (p.act_gelu) t = EXACT ? gelu_erf(t) : gelu_tanh3(t);
+      if (p.act_gelu == 1) t = EXACT ? gelu_erf(t) : gelu_tanh3(t);
       v[j] = t;
     }
   }
-  if (p.add && row_ok) {
+  if (p.add && row_ok && p.act_gelu == 2) {
+    // act_gelu == 2: the `add` operand is the pre-activation of a GELU and MULTIPLIES as gelu'(.) (activation adjoint)
+    const float* arow = p.add + blockIdx.y * p.sadd + (long long)row * p.ldadd;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (gn + j < grp.N) v[j] *= gelu_erf_grad(arow[gn + j]);
+  } else if (p.add && row_ok) {
     const float* arow = p.add + blockIdx.y * p.sadd + (long long)row * p.ldadd;
     if (full_vec && ((p.ldadd | p.sadd) & 3) == 0 && (reinterpret_cast<uintptr_t>(p.add) & 15) == 0) {
 #pragma unroll

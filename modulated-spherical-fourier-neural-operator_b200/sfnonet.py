@@ -183,9 +183,9 @@ class _FrozenMLPFn(torch.autograd.Function):
             w1m = w1.detach().reshape(w1.shape[0], -1).float()[:, :cin]  # [Chid, cin]
             W2T = _padded_matrix(w2m.t())                                # [Chid, Cout]
             W1aT = _padded_matrix(w1m.t())                               # [cin, Chid]
-            gh = conv1x1(gy, W2T, w2m.shape[0], final=True)              # W2^T g_y
-            check(lib.msfno_gelu_bwd_mul(ptr(gh), ptr(h), ptr(gh), gh.numel(), 1 if _precision.get_precision() == "tf32" else 0,
-                                         _stream()), "gelu_bwd_mul")
+            # gelu'(h) * (W2^T g_y) in the conv's epilogue (TF32-rounded there in the tensor-core tier: it feeds the next GEMM)
+            gh = conv1x1(gy, W2T, w2m.shape[0], gelu_grad_of=h)
+            del h
             gx = conv1x1(gh, W1aT, w1m.shape[0], final=True)
         return gx, None, None, None, None, None, None, None
 
