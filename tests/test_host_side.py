@@ -190,6 +190,11 @@ def test_c_abi_rejects_bad_arguments_without_a_gpu():
         "norm_film_coeffs": lambda: lib.msfno_norm_film_coeffs(None, None, None, None, None, 1.0, 1e-6, None, None, 1, 1, 10, None),
         "gelu_bwd_mul": lambda: lib.msfno_gelu_bwd_mul(None, None, None, 0, 0, None),
         "mean_carry": lambda: lib.msfno_mean_carry(None, 0, None, None, None, 0, None, None, None, None, 1, 1, None),
+        "lat_segments": lambda: lib.msfno_lat_segments(1, None, None, 0, 0, 0, 0, None, None, None),
+        "peer_alloc": lambda: lib.msfno_peer_alloc(0, None, None),
+        "peer_open": lambda: lib.msfno_peer_open(None, None),
+        "peer_block_copy": lambda: lib.msfno_peer_block_copy(None, 0, None, None),
+        "peer_barrier": lambda: lib.msfno_peer_barrier(None, 0, 0, None, None),
         "plane_affine": lambda: lib.msfno_plane_affine(None, None, None, None, 0, 0, None),
     }
     for name, call in cases.items():
