@@ -161,6 +161,22 @@ typedef struct msfno_peer_block {
   long long src_row0, src_col0, src_pitch;
   long long dst_row0, dst_col0, dst_pitch;
 } msfno_peer_block;
+/* The exchange FUSED into the longitude stage (B = 1, four-step FFT sizes): msfno_fft_stage_peer runs msfno_fft_stage on
+ * this rank's latitudes with the lat-contiguous intermediate living in the ranks' peer-mapped operand buffers --
+ * inverse = 0: x [C][nlat_loc][nlon] -> every (m, re/im) row segment is stored straight into buf[owner of m] (NVLink
+ * stores from the FFT kernel's epilogue; no local intermediate, no copy kernel, no collective);
+ * inverse = 1: the staging fill of the inverse FFT loads its segments from buf[owner of m] -> y [C][nlat_loc][nlon].
+ * buf[s]: rank s's buffer [m_bounds[s+1] - m_bounds[s]][2C][pitch] over all latitudes, this rank's at column lat_lo.
+ * Bracket with msfno_peer_barrier exactly like msfno_peer_block_copy. */
+typedef struct msfno_peer_map {
+  int world;
+  int m_bounds[MSFNO_MAX_PEERS + 1];
+  float* buf[MSFNO_MAX_PEERS];
+  int pitch;
+  int lat_lo;
+} msfno_peer_map;
+int msfno_fft_stage_peer(msfno_plan* plan, int inverse, const float* x, float* y, const msfno_peer_map* map, int C,
+                         void* stream);
 int msfno_peer_alloc(size_t bytes, void** ptr, void* handle64);
 int msfno_peer_free(void* ptr);
 int msfno_peer_open(const void* handle64, void** ptr);

@@ -64,6 +64,7 @@ _SIGS = {
     "msfno_fft_stage": (c_int, [_P, c_int, c_int, _P, _P, c_int, c_int, _P]),
     "msfno_legendre_stage": (c_int, [_P, c_int, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "msfno_lat_segments": (c_int, [c_int, _P, _P, c_long, c_int, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int), _P]),
+    "msfno_fft_stage_peer": (c_int, [_P, c_int, _P, _P, _P, c_int, _P]),
     "msfno_peer_alloc": (c_int, [c_size_t, ctypes.POINTER(c_void_p), _P]),
     "msfno_peer_free": (c_int, [_P]),
     "msfno_peer_open": (c_int, [_P, ctypes.POINTER(c_void_p)]),

@@ -25,7 +25,8 @@ template <int P1, int P2, int RW, int NZ2, int RT, bool TWG, bool DB>
 __global__ void __launch_bounds__(256, 1)
 rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __restrict__ g_tw,
               const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ in_scale,
-              const float* __restrict__ in_shift, int nlat, int mlim, int kpad, int C, int zero_imag, int round_tf32) {
+              const float* __restrict__ in_shift, int nlat, int mlim, int kpad, int C, int zero_imag, int round_tf32,
+              const PeerMapDev pm) {
   constexpr int H = P1 * P2, NLON = 2 * H, WP = WorkPitch<P2>::value;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nw = blockDim.x >> 5;
@@ -150,7 +151,15 @@ rfft2d_kernel(const float* __restrict__ x, float* __restrict__ Xt, const cf* __r
     if (lane >= RT) continue;   // (RT < 32: half-segment stores)
     float v = (lane < nvalid) ? ostage[seg * OST2 + lane] : 0.0f;
     if (round_tf32) { uint32_t rr; asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(rr) : "f"(v)); v = __uint_as_float(rr); }
-    Xt[(((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane] = v;
+    if (pm.world) {
+      // sharded transform: the segment goes straight into the operand buffer of the rank that owns order m (an NVLink
+      // store through its CUDA IPC mapping) -- the lat<->m exchange is this kernel's epilogue, not a collective
+      int s = 0;
+      while (s + 1 < pm.world && m >= pm.mb[s + 1]) ++s;
+      if (lane < nvalid) pm.buf[s][((size_t)(m - pm.mb[s]) * (2 * C) + 2 * c + ri) * pm.pitch + pm.lat_lo + k0 + lane] = v;
+    } else {
+      Xt[(((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane] = v;
+    }
   }
 }
 
@@ -160,7 +169,7 @@ __global__ void __launch_bounds__(256, 1)
 irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __restrict__ g_tw,
                const cf* __restrict__ g_tw2, const float* __restrict__ mscale, const float* __restrict__ skip,
                const float* __restrict__ out_scale, double* __restrict__ stats, int nlat, int mlim, int kpad, int C,
-               int act_gelu) {
+               int act_gelu, const PeerMapDev pm) {
   constexpr int H = P1 * P2, NLON = 2 * H, WP = WorkPitch<P2>::value;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int nw = blockDim.x >> 5;
@@ -197,7 +206,14 @@ irfft2d_kernel(const float* __restrict__ Yt, float* __restrict__ y, const cf* __
     const int m = seg >> 1, ri = seg & 1;
     if (lane >= RT) continue;
     if (lane < nvalid) {
-      const float* src = Yt + (((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane;
+      const float* src;
+      if (pm.world) {   // sharded transform: order m is read from its owner's buffer (NVLink load through the IPC mapping)
+        int s = 0;
+        while (s + 1 < pm.world && m >= pm.mb[s + 1]) ++s;
+        src = pm.buf[s] + ((size_t)(m - pm.mb[s]) * (2 * C) + 2 * c + ri) * pm.pitch + pm.lat_lo + k0 + lane;
+      } else {
+        src = Yt + (((size_t)b * mlim + m) * (2 * C) + 2 * c + ri) * kpad + k0 + lane;
+      }
       asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(istage + seg * OST2 + lane)), "l"(src) : "memory");
     } else {
       istage[seg * OST2 + lane] = 0.0f;
@@ -312,7 +328,7 @@ static bool pick_warps2(size_t fixed, size_t per_warp, int max_groups, int* nwar
 
 template <int P1, int P2, int RW, int NZ2 = 0, int RT = 32, bool TWG = false, bool DB = true>
 static int launch_fwd(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
-                      const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st) {
+                      const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st, const PeerMapDev& pm) {
   constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
   const int XS = xs_size(H, NZ2 > 0 ? NZ2 * P1 : p->mlim);
   const size_t fixed = sizeof(cf) * ((TWG ? 0 : H) + p->mlim + 1) + sizeof(float) * 2 * p->mlim * (RT + 1);
@@ -325,7 +341,7 @@ static int launch_fwd(const msfno_plan* p, const float* x, float* Xt, const floa
   dim3 grid((p->nlat + RT - 1) / RT, B * C);
   kern<<<grid, nw * 32, smem, st>>>(x, Xt, reinterpret_cast<const cf*>(p->d_tw), reinterpret_cast<const cf*>(p->d_tw2),
                                     mscale, in_scale, in_shift, p->nlat, p->mlim, p->kpad, C, zero_imag,
-                                    (p->precision == MSFNO_PREC_TF32 && !zero_imag) ? 1 : 0);
+                                    (p->precision == MSFNO_PREC_TF32 && !zero_imag) ? 1 : 0, pm);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
@@ -333,7 +349,7 @@ static int launch_fwd(const msfno_plan* p, const float* x, float* Xt, const floa
 
 template <int P1, int P2, int RW, int NZ = 0, int RT = 32, bool TWG = false>
 static int launch_inv(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
-                      const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st) {
+                      const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st, const PeerMapDev& pm) {
   constexpr int H = P1 * P2, WP = WorkPitch<P2>::value;
   const size_t fixed = sizeof(cf) * ((TWG ? 0 : H) + p->mlim + 1) + sizeof(float) * 2 * p->mlim * (RT + 1) + 16 * 8 + sizeof(float) * p->mlim + 128;
   const size_t per_warp = sizeof(cf) * ((size_t)RW * P1 * WP + (size_t)RW * H);
@@ -349,7 +365,7 @@ static int launch_inv(const msfno_plan* p, const float* Yt, float* y, const floa
   MSFNO_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p->nlat + RT - 1) / RT, B * C);
   kern<<<grid, nw * 32, smem, st>>>(Yt, y, reinterpret_cast<const cf*>(p->d_tw), reinterpret_cast<const cf*>(p->d_tw2),
-                                    mscale, skip, out_scale, stats, p->nlat, p->mlim, p->kpad, C, act_gelu);
+                                    mscale, skip, out_scale, stats, p->nlat, p->mlim, p->kpad, C, act_gelu, pm);
   count_launch();
   MSFNO_CUDA_OK(cudaGetLastError());
   return MSFNO_OK;
@@ -358,31 +374,35 @@ static int launch_inv(const msfno_plan* p, const float* Yt, float* y, const floa
 bool fft2d_supported(int nlon) { return nlon == 1440 || nlon == 240 || nlon == 2880; }
 
 int launch_rfft2d(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
-                  const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st) {
+                  const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st, const PeerMapDev* pmp) {
+  PeerMapDev pm{};
+  if (pmp) pm = *pmp;
   switch (p->nlon) {
     case 1440:
-      if (p->mlim <= 5 * 24) return launch_fwd<24, 30, 1, 5>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
-      return launch_fwd<24, 30, 1>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
-    case 240: return launch_fwd<15, 8, 4>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
+      if (p->mlim <= 5 * 24) return launch_fwd<24, 30, 1, 5>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st, pm);
+      return launch_fwd<24, 30, 1>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st, pm);
+    case 240: return launch_fwd<15, 8, 4>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st, pm);
     case 2880:   // 0.125 degree grid: eight warps per SM (see RT above); second-step outputs pruned to the kept orders
       // H = 1440 = 48 x 30: step 1 is ONE pass of 30 lane tasks (36 x 40 needs two passes of 40 and of 36 tasks, the
       // second with 8 / 4 active lanes)
-      if (p->mlim <= 5 * 48) return launch_fwd<48, 30, 1, 5, 16, true, false>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
-      return launch_fwd<48, 30, 1, 0, 16, true, false>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st);
+      if (p->mlim <= 5 * 48) return launch_fwd<48, 30, 1, 5, 16, true, false>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st, pm);
+      return launch_fwd<48, 30, 1, 0, 16, true, false>(p, x, Xt, mscale, zero_imag, in_scale, in_shift, B, C, st, pm);
     default: return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT: unsupported nlon");
   }
 }
 
 int launch_irfft2d(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
-                   const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st) {
+                   const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st, const PeerMapDev* pmp) {
+  PeerMapDev pm{};
+  if (pmp) pm = *pmp;
   switch (p->nlon) {
     case 1440:
-      if (p->mlim <= 4 * 30) return launch_inv<24, 30, 1, 4>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
-      return launch_inv<24, 30, 1>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
-    case 240: return launch_inv<15, 8, 4>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
+      if (p->mlim <= 4 * 30) return launch_inv<24, 30, 1, 4>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st, pm);
+      return launch_inv<24, 30, 1>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st, pm);
+    case 240: return launch_inv<15, 8, 4>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st, pm);
     case 2880:
-      if (p->mlim <= 8 * 30) return launch_inv<48, 30, 1, 8, 16, true>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
-      return launch_inv<48, 30, 1, 0, 16, true>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st);
+      if (p->mlim <= 8 * 30) return launch_inv<48, 30, 1, 8, 16, true>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st, pm);
+      return launch_inv<48, 30, 1, 0, 16, true>(p, Yt, y, mscale, skip, out_scale, act_gelu, stats, B, C, st, pm);
     default: return record_error(MSFNO_ERR_UNSUPPORTED, "four-step FFT: unsupported nlon");
   }
 }

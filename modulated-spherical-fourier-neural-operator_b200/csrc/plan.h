@@ -9,6 +9,7 @@
 #include <utility>
 #include <vector>
 
+#include "../../include/msfno_b200.h"
 #include "fft_core.cuh"
 
 namespace msfno {
@@ -119,10 +120,21 @@ int launch_dft_fwd(msfno_plan* p, const float* x, float* Xt, const float* in_sca
                    cudaStream_t st);
 int launch_dft_inv(msfno_plan* p, const float* Yt, float* y, const float* skip, int act_flags, double* stats, int B, int C,
                    cudaStream_t st);
+// Where the lat-contiguous intermediate of a SHARDED transform lives (spatial decomposition, B = 1): order m belongs to
+// rank s with mb[s] <= m < mb[s+1], whose operand buffer buf[s] is [mb[s+1]-mb[s]][2C][pitch] over ALL latitudes (a CUDA
+// IPC mapping for s != this rank); this rank's latitudes start at column lat_lo.  world == 0: the local [mlim][2C][kpad].
+struct PeerMapDev {
+  int world;
+  int mb[MSFNO_MAX_PEERS + 1];
+  float* buf[MSFNO_MAX_PEERS];
+  int pitch;
+  int lat_lo;
+};
 int launch_rfft2d(const msfno_plan* p, const float* x, float* Xt, const float* mscale, int zero_imag,
-                  const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st);
+                  const float* in_scale, const float* in_shift, int B, int C, cudaStream_t st, const PeerMapDev* pm = nullptr);
 int launch_irfft2d(const msfno_plan* p, const float* Yt, float* y, const float* mscale, const float* skip,
-                   const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st);
+                   const float* out_scale, int act_gelu, double* stats, int B, int C, cudaStream_t st,
+                   const PeerMapDev* pm = nullptr);
 
 // persistent weight-stationary conv kernel (conv_tc.cu); *handled = 0 -> caller falls back to launch_gemm_tc
 int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long long b_rows, long long b_cols,

@@ -159,6 +159,26 @@ int msfno_fft_stage(msfno_plan* p, int inverse, int adjoint, const float* src, f
                             C, st);
 }
 
+int msfno_fft_stage_peer(msfno_plan* p, int inverse, const float* x, float* y, const msfno_peer_map* map, int C, void* stream) {
+  if (!p || !map || C < 1 || (inverse ? !y : !x) || map->world < 1 || map->world > MSFNO_MAX_PEERS || map->pitch < 1 || map->lat_lo < 0 ||
+      map->lat_lo + p->nlat > map->pitch)
+    return record_error(MSFNO_ERR_BAD_SHAPE, "fft_stage_peer: bad argument");
+  PeerMapDev pm{};
+  pm.world = map->world; pm.pitch = map->pitch; pm.lat_lo = map->lat_lo;
+  for (int s = 0; s <= map->world; ++s) pm.mb[s] = map->m_bounds[s];
+  if (pm.mb[0] != 0 || pm.mb[map->world] != p->mlim) return record_error(MSFNO_ERR_BAD_SHAPE, "fft_stage_peer: order bounds do not cover [0, mlim)");
+  for (int s = 0; s < map->world; ++s) {
+    if (pm.mb[s + 1] < pm.mb[s] || (pm.mb[s + 1] > pm.mb[s] && !map->buf[s])) return record_error(MSFNO_ERR_BAD_SHAPE, "fft_stage_peer: bad peer entry");
+    pm.buf[s] = map->buf[s];
+  }
+  // the four-step kernels only (nlon 240 / 1440 / 2880): the generic radix kernels keep the local intermediate
+  if (!fft2d_supported(p->nlon) || (reinterpret_cast<uintptr_t>(inverse ? (const void*)y : (const void*)x) & 15))
+    return record_error(MSFNO_ERR_UNSUPPORTED, "fft_stage_peer: needs the four-step FFT kernels (nlon 240 / 1440 / 2880, 16-byte aligned grid)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!inverse) return launch_rfft2d(p, x, nullptr, p->d_scale_rfft, 0, nullptr, nullptr, 1, C, st, &pm);
+  return launch_irfft2d(p, nullptr, y, p->d_scale_irfft, nullptr, nullptr, 0, nullptr, 1, C, st, &pm);
+}
+
 int msfno_legendre_stage(msfno_plan* p, int kind, const float* src, float* dst, int m_lo, int m_hi, int B, int C,
                          void* stream) {
   if (!p || !src || !dst || B < 1 || C < 1 || m_lo < 0 || m_hi > p->mlim || m_lo >= m_hi)

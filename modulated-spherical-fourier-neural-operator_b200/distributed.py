@@ -59,9 +59,14 @@ def packed_offsets(lmax, mmax):
 
 
 def split_orders(lmax, mmax, parts):
-    """Boundaries of a contiguous split of the orders [0, mlim) balanced by Legendre work sum(lmax - m)."""
+    """Boundaries of a contiguous split of the orders [0, mlim) balanced by what an order really costs its owner: one unit
+    for its share of the lat<->m exchange and of the operand traffic (every order is 2C rows of nlat latitudes, whatever
+    its degree range) plus one unit per 128-row tile of its Legendre GEMM (lmax - m rows).  Balancing by flops
+    sum(lmax - m) alone gave the last of 8 ranks 85 of 240 orders: 35 % of the spectrum arrived through ONE rank's NVLink
+    port and its GEMMs ran 85 tiles against 30 on rank 0 (profiles/r02_sharded_sht_n8_peer.json: exchange phases
+    0.47 / 0.62 ms of a 2.1 ms round trip)."""
     mlim = min(lmax, mmax)
-    cost = [lmax - m for m in range(mlim)]
+    cost = [1 + (lmax - m + 127) // 128 for m in range(mlim)]
     total = sum(cost)
     bounds, acc, nxt = [0], 0, 1
     for m in range(mlim):
@@ -151,9 +156,10 @@ class CudaStages:
         _lib.check(_lib.lib.msfno_lat_segments(1 if gather else 0, flat.data_ptr(), full.data_ptr(), rows, full.shape[-1], self.nlat, n,
                                                lo, cnt, self._st()), "lat_segments")
 
-    def legendre_inv(self, cm, m_lo, m_hi):
+    def legendre_inv(self, cm, m_lo, m_hi, out=None):
         B, C = cm.shape[0], cm.shape[1] // 2
-        Yt = torch.empty((B, m_hi - m_lo, 2 * C, self.pad(self.nlat)), dtype=torch.float32, device=cm.device)
+        Yt = out if out is not None else torch.empty((B, m_hi - m_lo, 2 * C, self.pad(self.nlat)), dtype=torch.float32,
+                                                     device=cm.device)
         _lib.check(_lib.lib.msfno_legendre_stage(self.leg_s.h, 2, cm.data_ptr(), Yt.data_ptr(), m_lo, m_hi, B, C, self._st()),
                    "legendre_stage")
         return Yt
@@ -164,6 +170,11 @@ class _DevArray:
 
     def __init__(self, ptr, n, typestr="<f4"):
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class _PeerMap(ctypes.Structure):        # mirrors msfno_peer_map (include/msfno_b200.h)
+    _fields_ = [("world", ctypes.c_int), ("m_bounds", ctypes.c_int * 17), ("buf", ctypes.c_void_p * 16), ("pitch", ctypes.c_int),
+                ("lat_lo", ctypes.c_int)]
 
 
 class _PeerBlock(ctypes.Structure):      # mirrors msfno_peer_block (include/msfno_b200.h)
@@ -177,10 +188,14 @@ class PeerExchange:
          A [mloc][2C][pad(nlat)]     operand of ITS Legendre analysis -- filled by all ranks' longitude stages
          Bf [mlim][2C][pad(nlat_loc)] operand of ITS inverse longitude stage -- filled by all ranks' Legendre syntheses
     both cudaMalloc'ed, exported through CUDA IPC and mapped by every peer (one process per GPU, one node).  A direction
-    is barrier -> ONE block-copy launch -> barrier on the caller's stream; no library collective, no staging copy."""
+    is barrier -> ONE block-copy launch -> barrier on the caller's stream; no library collective, no staging copy.
+    fused=True goes one step further (msfno_fft_stage_peer): the forward FFT kernel's epilogue stores its row segments
+    straight into the owners' A, and the inverse FFT kernel's staging fill loads them straight from the owners' Legendre
+    synthesis output (which then lives in A as well) -- the exchange has no kernel of its own."""
 
-    def __init__(self, dsht, C, device, pad):
+    def __init__(self, dsht, C, device, pad, fused=False):
         self.d, self.C, self.device, self.group = dsht, C, device, dsht.group
+        self.fused = bool(fused)
         self.world, self.rank = dsht.world, dsht.rank
         if self.world > 16:
             raise ValueError("PeerExchange supports up to 16 ranks (MSFNO_MAX_PEERS)")
@@ -230,7 +245,38 @@ class PeerExchange:
         self.A_view = self.A.view(1, max(mloc, 1), C2, self.padN)[:, :mloc]
         self.B_view = self.Bf.view(1, d.mlim, C2, padl)
         self.mloc = mloc
+        pm = _PeerMap()
+        pm.world, pm.pitch, pm.lat_lo = self.world, self.padN, d.lat_lo
+        for s_ in range(self.world + 1):
+            pm.m_bounds[s_] = d.m_bounds[s_]
+        for s_ in range(self.world):
+            pm.buf[s_] = self.maps[s_][0]
+        self.peer_map = pm
         dist.barrier(group=self.group)      # every mapping exists before anyone stores through one
+
+    # ---- fused engine: the exchange inside the FFT kernels -------------------------------------------------------------
+    def fft_fwd_into_peers(self, stages, x_loc):
+        """x_loc [1][C][nlat_loc][nlon] -> view of A (all latitudes of this rank's orders), filled by every rank's FFT kernel."""
+        st = torch.cuda.current_stream().cuda_stream
+        self._barrier(st)                    # every peer has finished with its A (analysis / inverse-FFT loads of the last call)
+        _lib.check(_lib.lib.msfno_fft_stage_peer(stages.fft_plan.h, 0, x_loc.data_ptr(), None, ctypes.byref(self.peer_map), self.C, st),
+                   "fft_stage_peer")
+        self._barrier(st)                    # every peer's stores into MY A are visible
+        return self.A_view
+
+    def synthesis_target(self):
+        """Where this rank's Legendre synthesis must write (A: the peers' inverse FFTs load from it)."""
+        self._barrier(torch.cuda.current_stream().cuda_stream)     # nobody still loads the previous contents
+        return self.A_view
+
+    def fft_inv_from_peers(self, stages, C):
+        st = torch.cuda.current_stream().cuda_stream
+        self._barrier(st)                    # every rank's synthesis output is complete and visible
+        d = self.d
+        y = torch.empty((1, C, d.nlat_loc, d.nlon), dtype=torch.float32, device=self.device)
+        _lib.check(_lib.lib.msfno_fft_stage_peer(stages.fft_plan.h, 1, None, y.data_ptr(), ctypes.byref(self.peer_map), C, st),
+                   "fft_stage_peer")
+        return y
 
     def _barrier(self, st):
         _lib.check(_lib.lib.msfno_peer_barrier(self.flag_ptrs, self.rank, self.world, self.state.data_ptr(), st), "peer_barrier")
@@ -280,9 +326,10 @@ class DistributedSHT:
 
     def __init__(self, nlat, nlon, lmax, mmax, stages_factory, group=None, peer_exchange=False):
         """peer_exchange=True (NCCL process group on one node, B = 1): the lat<->m transpose runs as direct NVLink stores
-        into the peers' operand buffers (PeerExchange) instead of all_to_all_single + pack / unpack launches."""
+        into the peers' operand buffers (PeerExchange) instead of all_to_all_single + pack / unpack launches;
+        peer_exchange="fused": those stores / loads are issued by the FFT kernels themselves (msfno_fft_stage_peer)."""
         self.group = group
-        self.use_peer, self.peer = bool(peer_exchange), None
+        self.use_peer, self.peer = (peer_exchange if peer_exchange == "fused" else bool(peer_exchange)), None
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.nlat, self.nlon, self.lmax, self.mmax = nlat, nlon, lmax, mmax
@@ -302,8 +349,12 @@ class DistributedSHT:
         if self.peer is None or self.peer.C != C:
             if self.peer is not None:
                 self.peer.close()
-            self.peer = PeerExchange(self, C, st.device, st.pad)
+            self.peer = PeerExchange(self, C, st.device, st.pad, fused=self.use_peer == "fused")
         return self.peer
+
+    def _fused(self, B, C, st):
+        """peer_exchange="fused": the exchange inside the four-step FFT kernels (nlon 240 / 1440 / 2880)."""
+        return self.use_peer == "fused" and self.nlon in (240, 1440, 2880) and self._peer(B, C, st) is not None
 
     def _single_exchange(self, B, st):
         """all_to_all_single + one pack / unpack launch (NCCL, B = 1, stages that provide lat_segments)."""
@@ -319,8 +370,14 @@ class DistributedSHT:
     def forward_packed(self, x_loc):
         st = self.stages
         B, C = x_loc.shape[0], x_loc.shape[1]
-        Xt_loc = st.fft_fwd(x_loc.contiguous())                       # [B, mlim, 2C, pad(nlat_loc)]
         mloc = self.m_hi - self.m_lo
+        if self.world > 1 and self._fused(B, C, st):
+            Xt = self.peer.fft_fwd_into_peers(st, x_loc.contiguous())
+            if mloc == 0:
+                return torch.zeros((B, 0, 2 * C), dtype=x_loc.dtype, device=x_loc.device)
+            p0, p1 = self.pos_range()
+            return st.legendre_fwd(Xt, self.m_lo, self.m_hi, p1 - p0)
+        Xt_loc = st.fft_fwd(x_loc.contiguous())                       # [B, mlim, 2C, pad(nlat_loc)]
         if self.world == 1:
             Xt = Xt_loc                                               # the stage's own padded layout: nothing to move
         elif self._peer(B, C, st) is not None:
@@ -362,6 +419,11 @@ class DistributedSHT:
         st = self.stages
         B, C = cm_loc.shape[0], cm_loc.shape[1] // 2
         mloc = self.m_hi - self.m_lo
+        if self.world > 1 and self._fused(B, C, st):
+            out = self.peer.synthesis_target()
+            if mloc > 0:
+                st.legendre_inv(cm_loc.contiguous(), self.m_lo, self.m_hi, out=out)
+            return self.peer.fft_inv_from_peers(st, C)
         if mloc > 0:
             Yt = st.legendre_inv(cm_loc.contiguous(), self.m_lo, self.m_hi)  # [B, mloc, 2C, pad(nlat)]
         else:

@@ -26,9 +26,12 @@ def test_shard_members_and_bounds():
     for L, M, w in ((120, 121, 2), (120, 121, 8), (240, 241, 4), (12, 13, 3), (4, 5, 8)):
         b = D.split_orders(L, M, w)
         assert len(b) == w + 1 and b[0] == 0 and b[-1] == min(L, M) and all(x <= y for x, y in zip(b, b[1:]))
-        cost = [sum(L - m for m in range(b[r], b[r + 1])) for r in range(w)]
+        # cost of an order to its owner: exchange / operand traffic (one unit) + 128-row tiles of its Legendre GEMM
+        cost = [sum(1 + (L - m + 127) // 128 for m in range(b[r], b[r + 1])) for r in range(w)]
         if min(L, M) >= 4 * w:
-            assert max(cost) <= 1.25 * sum(cost) / w + L  # balanced by Legendre work
+            assert max(cost) <= 1.25 * sum(cost) / w + 3
+            n_orders = [b[r + 1] - b[r] for r in range(w)]
+            assert max(n_orders) <= 2 * min(n_orders)      # no rank receives a multiple of another's share of the spectrum
     poff, plen4, P = D.packed_offsets(120, 121)
     assert P == 7440 and poff[0] == 0 and poff[1] == 120 and plen4[119] == 4
 

@@ -40,19 +40,22 @@ def _worker(rank, world, port, nlat, nlon, L, M, grid, B, q):
             yr = y_ref[:, :, dsht.lat_lo:dsht.lat_hi]
             e_i = float((y_loc - yr).norm() / yr.norm())
             if B == 1:
-                # the same transform with the lat<->m transpose as direct NVLink stores into the peers' buffers
-                # (PeerExchange); twice, so that buffer re-use across calls goes through the flag barriers
-                dp = D.DistributedSHT(nlat, nlon, L, M, lambda nloc: D.CudaStages(nlat, nloc, nlon, L, M, sht.weights, isht.pct, dev),
-                                      peer_exchange=True)
-                for it in range(2):
-                    xs = x * (1.0 + it)
-                    pm2 = dp.gather_pm(dp.forward_packed(xs[:, :, dp.lat_lo:dp.lat_hi].contiguous()))
-                    e_f = max(e_f, float((pm2 - pm_ref * (1.0 + it)).norm() / pm_ref.norm()))
-                    y2 = dp.inverse_packed((cm_ref * (1.0 + it))[:, :, p0:p1].contiguous())
-                    e_i = max(e_i, float((y2 - yr * (1.0 + it)).norm() / yr.norm()))
-                assert dp.peer is not None
-                dp.peer.check()
-                dp.peer.close()
+                # the same transform with the lat<->m transpose over NVLink peer memory (PeerExchange): True = one block-copy
+                # launch per direction, "fused" = the stores / loads are issued by the FFT kernels themselves; each twice, so
+                # that buffer re-use across calls goes through the flag barriers
+                for engine in (True, "fused"):
+                    dp = D.DistributedSHT(nlat, nlon, L, M,
+                                          lambda nloc: D.CudaStages(nlat, nloc, nlon, L, M, sht.weights, isht.pct, dev),
+                                          peer_exchange=engine)
+                    for it in range(2):
+                        xs = x * (1.0 + it)
+                        pm2 = dp.gather_pm(dp.forward_packed(xs[:, :, dp.lat_lo:dp.lat_hi].contiguous()))
+                        e_f = max(e_f, float((pm2 - pm_ref * (1.0 + it)).norm() / pm_ref.norm()))
+                        y2 = dp.inverse_packed((cm_ref * (1.0 + it))[:, :, p0:p1].contiguous())
+                        e_i = max(e_i, float((y2 - yr * (1.0 + it)).norm() / yr.norm()))
+                    assert dp.peer is not None and dp.peer.fused == (engine == "fused")
+                    dp.peer.check()
+                    dp.peer.close()
         torch.cuda.synchronize()
         q.put((rank, e_f, e_i))
     finally:

@@ -42,7 +42,7 @@ def run(dev, rank, world, max_over_ranks, sync_all, steps=10, nlat=1441, nlon=28
     dsht = D.DistributedSHT(nlat, nlon, L, M, stages, peer_exchange=False)
     x = torch.randn(B, C, dsht.nlat_loc, nlon, device=dev)
     ms_nccl, y = timed(dsht)
-    ms, engine, peer_err, ms_graph, graph_same, phases = ms_nccl, "nccl", None, None, None, None
+    ms, engine, peer_err, ms_graph, graph_same, phases, fused, ms_peer, same = ms_nccl, "nccl", None, None, None, None, None, None, None
     if world > 1 and B == 1:
         try:
             dp = D.DistributedSHT(nlat, nlon, L, M, stages, peer_exchange=True)
@@ -97,6 +97,34 @@ def run(dev, rank, world, max_over_ranks, sync_all, steps=10, nlat=1441, nlon=28
                 ms_graph, graph_same = None, repr(e)
             dp.peer.close()
             ms, engine = ms_peer, "peer"
+            # third engine: the exchange fused into the FFT kernels (msfno_fft_stage_peer)
+            try:
+                df = D.DistributedSHT(nlat, nlon, L, M, stages, peer_exchange="fused")
+                ms_fused, y3 = timed(df)
+                df.peer.check()
+                fused_same = bool(torch.equal(y, y3))
+                with torch.no_grad():
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        roundtrips(df, 1)
+                    for _ in range(2):
+                        g.replay()
+                    sync_all()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for _ in range(steps):
+                        g.replay()
+                    e1.record()
+                    sync_all()
+                ms_fused_graph = max_over_ranks(e0.elapsed_time(e1) / steps)
+                df.peer.check()
+                del g
+                df.peer.close()
+                fused = {"ms_per_roundtrip": ms_fused, "ms_per_roundtrip_cuda_graph": ms_fused_graph, "bit_identical_to_nccl": fused_same}
+                if ms_fused < ms:
+                    ms, engine = ms_fused, "fused"
+            except Exception as e:
+                fused = {"error": repr(e)}
         except Exception as e:   # no IPC / no P2P between the ranks: the NCCL engine is the result
             peer_err = repr(e)
     gb = 2 * (4 * B * C * nlat * nlon + 8 * B * C * L * M + 4 * M * L * nlat) / 1e9
@@ -106,7 +134,8 @@ def run(dev, rank, world, max_over_ranks, sync_all, steps=10, nlat=1441, nlon=28
     wire = payload * (world - 1) / world
     return {"config": "configs[4] (A): sharded SHT + ISHT round trip, %d x %d, C = %d, lmax = %d" % (nlat, nlon, C, L), "n_gpus": world,
             "exchange": engine, "ms_per_roundtrip": ms, "ms_per_roundtrip_nccl_exchange": ms_nccl,
-            "peer_result_bit_identical_to_nccl": same if engine == "peer" else None, "peer_exchange_error": peer_err,
+            "ms_per_roundtrip_peer_copy_exchange": ms_peer, "fused_into_fft_kernels": fused,
+            "peer_result_bit_identical_to_nccl": same if ms_peer is not None else None, "peer_exchange_error": peer_err,
             "ms_per_roundtrip_cuda_graph": ms_graph, "graph_result_bit_identical": graph_same,
             "phases_ms_max_over_ranks": phases,
             "algorithmic_GB": gb, "aggregate_GBps": gb / ms * 1e3,
