@@ -194,9 +194,10 @@ int msfno_set_fp32_engine(int engine) {
 int msfno_get_fp32_engine(void) { return g_fp32_engine.load(std::memory_order_relaxed); }
 
 const char* msfno_build_info(void) {
-  return "{\"arch\": \"sm_100a\", \"abi\": 3, \"tiers\": [\"fp32 (3xTF32 on tcgen05, or FFMA)\", \"tf32\"], \"fft\": \"four-step in-register (fp32 tier)\", "
-         "\"tensor_core\": [\"tcgen05 tf32 gemm (cta_group::1 and ::2)\", \"dft gemm\", \"parity-split persistent inverse dft (tma stores)\", \"fused mlp (A operand in TMEM)\", \"1x1 conv\"], "
-         "\"streams\": [\"specconv tma ring\"]}";
+  return "{\"arch\": \"sm_100a\", \"abi\": 4, \"tiers\": [\"fp32 (3xTF32 on tcgen05, or FFMA)\", \"tf32\"], \"fft\": \"four-step in-register (fp32 tier; nlon 240 / 1440 / 2880)\", "
+         "\"tensor_core\": [\"tcgen05 tf32 gemm (cta_group::1 and ::2)\", \"3xTF32 gemm (two issuing threads, A operand in TMEM, small terms in a persistent accumulator)\", \"dft gemm\", "
+         "\"parity-split persistent inverse dft (tma stores)\", \"fused mlp (A operand in TMEM)\", \"1x1 conv\"], "
+         "\"streams\": [\"specconv tma ring\"], \"multi_gpu\": [\"cuda ipc peer buffers\", \"nvlink block copy\", \"exchange fused into the fft kernels\", \"flag barrier\"]}";
 }
 
 int msfno_plan_create(msfno_plan** out, int nlat, int nlon, int lmax, int mmax) {
