@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "../../include/msfno_b200.h"
 
 namespace msfno {
@@ -23,6 +25,28 @@ inline int dbg_env_int(const char* name, int dflt) { const char* e = getenv(name
 constexpr bool dbg_env(const char*) { return false; }
 constexpr int dbg_env_int(const char*, int dflt) { return dflt; }
 #endif
+
+// One-time set-up that is PER DEVICE (cudaFuncSetAttribute applies to the current device's copy of a kernel): a process that
+// drives several GPUs -- a module on cuda:1 while cuda:0 is current, tests/test_gpu_serving.py -- must opt every device in,
+// which a plain std::call_once does not.
+struct PerDeviceOnce {
+  std::mutex mu;
+  bool done[64] = {};
+  cudaError_t err[64] = {};
+  template <typename F>
+  cudaError_t run(F&& f) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64) return f();
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done[dev]) {
+      err[dev] = f();
+      done[dev] = true;
+    }
+    return err[dev];
+  }
+};
 
 int record_cuda_error(cudaError_t e, const char* file, int line);
 int record_error(int code, const char* msg);

@@ -273,12 +273,8 @@ int launch_conv_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     tmA2 = tmA;   // stream_all: pair 2 is the only pair and uses the same buffers
     tmB2 = tmB;
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  });
-  MSFNO_CUDA_OK(attr_err);
+  static PerDeviceOnce once;
+  MSFNO_CUDA_OK(once.run([] { return cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); }));
   ConvTcParams p{};
   p.D = g.D; p.lda = g.lda; p.lda2 = g.A2 ? g.lda2 : g.lda; p.ldb = g.ldb; p.ldb2 = g.A2 ? g.ldb2 : g.ldb; p.ldd = g.ldd;
   p.sa = g.sa; p.sb = g.sb; p.sb2 = g.A2 ? g.sb2 : g.sb; p.sd = g.sd;

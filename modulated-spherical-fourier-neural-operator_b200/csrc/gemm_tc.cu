@@ -933,18 +933,16 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
       tmA2 = tmA;
       tmB2 = tmB;
     }
-    static std::once_flag once3;
-    static cudaError_t attr_err3 = cudaSuccess;
-    std::call_once(once3, [] {
+    static PerDeviceOnce once3;
+    MSFNO_CUDA_OK(once3.run([] {
       cudaError_t e = cudaSuccess;
       auto set = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
       set(opt_in_smem(gemm_tc3_kernel<false, false>, Tc3Cfg<false>::SMEM_BYTES));
       set(opt_in_smem(gemm_tc3_kernel<false, true>, Tc3Cfg<false>::SMEM_BYTES));
       set(opt_in_smem(gemm_tc3_kernel<true, false>, Tc3Cfg<true>::SMEM_BYTES));
       set(opt_in_smem(gemm_tc3_kernel<true, true>, Tc3Cfg<true>::SMEM_BYTES));
-      attr_err3 = e;
-    });
-    MSFNO_CUDA_OK(attr_err3);
+      return e;
+    }));
     p.lda2 = g.A2 ? g.lda2 : 4; p.ldb2 = g.A2 ? g.ldb2 : 4; p.sa2 = g.sa2; p.sb2 = g.sb2; p.K2 = g.A2 ? g.K2 : 0;
     p.tilesM = (g.maxM + TC_BM - 1) / TC_BM;
     p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;
@@ -989,10 +987,8 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     if (rc) return rc;
     rc = make_map(&tmB, g.B, b_rows, b_cols, g.ldb, TC_BM);
     if (rc) return rc;
-    static std::once_flag once2;
-    static cudaError_t attr_err2 = cudaSuccess;
-    std::call_once(once2, [] { attr_err2 = opt_in_smem(gemm_tc2_kernel, TC2_SMEM_BYTES); });
-    MSFNO_CUDA_OK(attr_err2);
+    static PerDeviceOnce once2;
+    MSFNO_CUDA_OK(once2.run([] { return opt_in_smem(gemm_tc2_kernel, TC2_SMEM_BYTES); }));
     p.tilesM = (g.maxM + 255) / 256;
     p.tilesN = (g.maxN + TC2_BN - 1) / TC2_BN;
     dim3 grid(2 * p.tilesM * p.tilesN, g.ngroups);
@@ -1017,18 +1013,16 @@ int launch_gemm_tc(const GemmLaunch& g, long long a_rows, long long a_cols, long
     tmA2 = tmA;
     tmB2 = tmB;
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
+  static PerDeviceOnce once;
+  MSFNO_CUDA_OK(once.run([] {
     cudaError_t e = cudaSuccess;
     auto set = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
     set(opt_in_smem(gemm_tc_kernel<false, false>, TC_SMEM_BYTES));
     set(opt_in_smem(gemm_tc_kernel<false, true>, TC_SMEM_BYTES));
     set(opt_in_smem(gemm_tc_kernel<true, false>, TC_SMEM_BYTES));
     set(opt_in_smem(gemm_tc_kernel<true, true>, TC_SMEM_BYTES));
-    attr_err = e;
-  });
-  MSFNO_CUDA_OK(attr_err);
+    return e;
+  }));
   p.lda2 = g.A2 ? g.lda2 : 4; p.ldb2 = g.A2 ? g.ldb2 : 4; p.sa2 = g.sa2; p.sb2 = g.sb2; p.K2 = g.A2 ? g.K2 : 0;
   p.tilesM = (g.maxM + TC_BM - 1) / TC_BM;
   p.tilesN = (g.maxN + TC_BN - 1) / TC_BN;

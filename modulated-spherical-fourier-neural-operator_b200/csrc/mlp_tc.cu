@@ -457,10 +457,8 @@ extern "C" int msfno_mlp1x1_fwd(const float* x, long x_bstride, int Cin, const f
     rc = make_wmap(&tmId, d_ident, 32, 32, 32, 32);
     if (rc) return rc;
   }
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] { attr_err = cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM); });
-  MSFNO_CUDA_OK(attr_err);
+  static PerDeviceOnce once;
+  MSFNO_CUDA_OK(once.run([] { return cudaFuncSetAttribute(mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ML_SMEM); }));
   MlpTcParams p{};
   p.D = y; p.ldd = HW; p.sd = (long long)Cout * HW;
   p.b1 = b1; p.sb1 = b1_bstride; p.b2 = b2; p.sb2 = b2_bstride;

@@ -112,3 +112,41 @@ def test_host_pipeline_matches_eager():
     torch.cuda.synchronize()
     for a, b in zip(ys2, want):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("tier", ["fp32", "tf32"])
+def test_module_on_second_gpu_while_the_first_is_current(tier):
+    """A net living on cuda:1 must run (forward and backward) while cuda:0 is the CURRENT device -- the reference's
+    PyTorch modules guard the device themselves, so a drop-in has to as well (launch stream, tensor-map encoding and
+    per-device constants all follow the input tensor's device).  Needs two GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    msfno_b200.set_precision(tier)
+    try:
+        net0, d = _small_net("non-linear")
+        torch.cuda.set_device(0)
+        net1 = msfno_b200.FourierNeuralOperatorNet("cuda:1", None, **d["cfg"])
+        net1.load_state_dict(net0.state_dict(), strict=True)
+        net1 = net1.to("cuda:1").eval()
+        x0 = d["x"].cuda(0)
+        x1 = d["x"].to("cuda:1")
+        assert torch.cuda.current_device() == 0
+        with torch.no_grad():
+            y0 = net0(x0)
+            y1 = net1(x1)                      # fused inference path on the non-current device
+        assert y1.device.index == 1 and torch.equal(y0.cpu(), y1.cpu())
+        # autograd path (adjoint kernels run on autograd's worker thread of device 1)
+        for p0, p1 in zip(net0.parameters(), net1.parameters()):
+            p0.requires_grad_(True)
+            p1.requires_grad_(True)
+        g = torch.randn(y0.shape, generator=torch.Generator().manual_seed(3))
+        with msfno_b200.precision.library_scope():
+            net0(x0).backward(g.cuda(0))
+            net1(x1).backward(g.to("cuda:1"))
+        assert torch.cuda.current_device() == 0
+        for (n, p0), p1 in zip(net0.named_parameters(), net1.parameters()):
+            if p0.grad is not None:
+                assert p1.grad is not None and rel_l2(p1.grad.cpu(), p0.grad.cpu()) < 1e-6, n
+    finally:
+        msfno_b200.set_precision("fp32")
+        torch.cuda.set_device(0)
