@@ -90,17 +90,54 @@ class GraphedForward:
             _lib._capture_refs = None
             del self.net._decode_out
 
-    def rollout(self, x0, steps):
+    def rollout(self, x0, steps, host_out=None, every=1):
         """Autoregressive rollout x <- net(x) (reference: /root/reference MSFNO/Models/sfno/model.py:327-331).
-        Returns the state after `steps` steps (valid until the next call)."""
+        Returns the state after `steps` steps (valid until the next call).
+
+        host_out: optional sequence of (pinned) host tensors; host_out[k] receives the state after (k + 1) * every steps.
+        The reference copies every step's fields to the host synchronously before the next step starts
+        (sfno/model.py:345-370); here a step's state is snapshotted on the device (0.1 ms: the in-place graph overwrites
+        its input) and drained to the host on a side stream under the following steps, double-buffered -- the rollout runs
+        at max(step, device->host copy) instead of their sum."""
         if not hasattr(self, "inplace_graph"):
             self._capture_inplace()
         self.static_x.copy_(x0, non_blocking=True)
-        if self.inplace_graph is not None:
+        inplace = self.inplace_graph is not None
+        if host_out is None:
+            if inplace:
+                for _ in range(steps):
+                    self.inplace_graph.replay()
+                return self.static_x
             for _ in range(steps):
+                self.graph.replay()
+                self.static_x.copy_(self.static_y, non_blocking=True)
+            return self.static_y
+        main = torch.cuda.current_stream()
+        if not hasattr(self, "_snap"):
+            self._snap = [torch.empty_like(self.static_x) for _ in range(2)]
+            self._s_out = torch.cuda.Stream()
+            self._ev_out = [torch.cuda.Event() for _ in range(2)]
+        k = 0
+        for t in range(1, steps + 1):
+            if inplace:
                 self.inplace_graph.replay()
-            return self.static_x
-        for _ in range(steps):
-            self.graph.replay()
-            self.static_x.copy_(self.static_y, non_blocking=True)
-        return self.static_y
+                state = self.static_x
+            else:
+                self.graph.replay()
+                state = self.static_y
+            if t % every == 0 and k < len(host_out):
+                j = k % 2
+                if k >= 2:
+                    main.wait_event(self._ev_out[j])           # staging buffer j has been drained to the host
+                self._snap[j].copy_(state, non_blocking=True)   # the next step may now overwrite the state
+                ev = torch.cuda.Event()
+                ev.record(main)
+                self._s_out.wait_event(ev)
+                with torch.cuda.stream(self._s_out):
+                    host_out[k].copy_(self._snap[j], non_blocking=True)
+                    self._ev_out[j].record(self._s_out)
+                k += 1
+            if not inplace:
+                self.static_x.copy_(self.static_y, non_blocking=True)
+        main.wait_stream(self._s_out)
+        return self.static_x if inplace else self.static_y

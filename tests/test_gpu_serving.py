@@ -150,3 +150,35 @@ def test_module_on_second_gpu_while_the_first_is_current(tier):
     finally:
         msfno_b200.set_precision("fp32")
         torch.cuda.set_device(0)
+
+
+@pytest.mark.parametrize("tier", ["fp32", "tf32"])
+def test_rollout_with_per_step_host_output(tier):
+    """GraphedForward.rollout(host_out=...) (N4: the reference's running() loop copies every step to the host,
+    sfno/model.py:345-370): every saved step must equal the eager iterate, whichever graph (in-place / copying) runs."""
+    msfno_b200.set_precision(tier)
+    try:
+        net, d = _small_net("non-linear")
+        if d["cfg"]["in_chans"] != d["cfg"]["out_chans"]:
+            pytest.skip("rollout needs in_chans == out_chans")
+        x = d["x"].cuda()
+        steps, every = 6, 2
+        with torch.no_grad():
+            want, cur = [], x
+            for t in range(1, steps + 1):
+                cur = net(cur)
+                if t % every == 0:
+                    want.append(cur.clone())
+        g = msfno_b200.GraphedForward(net, x)
+        host = [torch.empty(x.shape, dtype=x.dtype).pin_memory() for _ in range(steps // every)]
+        last = g.rollout(x, steps, host_out=host, every=every)
+        torch.cuda.synchronize()
+        assert torch.equal(last.cpu(), want[-1].cpu())
+        for h, w in zip(host, want):
+            assert torch.equal(h, w.cpu())
+        # and again (the staging buffers and events are re-used)
+        last = g.rollout(x, steps, host_out=host, every=every)
+        torch.cuda.synchronize()
+        assert all(torch.equal(h, w.cpu()) for h, w in zip(host, want))
+    finally:
+        msfno_b200.set_precision("fp32")

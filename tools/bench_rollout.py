@@ -39,10 +39,24 @@ def run(dev, rank, world, max_over_ranks, sync_all, members=8, batch=1, steps=11
         ms = max_over_ranks(e0.elapsed_time(e1))
         finite = bool(torch.isfinite(final).all())
         total = world * members * steps
+        # the same rollout with EVERY step's fields copied to pinned host memory (what the reference's running() loop does,
+        # sfno/model.py:345-370), for one batch of members: device-side snapshot + double-buffered D2H under the next steps
+        host = [torch.empty(ens[:batch].shape, dtype=ens.dtype).pin_memory() for _ in range(steps)]
+        gf.rollout(ens[:batch], 4, host_out=host[:4])
+        sync_all()
+        e0.record()
+        gf.rollout(ens[:batch], steps, host_out=host)
+        e1.record()
+        sync_all()
+        ms_host = max_over_ranks(e0.elapsed_time(e1))
+        d2h_bytes = host[0].numel() * 4
         return {"metric": "sfno_rollout_member_steps_per_sec_721x1440x73", "value": total / (ms * 1e-3), "unit": "member-steps/s",
                 "n_gpus": world, "members_per_gpu": members, "members_total": world * members, "batch": batch,
                 "steps_per_member": steps, "ms_per_member_step": ms / (members * steps),
                 "rollout_seconds_per_member": ms * 1e-3 / members, "wall_ms": ms, "scaling": "weak", "dtype": precision,
+                "with_every_step_copied_to_host": {"ms_per_member_step": ms_host / (batch * steps), "d2h_bytes_per_step": d2h_bytes,
+                                                   "d2h_GBps_per_gpu": d2h_bytes * steps / (ms_host * 1e-3) / 1e9,
+                                                   "member_steps_per_sec": world * batch * steps / (ms_host * 1e-3)},
                 "data": "synthetic (random-init weights: the iterated map is not a forecast, only its cost is meaningful)",
                 "output_finite_this_rank": finite,
                 "config": {"workload": "configs[3]: 112-step autoregressive rollout, ensemble members sharded across GPUs, "
