@@ -469,8 +469,10 @@ def run_ours(args):
         del other["net"], other["eager"]
         torch.cuda.empty_cache()
 
+    # the configs that shard / communicate (config 5 sharded transform, config 3 DDP step, config 4 ensemble rollout): timed
+    # in the same run at every N -- at N = 1 too, so that a 1 -> 8 scaling run carries its own single-GPU baselines
     multi = None
-    if world > 1 and not args.no_multi_gpu_extras:
+    if not args.no_multi_gpu_extras and args.workload == "sfno12_nonlinear":
         multi = multi_gpu_extras(args, dev, rank, world, max_over_ranks, sync_all)
 
     if world > 1:
@@ -535,7 +537,7 @@ def run_ours(args):
 
 
 def multi_gpu_extras(args, dev, rank, world, max_over_ranks, sync_all):
-    """N > 1 only: the two paths that really communicate, timed in the same run (device time, max over ranks).
+    """The paths that shard or communicate, timed in the same run at every N (device time, max over ranks).
     sharded_sht: BASELINE configs[4] (A): 1441 x 2880, 256 channels, lmax 240 -- latitude-sharded FFT, all-to-all
                  lat<->m over NVLink, order-sharded Legendre, and back.
     ddp_train:   BASELINE configs[2]: MSFNO fwd + bwd + Adam on the FiLM head, per-rank batch 8, film_layers 1,
@@ -543,13 +545,30 @@ def multi_gpu_extras(args, dev, rank, world, max_over_ranks, sync_all):
     ensemble_rollout: BASELINE configs[3]: 28-day (112-step) autoregressive rollout, 8 members per GPU (64 on 8 GPUs),
                  members sharded across ranks, no data-path collective."""
     import torch
+    import torch.distributed as dist
     out = {}
+    own_group = False
     try:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_sharded_sht
+        if world == 1 and not dist.is_initialized():
+            # the sharded transform talks to torch.distributed even with one rank: a private single-rank group
+            import socket
+            s = socket.socket()
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+            s.close()
+            dist.init_process_group("nccl", init_method="tcp://127.0.0.1:%d" % port, rank=0, world_size=1, device_id=dev)
+            own_group = True
         out["sharded_sht"] = bench_sharded_sht.run(dev, rank, world, max_over_ranks, sync_all, steps=max(3, min(args.steps, 10)))
     except Exception as e:
         out["sharded_sht"] = {"error": repr(e)}
+    finally:
+        if own_group:
+            try:
+                dist.destroy_process_group()
+            except Exception:
+                pass
     torch.cuda.empty_cache()
     try:
         import bench_train_step
