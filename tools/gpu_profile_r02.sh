@@ -3,9 +3,9 @@
 # 2880-point FFT kernels and of the fp32 / tf32 sharded-transform stages.  Every profiled command first runs without ncu.
 mkdir -p gpurun_out
 for t in fp32 tf32; do
-  python bench.py --one-tier --precision $t --no-cpu-baseline --no-graph --steps 2 --warmup 3 > /dev/null 2>&1 || exit 1
+  python bench.py --one-tier --precision $t --no-cpu-baseline --no-multi-gpu-extras --no-graph --steps 2 --warmup 3 > /dev/null 2>&1 || exit 1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/r02_launches_bench_${t}_v2.csv \
-    python bench.py --one-tier --precision $t --no-cpu-baseline --no-graph --steps 2 --warmup 3 > gpurun_out/ncu_$t.log 2>&1
+    python bench.py --one-tier --precision $t --no-cpu-baseline --no-multi-gpu-extras --no-graph --steps 2 --warmup 3 > gpurun_out/ncu_$t.log 2>&1
   python tools/launch_shares.py gpurun_out/r02_launches_bench_${t}_v2.csv > gpurun_out/r02_launch_shares_${t}_v2.txt 2>&1
   head -12 gpurun_out/r02_launch_shares_${t}_v2.txt
 done
